@@ -1,0 +1,173 @@
+/*
+ * eon_kzg.h — C ABI of the B200-native BN254 KZG hot path (libeon_kzg.so, sm_100a).
+ *
+ * Drop-in boundary for the reference's plugin surface (Lolazyx/plonky3-eon):
+ *   p3-dft   TwoAdicSubgroupDft<Fr>      dft/src/traits.rs:27-507
+ *   p3-bn254 G1::multi_exp               bn254/src/curve.rs:158-180
+ *   p3-kzg   KzgPcs (Pcs<Fr, _>)          kzg/src/pcs.rs:143-335
+ *            commit_column / quotient     kzg/src/util.rs:37-40,100-111
+ *            init_srs_unsafe              kzg/src/params.rs:123-139
+ *
+ * Wire formats (identical to the reference's in-memory layout, so Rust can pass
+ * `values.as_ptr() as *const u64` directly):
+ *   Fr      4 x u64 little-endian, Montgomery form (a * 2^256 mod r), canonical (< r)
+ *           — `Fr { value: [u64; 4] }`, bn254/src/field.rs:96-105.
+ *   matrix  row-major, `height x width` Fr, row = width * 32 contiguous bytes
+ *           — RowMajorMatrix<Fr>, matrix/src/dense.rs:24-37.
+ *   G1      affine, 8 x u64: [x: 4 x u64][y: 4 x u64], Montgomery Fq (R = 2^256),
+ *           identity = all zero (halo2curves G1Affine::identity()).
+ *
+ * All functions return EON_OK (0) or a negative error code; none aborts or unwinds.
+ * `eon_last_error(ctx)` gives a human-readable message for the last failure on that ctx.
+ * There is NO CPU fallback: every entry point fails with EON_ERR_CUDA if no sm_100 device
+ * is usable.
+ *
+ * Pointer arguments named `h_*` are host pointers; `d_*` are device pointers on the
+ * context's device (from eon_dev_alloc or any CUDA allocation, e.g. a torch tensor).
+ */
+#ifndef EON_KZG_H
+#define EON_KZG_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct eon_ctx eon_ctx;
+typedef uint64_t eon_handle; /* opaque id of device-resident prover data (0 = invalid) */
+
+enum {
+  EON_OK = 0,
+  EON_ERR_BAD_ARG = -1,      /* null pointer, bad shape (e.g. height not a power of two:
+                                the reference panics in log2_strict_usize, util/src/lib.rs:39) */
+  EON_ERR_SRS_TOO_SHORT = -2,/* KzgError::DegreeTooLarge, kzg/src/params.rs:164-173 */
+  EON_ERR_CUDA = -3,         /* CUDA runtime failure / no device */
+  EON_ERR_OOM = -4,          /* device allocation failed */
+  EON_ERR_BAD_HANDLE = -5,
+  EON_ERR_TWO_ADICITY = -6   /* transform size exceeds 2^28 (Fr::TWO_ADICITY, field.rs:564) */
+};
+
+/* ---- context ------------------------------------------------------------------------- */
+/* One context per GPU.  `stream` is a cudaStream_t (NULL = the legacy default stream); every
+ * kernel of the context is launched on it, so callers can bracket calls with their own
+ * events (e.g. torch.cuda.current_stream().cuda_stream).
+ * Replaces the implicit "process-global Radix2Dit / KzgPcs state" of the reference
+ * (twiddle caches dft/src/radix_2_dit.rs:33-58; SRS kzg/src/params.rs:57-77). */
+int eon_ctx_create(int device, void* stream, eon_ctx** out);
+void eon_ctx_destroy(eon_ctx* ctx);
+const char* eon_last_error(const eon_ctx* ctx);
+int eon_ctx_sync(eon_ctx* ctx);
+/* number of CUDA kernels this context has launched so far (for bench.py "gpu_launches") */
+uint64_t eon_ctx_launch_count(const eon_ctx* ctx);
+/* library build tag, e.g. "eon_kzg sm_100a" */
+const char* eon_version(void);
+
+/* ---- device memory helpers (plain cudaMalloc / cudaMemcpyAsync on the ctx stream) -------- */
+int eon_dev_alloc(eon_ctx* ctx, size_t bytes, void** d_out);
+int eon_dev_free(eon_ctx* ctx, void* d_ptr);
+int eon_h2d(eon_ctx* ctx, void* d_dst, const void* h_src, size_t bytes);
+int eon_d2h(eon_ctx* ctx, void* h_dst, const void* d_src, size_t bytes);
+
+/* ---- TwoAdicSubgroupDft<Fr> (dft/src/traits.rs) --------------------------------------------
+ * All matrices natural row order in and out (what the trait's logical view is).
+ * `shift` = 4 x u64 Montgomery Fr, must be non-zero.  height = 1 << log_h.                  */
+
+/* dft_batch (traits.rs:61; semantics dft/src/naive.rs:15-31).  d_out may not alias d_in. */
+int eon_dft_batch_dev(eon_ctx* ctx, const uint64_t* d_in, uint64_t* d_out, unsigned log_h, size_t width);
+/* coset_dft_batch (traits.rs:83-91) */
+int eon_coset_dft_batch_dev(eon_ctx* ctx, const uint64_t* d_in, uint64_t* d_out, unsigned log_h, size_t width,
+                            const uint64_t shift[4]);
+/* idft_batch (traits.rs:111-122) */
+int eon_idft_batch_dev(eon_ctx* ctx, const uint64_t* d_in, uint64_t* d_out, unsigned log_h, size_t width);
+/* coset_idft_batch (traits.rs:144-153) */
+int eon_coset_idft_batch_dev(eon_ctx* ctx, const uint64_t* d_in, uint64_t* d_out, unsigned log_h, size_t width,
+                             const uint64_t shift[4]);
+/* coset_lde_batch (traits.rs:226-249): d_out has (1 << (log_h + added_bits)) rows. */
+int eon_coset_lde_batch_dev(eon_ctx* ctx, const uint64_t* d_in, uint64_t* d_out, unsigned log_h, size_t width,
+                            unsigned added_bits, const uint64_t shift[4]);
+
+/* Host-buffer forms (what a Rust `impl TwoAdicSubgroupDft<Fr>` binds): copy in, run, copy out. */
+int eon_dft_batch(eon_ctx* ctx, const uint64_t* h_in, uint64_t* h_out, unsigned log_h, size_t width);
+int eon_coset_dft_batch(eon_ctx* ctx, const uint64_t* h_in, uint64_t* h_out, unsigned log_h, size_t width,
+                        const uint64_t shift[4]);
+int eon_idft_batch(eon_ctx* ctx, const uint64_t* h_in, uint64_t* h_out, unsigned log_h, size_t width);
+int eon_coset_idft_batch(eon_ctx* ctx, const uint64_t* h_in, uint64_t* h_out, unsigned log_h, size_t width,
+                         const uint64_t shift[4]);
+int eon_coset_lde_batch(eon_ctx* ctx, const uint64_t* h_in, uint64_t* h_out, unsigned log_h, size_t width,
+                        unsigned added_bits, const uint64_t shift[4]);
+
+/* ---- SRS (kzg/src/params.rs) ------------------------------------------------------------- */
+/* Upload g1_powers as n affine points (8 x u64 each).  Replaces the per-call `to_affine` of
+ * bn254/src/curve.rs:170: points are normalised once by the caller and stay resident. */
+int eon_srs_load_affine(eon_ctx* ctx, const uint64_t* h_xy, size_t n);
+/* init_srs_unsafe (params.rs:123-139), G1 part: g1_powers[i] = alpha^i * G for i < n, generated
+ * on the device.  alpha: Montgomery Fr. */
+int eon_srs_generate_unsafe(eon_ctx* ctx, const uint64_t alpha[4], size_t n);
+/* number of G1 powers resident (max_degree + 1), 0 if none */
+size_t eon_srs_size(const eon_ctx* ctx);
+/* copy SRS points [first, first + n) back to the host as affine wire points */
+int eon_srs_read(eon_ctx* ctx, size_t first, size_t n, uint64_t* h_xy);
+
+/* ---- G1::multi_exp (bn254/src/curve.rs:158-180) -------------------------------------------
+ * out[c] = sum_{i<n} scalar[i][c] * bases[i]   for c in [0, ncols)
+ * scalars: row-major matrix with `ld` Fr per row (ld >= ncols), Montgomery form;
+ * bases: the resident SRS (points [0, n)) or an explicit affine array.
+ * n == 0 -> identity (curve.rs:165-167).  Results: ncols affine wire points (host). */
+int eon_msm_srs_dev(eon_ctx* ctx, const uint64_t* d_scalars, size_t n, size_t ncols, size_t ld, uint64_t* h_out_xy);
+int eon_msm_srs(eon_ctx* ctx, const uint64_t* h_scalars, size_t n, size_t ncols, size_t ld, uint64_t* h_out_xy);
+int eon_msm_points(eon_ctx* ctx, const uint64_t* h_points_xy, const uint64_t* h_scalars, size_t n, uint64_t* h_out_xy);
+/* MSM over the SRS slice [first, first + n) — the index-range shard of a multi-GPU MSM. */
+int eon_msm_srs_range_dev(eon_ctx* ctx, const uint64_t* d_scalars, size_t first, size_t n, size_t ncols, size_t ld,
+                          uint64_t* h_out_xy);
+/* out = sum of n affine points (combining per-GPU partial sums). */
+int eon_g1_sum(eon_ctx* ctx, const uint64_t* h_points_xy, size_t n, uint64_t* h_out_xy);
+
+/* ---- KzgPcs (kzg/src/pcs.rs) ------------------------------------------------------------- */
+/* commit (pcs.rs:223-265) for ONE matrix: coefficients = coset_idft_batch(evals, shift);
+ * commitment[c] = MSM(srs[..h], coefficients[:, c]).  The coefficient matrix stays on the
+ * device behind `*out_handle` (MatrixProverData.coeffs, pcs.rs:252-256).
+ * Fails with EON_ERR_SRS_TOO_SHORT if srs_size < h (pcs.rs:238-240). */
+int eon_kzg_commit(eon_ctx* ctx, const uint64_t* h_evals, unsigned log_h, size_t width, const uint64_t shift[4],
+                   uint64_t* h_commit_xy, eon_handle* out_handle);
+int eon_kzg_commit_dev(eon_ctx* ctx, const uint64_t* d_evals, unsigned log_h, size_t width, const uint64_t shift[4],
+                       uint64_t* h_commit_xy, eon_handle* out_handle);
+/* copy the retained coefficient matrix (natural order, h x width) to the host */
+int eon_kzg_read_coeffs(eon_ctx* ctx, eon_handle h, uint64_t* h_out);
+/* get_evaluations_on_domain (pcs.rs:267-287) on the coset shift*<omega_{2^log_size}>,
+ * natural order, (1 << log_size) x width.  Computed as zero-pad + coset NTT, which is
+ * bit-identical to the reference's Horner evaluation.  Requires 2^log_size >= h. */
+int eon_kzg_evals_on_coset(eon_ctx* ctx, eon_handle h, unsigned log_size, const uint64_t shift[4], uint64_t* h_out);
+int eon_kzg_evals_on_coset_dev(eon_ctx* ctx, eon_handle h, unsigned log_size, const uint64_t shift[4], uint64_t* d_out);
+/* open (pcs.rs:289-335) of one matrix at `npoints` points: for point p and column c
+ *   h_values[p*width + c]       = f_c(z_p)                         (Fr)
+ *   h_witness_xy[(p*width+c)*8] = commit((f_c - f_c(z_p))/(X - z_p)) (G1 affine)
+ * (quotient_and_eval, util.rs:100-111, then commit_column). */
+int eon_kzg_open(eon_ctx* ctx, eon_handle h, const uint64_t* h_points, size_t npoints, uint64_t* h_values,
+                 uint64_t* h_witness_xy);
+int eon_handle_dims(eon_ctx* ctx, eon_handle h, unsigned* log_h, size_t* width);
+int eon_handle_free(eon_ctx* ctx, eon_handle h);
+
+/* quotient_and_eval (util.rs:100-111) on a device coefficient matrix (h x width, natural):
+ * d_quot gets an h x width matrix whose rows [0, h-1) are the quotient coefficients and
+ * whose last row is zero; h_values gets the width evaluations f_c(z). */
+int eon_quotient_and_eval_dev(eon_ctx* ctx, const uint64_t* d_coeffs, size_t h, size_t width, const uint64_t z[4],
+                              uint64_t* d_quot, uint64_t* h_values);
+
+/* ---- measurement helpers ------------------------------------------------------------------- */
+/* Dependency-free integer-multiply microbenchmark: launches `iters` rounds on all SMs and
+ * returns the achieved 32-bit multiply-add rate in 1e12 ops/s (the IMAD roofline
+ * denominator; not in MEASURED_PEAKS.json).  kind: 0 = mad.lo.u32, 1 = mad.hi.u32,
+ * 2 = mad.wide.u32 (counted as 2 ops). */
+int eon_bench_imad_peak(eon_ctx* ctx, int kind, double* out_tops);
+/* Montgomery-product throughput (independent chains), in 1e9 modmul/s.  field: 0 Fr, 1 Fq. */
+int eon_bench_modmul(eon_ctx* ctx, int field, double* out_gmuls);
+/* per-phase device time (ms) of the last MSM / NTT call on this ctx; names via eon_phase_name */
+int eon_last_phase_ms(eon_ctx* ctx, int phase, float* out_ms);
+const char* eon_phase_name(int phase);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EON_KZG_H */

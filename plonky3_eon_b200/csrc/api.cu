@@ -1,0 +1,601 @@
+// extern "C" entry points of libeon_kzg (see include/eon_kzg.h for the contract and the
+// reference file:line each function replaces).
+#include "common.cuh"
+
+using namespace eon;
+
+namespace {
+
+struct Lock {
+  std::unique_lock<std::mutex> l;
+  explicit Lock(eon_ctx* c) : l(c->mu) {}
+};
+
+int check_shift(eon_ctx* ctx, const uint64_t shift[4], Fr* out) {
+  if (!shift) return fail(ctx, EON_ERR_BAD_ARG, "shift is null");
+  if (!fr_wire_is_canonical(shift)) return fail(ctx, EON_ERR_BAD_ARG, "shift is not a canonical Fr (>= modulus)");
+  *out = fr_from_wire(shift);
+  // TwoAdicMultiplicativeCoset::new rejects a zero shift (field/src/coset.rs:77-86)
+  if (out->is_zero()) return fail(ctx, EON_ERR_BAD_ARG, "shift must be non-zero");
+  return EON_OK;
+}
+
+int set_device(eon_ctx* ctx) {
+  EON_CUDA(ctx, cudaSetDevice(ctx->device));
+  return EON_OK;
+}
+
+size_t mat_bytes(unsigned log_h, size_t width) { return (((size_t)1) << log_h) * width * sizeof(Fr); }
+
+// host-buffer wrapper: H2D into scratch A, run f(d_in, d_out), D2H from scratch B
+template <class F>
+int host_io(eon_ctx* ctx, const uint64_t* h_in, size_t in_bytes, uint64_t* h_out, size_t out_bytes, F f) {
+  if ((in_bytes && !h_in) || (out_bytes && !h_out)) return fail(ctx, EON_ERR_BAD_ARG, "null host buffer");
+  void *d_in = nullptr, *d_out = nullptr;
+  EON_TRY(scratch_get(ctx, SC_IO_A, in_bytes + 32, &d_in));
+  EON_TRY(scratch_get(ctx, SC_IO_B, out_bytes + 32, &d_out));
+  if (in_bytes) EON_CUDA(ctx, cudaMemcpyAsync(d_in, h_in, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
+  EON_TRY(f((const Fr*)d_in, (Fr*)d_out));
+  if (out_bytes) EON_CUDA(ctx, cudaMemcpyAsync(h_out, d_out, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  EON_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return EON_OK;
+}
+
+int check_dims(eon_ctx* ctx, unsigned log_h, size_t width, unsigned added = 0) {
+  if (log_h + added > 28) return fail(ctx, EON_ERR_TWO_ADICITY, "transform size exceeds 2^28 (Fr::TWO_ADICITY)");
+  if (width > 0xffffffffull) return fail(ctx, EON_ERR_BAD_ARG, "width too large");
+  return EON_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* eon_version(void) { return "eon_kzg 0.1 sm_100a"; }
+
+int eon_ctx_create(int device, void* stream, eon_ctx** out) {
+  if (!out) return EON_ERR_BAD_ARG;
+  *out = nullptr;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0 || device < 0 || device >= count) return EON_ERR_CUDA;
+  if (cudaSetDevice(device) != cudaSuccess) return EON_ERR_CUDA;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return EON_ERR_CUDA;
+  if (prop.major < 10) return EON_ERR_CUDA;  // sm_100a cubins only; no fallback path
+  eon_ctx* ctx = new eon_ctx();
+  ctx->device = device;
+  ctx->stream = (cudaStream_t)stream;
+  ctx->num_sms = prop.multiProcessorCount;
+  for (int p = 0; p < PH_COUNT; p++) {
+    cudaEventCreate(&ctx->ev[p][0]);
+    cudaEventCreate(&ctx->ev[p][1]);
+    ctx->ev_used[p] = false;
+    ctx->phase_ms[p] = 0.f;
+  }
+  *out = ctx;
+  return EON_OK;
+}
+
+void eon_ctx_destroy(eon_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  for (auto& s : ctx->scratch)
+    if (s.ptr) cudaFree(s.ptr);
+  for (auto& kv : ctx->twiddles) cudaFree(kv.second);
+  for (auto& kv : ctx->handles) cudaFree(kv.second.d_coeffs);
+  if (ctx->d_srs) cudaFree(ctx->d_srs);
+  for (int p = 0; p < PH_COUNT; p++) {
+    cudaEventDestroy(ctx->ev[p][0]);
+    cudaEventDestroy(ctx->ev[p][1]);
+  }
+  delete ctx;
+}
+
+const char* eon_last_error(const eon_ctx* ctx) { return ctx ? ctx->last_error.c_str() : "null context"; }
+
+int eon_ctx_sync(eon_ctx* ctx) {
+  if (!ctx) return EON_ERR_BAD_ARG;
+  Lock lk(ctx);
+  EON_TRY(set_device(ctx));
+  EON_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return EON_OK;
+}
+
+uint64_t eon_ctx_launch_count(const eon_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int eon_dev_alloc(eon_ctx* ctx, size_t bytes, void** d_out) {
+  if (!ctx || !d_out) return EON_ERR_BAD_ARG;
+  Lock lk(ctx);
+  EON_TRY(set_device(ctx));
+  EON_CUDA(ctx, cudaMalloc(d_out, bytes ? bytes : 1));
+  return EON_OK;
+}
+int eon_dev_free(eon_ctx* ctx, void* d_ptr) {
+  if (!ctx) return EON_ERR_BAD_ARG;
+  Lock lk(ctx);
+  EON_TRY(set_device(ctx));
+  EON_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  EON_CUDA(ctx, cudaFree(d_ptr));
+  return EON_OK;
+}
+int eon_h2d(eon_ctx* ctx, void* d_dst, const void* h_src, size_t bytes) {
+  if (!ctx) return EON_ERR_BAD_ARG;
+  Lock lk(ctx);
+  EON_TRY(set_device(ctx));
+  EON_CUDA(ctx, cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  EON_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return EON_OK;
+}
+int eon_d2h(eon_ctx* ctx, void* h_dst, const void* d_src, size_t bytes) {
+  if (!ctx) return EON_ERR_BAD_ARG;
+  Lock lk(ctx);
+  EON_TRY(set_device(ctx));
+  EON_CUDA(ctx, cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  EON_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return EON_OK;
+}
+
+// ---- DFT --------------------------------------------------------------------------------------
+static int dft_dev(eon_ctx* ctx, const uint64_t* d_in, uint64_t* d_out, unsigned log_h, size_t width, const Fr& shift) {
+  if (!d_in || !d_out) return fail(ctx, EON_ERR_BAD_ARG, "null device buffer");
+  if (d_in == d_out) return fail(ctx, EON_ERR_BAD_ARG, "in-place transform not supported: d_out aliases d_in");
+  EON_TRY(check_dims(ctx, log_h, width));
+  return ntt_forward(ctx, (const Fr*)d_in, (Fr*)d_out, log_h, 0, width, shift, LAYOUT_NATURAL);
+}
+static int idft_dev(eon_ctx* ctx, const uint64_t* d_in, uint64_t* d_out, unsigned log_h, size_t width, const Fr& shift) {
+  if (!d_in || !d_out) return fail(ctx, EON_ERR_BAD_ARG, "null device buffer");
+  if (d_in == d_out) return fail(ctx, EON_ERR_BAD_ARG, "in-place transform not supported: d_out aliases d_in");
+  EON_TRY(check_dims(ctx, log_h, width));
+  return ntt_inverse(ctx, (const Fr*)d_in, (Fr*)d_out, log_h, width, shift, LAYOUT_NATURAL);
+}
+static int lde_dev(eon_ctx* ctx, const uint64_t* d_in, uint64_t* d_out, unsigned log_h, size_t width, unsigned added,
+                   const Fr& shift) {
+  if (!d_in || !d_out) return fail(ctx, EON_ERR_BAD_ARG, "null device buffer");
+  if (d_in == d_out) return fail(ctx, EON_ERR_BAD_ARG, "in-place transform not supported: d_out aliases d_in");
+  EON_TRY(check_dims(ctx, log_h, width, added));
+  if (width == 0) return EON_OK;
+  // idft (no shift) -> coefficients in bit-reversed order -> zero-pad (replicate) + coset DFT:
+  // no permutation pass in between (cf. Radix2DFTSmallBatch, dft/src/radix_2_small_batch.rs:246-351)
+  void* tmp = nullptr;
+  EON_TRY(scratch_get(ctx, SC_NTT_TMP, mat_bytes(log_h, width), &tmp));
+  EON_TRY(ntt_inverse(ctx, (const Fr*)d_in, (Fr*)tmp, log_h, width, Fr::one(), LAYOUT_BITREV));
+  return ntt_forward(ctx, (const Fr*)tmp, (Fr*)d_out, log_h + added, added, width, shift, LAYOUT_BITREV);
+}
+
+int eon_dft_batch_dev(eon_ctx* ctx, const uint64_t* d_in, uint64_t* d_out, unsigned log_h, size_t width) {
+  if (!ctx) return EON_ERR_BAD_ARG;
+  Lock lk(ctx);
+  EON_TRY(set_device(ctx));
+  return dft_dev(ctx, d_in, d_out, log_h, width, Fr::one());
+}
+int eon_coset_dft_batch_dev(eon_ctx* ctx, const uint64_t* d_in, uint64_t* d_out, unsigned log_h, size_t width,
+                            const uint64_t shift[4]) {
+  if (!ctx) return EON_ERR_BAD_ARG;
+  Lock lk(ctx);
+  EON_TRY(set_device(ctx));
+  Fr s;
+  EON_TRY(check_shift(ctx, shift, &s));
+  return dft_dev(ctx, d_in, d_out, log_h, width, s);
+}
+int eon_idft_batch_dev(eon_ctx* ctx, const uint64_t* d_in, uint64_t* d_out, unsigned log_h, size_t width) {
+  if (!ctx) return EON_ERR_BAD_ARG;
+  Lock lk(ctx);
+  EON_TRY(set_device(ctx));
+  return idft_dev(ctx, d_in, d_out, log_h, width, Fr::one());
+}
+int eon_coset_idft_batch_dev(eon_ctx* ctx, const uint64_t* d_in, uint64_t* d_out, unsigned log_h, size_t width,
+                             const uint64_t shift[4]) {
+  if (!ctx) return EON_ERR_BAD_ARG;
+  Lock lk(ctx);
+  EON_TRY(set_device(ctx));
+  Fr s;
+  EON_TRY(check_shift(ctx, shift, &s));
+  return idft_dev(ctx, d_in, d_out, log_h, width, s);
+}
+int eon_coset_lde_batch_dev(eon_ctx* ctx, const uint64_t* d_in, uint64_t* d_out, unsigned log_h, size_t width,
+                            unsigned added_bits, const uint64_t shift[4]) {
+  if (!ctx) return EON_ERR_BAD_ARG;
+  Lock lk(ctx);
+  EON_TRY(set_device(ctx));
+  Fr s;
+  EON_TRY(check_shift(ctx, shift, &s));
+  return lde_dev(ctx, d_in, d_out, log_h, width, added_bits, s);
+}
+
+int eon_dft_batch(eon_ctx* ctx, const uint64_t* h_in, uint64_t* h_out, unsigned log_h, size_t width) {
+  if (!ctx) return EON_ERR_BAD_ARG;
+  Lock lk(ctx);
+  EON_TRY(set_device(ctx));
+  EON_TRY(check_dims(ctx, log_h, width));
+  size_t b = mat_bytes(log_h, width);
+  return host_io(ctx, h_in, b, h_out, b, [&](const Fr* i, Fr* o) {
+    return dft_dev(ctx, (const uint64_t*)i, (uint64_t*)o, log_h, width, Fr::one());
+  });
+}
+int eon_coset_dft_batch(eon_ctx* ctx, const uint64_t* h_in, uint64_t* h_out, unsigned log_h, size_t width,
+                        const uint64_t shift[4]) {
+  if (!ctx) return EON_ERR_BAD_ARG;
+  Lock lk(ctx);
+  EON_TRY(set_device(ctx));
+  EON_TRY(check_dims(ctx, log_h, width));
+  Fr s;
+  EON_TRY(check_shift(ctx, shift, &s));
+  size_t b = mat_bytes(log_h, width);
+  return host_io(ctx, h_in, b, h_out, b,
+                 [&](const Fr* i, Fr* o) { return dft_dev(ctx, (const uint64_t*)i, (uint64_t*)o, log_h, width, s); });
+}
+int eon_idft_batch(eon_ctx* ctx, const uint64_t* h_in, uint64_t* h_out, unsigned log_h, size_t width) {
+  if (!ctx) return EON_ERR_BAD_ARG;
+  Lock lk(ctx);
+  EON_TRY(set_device(ctx));
+  EON_TRY(check_dims(ctx, log_h, width));
+  size_t b = mat_bytes(log_h, width);
+  return host_io(ctx, h_in, b, h_out, b, [&](const Fr* i, Fr* o) {
+    return idft_dev(ctx, (const uint64_t*)i, (uint64_t*)o, log_h, width, Fr::one());
+  });
+}
+int eon_coset_idft_batch(eon_ctx* ctx, const uint64_t* h_in, uint64_t* h_out, unsigned log_h, size_t width,
+                         const uint64_t shift[4]) {
+  if (!ctx) return EON_ERR_BAD_ARG;
+  Lock lk(ctx);
+  EON_TRY(set_device(ctx));
+  EON_TRY(check_dims(ctx, log_h, width));
+  Fr s;
+  EON_TRY(check_shift(ctx, shift, &s));
+  size_t b = mat_bytes(log_h, width);
+  return host_io(ctx, h_in, b, h_out, b,
+                 [&](const Fr* i, Fr* o) { return idft_dev(ctx, (const uint64_t*)i, (uint64_t*)o, log_h, width, s); });
+}
+int eon_coset_lde_batch(eon_ctx* ctx, const uint64_t* h_in, uint64_t* h_out, unsigned log_h, size_t width,
+                        unsigned added_bits, const uint64_t shift[4]) {
+  if (!ctx) return EON_ERR_BAD_ARG;
+  Lock lk(ctx);
+  EON_TRY(set_device(ctx));
+  EON_TRY(check_dims(ctx, log_h, width, added_bits));
+  Fr s;
+  EON_TRY(check_shift(ctx, shift, &s));
+  return host_io(ctx, h_in, mat_bytes(log_h, width), h_out, mat_bytes(log_h + added_bits, width),
+                 [&](const Fr* i, Fr* o) {
+                   return lde_dev(ctx, (const uint64_t*)i, (uint64_t*)o, log_h, width, added_bits, s);
+                 });
+}
+
+// ---- SRS ---------------------------------------------------------------------------------------
+int eon_srs_load_affine(eon_ctx* ctx, const uint64_t* h_xy, size_t n) {
+  if (!ctx) return EON_ERR_BAD_ARG;
+  Lock lk(ctx);
+  EON_TRY(set_device(ctx));
+  if (n && !h_xy) return fail(ctx, EON_ERR_BAD_ARG, "null SRS pointer");
+  if (ctx->d_srs) {
+    EON_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    EON_CUDA(ctx, cudaFree(ctx->d_srs));
+    ctx->d_srs = nullptr;
+    ctx->srs_n = 0;
+  }
+  if (n == 0) return EON_OK;
+  EON_CUDA(ctx, cudaMalloc(&ctx->d_srs, n * sizeof(G1Affine)));
+  EON_CUDA(ctx, cudaMemcpyAsync(ctx->d_srs, h_xy, n * sizeof(G1Affine), cudaMemcpyHostToDevice, ctx->stream));
+  EON_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->srs_n = n;
+  return EON_OK;
+}
+
+int eon_srs_generate_unsafe(eon_ctx* ctx, const uint64_t alpha[4], size_t n) {
+  if (!ctx) return EON_ERR_BAD_ARG;
+  Lock lk(ctx);
+  EON_TRY(set_device(ctx));
+  if (!alpha || !fr_wire_is_canonical(alpha)) return fail(ctx, EON_ERR_BAD_ARG, "alpha is not a canonical Fr");
+  EON_TRY(srs_generate(ctx, fr_from_wire(alpha), n));
+  EON_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return EON_OK;
+}
+
+size_t eon_srs_size(const eon_ctx* ctx) { return ctx ? ctx->srs_n : 0; }
+
+int eon_srs_read(eon_ctx* ctx, size_t first, size_t n, uint64_t* h_xy) {
+  if (!ctx) return EON_ERR_BAD_ARG;
+  Lock lk(ctx);
+  EON_TRY(set_device(ctx));
+  if (first + n > ctx->srs_n) return fail(ctx, EON_ERR_BAD_ARG, "SRS range out of bounds");
+  if (n == 0) return EON_OK;
+  EON_CUDA(ctx, cudaMemcpyAsync(h_xy, ctx->d_srs + first, n * sizeof(G1Affine), cudaMemcpyDeviceToHost, ctx->stream));
+  EON_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return EON_OK;
+}
+
+// ---- MSM ---------------------------------------------------------------------------------------
+static int msm_to_host(eon_ctx* ctx, const G1Affine* d_bases, const Fr* d_scalars, size_t n, size_t ncols, size_t ld,
+                       uint64_t* h_out_xy) {
+  if (ncols == 0) return EON_OK;
+  if (!h_out_xy) return fail(ctx, EON_ERR_BAD_ARG, "null output pointer");
+  if (ld < ncols) return fail(ctx, EON_ERR_BAD_ARG, "ld < ncols");
+  void* d_res = nullptr;
+  EON_TRY(scratch_get(ctx, SC_MSM_RESULT, ncols * sizeof(G1Affine), &d_res));
+  EON_TRY(msm_run(ctx, d_bases, d_scalars, n, ncols, ld, (G1Affine*)d_res));
+  EON_CUDA(ctx, cudaMemcpyAsync(h_out_xy, d_res, ncols * sizeof(G1Affine), cudaMemcpyDeviceToHost, ctx->stream));
+  EON_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return EON_OK;
+}
+
+int eon_msm_srs_range_dev(eon_ctx* ctx, const uint64_t* d_scalars, size_t first, size_t n, size_t ncols, size_t ld,
+                          uint64_t* h_out_xy) {
+  if (!ctx) return EON_ERR_BAD_ARG;
+  Lock lk(ctx);
+  EON_TRY(set_device(ctx));
+  if (first + n > ctx->srs_n) {
+    // commit_column's degree guard (kzg/src/util.rs:38, params.rs:164-173)
+    char b[128];
+    snprintf(b, sizeof(b), "DegreeTooLarge: need %zu SRS points, have %zu", first + n, ctx->srs_n);
+    return fail(ctx, EON_ERR_SRS_TOO_SHORT, b);
+  }
+  if (n && ncols && !d_scalars) return fail(ctx, EON_ERR_BAD_ARG, "null scalars");
+  return msm_to_host(ctx, ctx->d_srs + first, (const Fr*)d_scalars, n, ncols, ld, h_out_xy);
+}
+
+int eon_msm_srs_dev(eon_ctx* ctx, const uint64_t* d_scalars, size_t n, size_t ncols, size_t ld, uint64_t* h_out_xy) {
+  return eon_msm_srs_range_dev(ctx, d_scalars, 0, n, ncols, ld, h_out_xy);
+}
+
+int eon_msm_srs(eon_ctx* ctx, const uint64_t* h_scalars, size_t n, size_t ncols, size_t ld, uint64_t* h_out_xy) {
+  if (!ctx) return EON_ERR_BAD_ARG;
+  Lock lk(ctx);
+  EON_TRY(set_device(ctx));
+  if (n > ctx->srs_n) return fail(ctx, EON_ERR_SRS_TOO_SHORT, "DegreeTooLarge: polynomial longer than the SRS");
+  if (n && ncols && !h_scalars) return fail(ctx, EON_ERR_BAD_ARG, "null scalars");
+  if (ld < ncols) return fail(ctx, EON_ERR_BAD_ARG, "ld < ncols");
+  void* d_sc = nullptr;
+  size_t bytes = n * ld * sizeof(Fr);
+  EON_TRY(scratch_get(ctx, SC_IO_A, bytes + 32, &d_sc));
+  if (bytes) EON_CUDA(ctx, cudaMemcpyAsync(d_sc, h_scalars, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  return msm_to_host(ctx, ctx->d_srs, (const Fr*)d_sc, n, ncols, ld, h_out_xy);
+}
+
+int eon_msm_points(eon_ctx* ctx, const uint64_t* h_points_xy, const uint64_t* h_scalars, size_t n,
+                   uint64_t* h_out_xy) {
+  if (!ctx) return EON_ERR_BAD_ARG;
+  Lock lk(ctx);
+  EON_TRY(set_device(ctx));
+  if (n && (!h_points_xy || !h_scalars)) return fail(ctx, EON_ERR_BAD_ARG, "null input");
+  void *d_sc = nullptr, *d_pt = nullptr;
+  EON_TRY(scratch_get(ctx, SC_IO_A, n * sizeof(Fr) + 32, &d_sc));
+  EON_TRY(scratch_get(ctx, SC_IO_B, n * sizeof(G1Affine) + 64, &d_pt));
+  if (n) {
+    EON_CUDA(ctx, cudaMemcpyAsync(d_sc, h_scalars, n * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
+    EON_CUDA(ctx, cudaMemcpyAsync(d_pt, h_points_xy, n * sizeof(G1Affine), cudaMemcpyHostToDevice, ctx->stream));
+  }
+  return msm_to_host(ctx, (const G1Affine*)d_pt, (const Fr*)d_sc, n, 1, 1, h_out_xy);
+}
+
+int eon_g1_sum(eon_ctx* ctx, const uint64_t* h_points_xy, size_t n, uint64_t* h_out_xy) {
+  if (!ctx) return EON_ERR_BAD_ARG;
+  Lock lk(ctx);
+  EON_TRY(set_device(ctx));
+  if ((n && !h_points_xy) || !h_out_xy) return fail(ctx, EON_ERR_BAD_ARG, "null input");
+  void* d_pt = nullptr;
+  EON_TRY(scratch_get(ctx, SC_IO_B, (n + 1) * sizeof(G1Affine), &d_pt));
+  G1Affine* pts = (G1Affine*)d_pt;
+  if (n) EON_CUDA(ctx, cudaMemcpyAsync(pts + 1, h_points_xy, n * sizeof(G1Affine), cudaMemcpyHostToDevice, ctx->stream));
+  EON_TRY(g1_sum_run(ctx, pts + 1, n, pts));
+  EON_CUDA(ctx, cudaMemcpyAsync(h_out_xy, pts, sizeof(G1Affine), cudaMemcpyDeviceToHost, ctx->stream));
+  EON_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return EON_OK;
+}
+
+// ---- KZG ---------------------------------------------------------------------------------------
+static int kzg_commit_locked(eon_ctx* ctx, const uint64_t* d_evals, unsigned log_h, size_t width,
+                             const uint64_t shift[4], uint64_t* h_commit_xy, eon_handle* out_handle) {
+  if (!out_handle) return fail(ctx, EON_ERR_BAD_ARG, "null handle pointer");
+  *out_handle = 0;
+  EON_TRY(check_dims(ctx, log_h, width));
+  Fr s;
+  EON_TRY(check_shift(ctx, shift, &s));
+  const size_t h = (size_t)1 << log_h;
+  if (h > ctx->srs_n) {  // ensure_supported(height - 1), kzg/src/pcs.rs:238-240
+    char b[128];
+    snprintf(b, sizeof(b), "DegreeTooLarge: degree %zu > max %zu", h - 1, ctx->srs_n ? ctx->srs_n - 1 : 0);
+    return fail(ctx, EON_ERR_SRS_TOO_SHORT, b);
+  }
+  if (width && (!d_evals || !h_commit_xy)) return fail(ctx, EON_ERR_BAD_ARG, "null buffer");
+  Fr* d_coeffs = nullptr;
+  EON_CUDA(ctx, cudaMalloc(&d_coeffs, mat_bytes(log_h, width) + 32));
+  int rc = ntt_inverse(ctx, (const Fr*)d_evals, d_coeffs, log_h, width, s, LAYOUT_NATURAL);
+  if (rc == EON_OK) rc = msm_to_host(ctx, ctx->d_srs, d_coeffs, h, width, width, h_commit_xy);
+  if (rc != EON_OK) {
+    cudaFree(d_coeffs);
+    return rc;
+  }
+  ProverMatrix pm;
+  pm.d_coeffs = d_coeffs;
+  pm.log_h = log_h;
+  pm.width = width;
+  eon_handle id = ctx->next_handle++;
+  ctx->handles[id] = pm;
+  *out_handle = id;
+  return EON_OK;
+}
+
+int eon_kzg_commit_dev(eon_ctx* ctx, const uint64_t* d_evals, unsigned log_h, size_t width, const uint64_t shift[4],
+                       uint64_t* h_commit_xy, eon_handle* out_handle) {
+  if (!ctx) return EON_ERR_BAD_ARG;
+  Lock lk(ctx);
+  EON_TRY(set_device(ctx));
+  return kzg_commit_locked(ctx, d_evals, log_h, width, shift, h_commit_xy, out_handle);
+}
+
+int eon_kzg_commit(eon_ctx* ctx, const uint64_t* h_evals, unsigned log_h, size_t width, const uint64_t shift[4],
+                   uint64_t* h_commit_xy, eon_handle* out_handle) {
+  if (!ctx) return EON_ERR_BAD_ARG;
+  Lock lk(ctx);
+  EON_TRY(set_device(ctx));
+  EON_TRY(check_dims(ctx, log_h, width));
+  size_t b = mat_bytes(log_h, width);
+  if (b && !h_evals) return fail(ctx, EON_ERR_BAD_ARG, "null evals");
+  void* d_in = nullptr;
+  EON_TRY(scratch_get(ctx, SC_IO_A, b + 32, &d_in));
+  if (b) EON_CUDA(ctx, cudaMemcpyAsync(d_in, h_evals, b, cudaMemcpyHostToDevice, ctx->stream));
+  return kzg_commit_locked(ctx, (const uint64_t*)d_in, log_h, width, shift, h_commit_xy, out_handle);
+}
+
+static int find_handle(eon_ctx* ctx, eon_handle h, ProverMatrix* pm) {
+  auto it = ctx->handles.find(h);
+  if (it == ctx->handles.end()) return fail(ctx, EON_ERR_BAD_HANDLE, "unknown prover-data handle");
+  *pm = it->second;
+  return EON_OK;
+}
+
+int eon_handle_dims(eon_ctx* ctx, eon_handle h, unsigned* log_h, size_t* width) {
+  if (!ctx) return EON_ERR_BAD_ARG;
+  Lock lk(ctx);
+  ProverMatrix pm;
+  EON_TRY(find_handle(ctx, h, &pm));
+  if (log_h) *log_h = pm.log_h;
+  if (width) *width = pm.width;
+  return EON_OK;
+}
+
+int eon_handle_free(eon_ctx* ctx, eon_handle h) {
+  if (!ctx) return EON_ERR_BAD_ARG;
+  Lock lk(ctx);
+  EON_TRY(set_device(ctx));
+  ProverMatrix pm;
+  EON_TRY(find_handle(ctx, h, &pm));
+  EON_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  EON_CUDA(ctx, cudaFree(pm.d_coeffs));
+  ctx->handles.erase(h);
+  return EON_OK;
+}
+
+int eon_kzg_read_coeffs(eon_ctx* ctx, eon_handle h, uint64_t* h_out) {
+  if (!ctx) return EON_ERR_BAD_ARG;
+  Lock lk(ctx);
+  EON_TRY(set_device(ctx));
+  ProverMatrix pm;
+  EON_TRY(find_handle(ctx, h, &pm));
+  size_t b = mat_bytes(pm.log_h, pm.width);
+  if (b == 0) return EON_OK;
+  if (!h_out) return fail(ctx, EON_ERR_BAD_ARG, "null output");
+  EON_CUDA(ctx, cudaMemcpyAsync(h_out, pm.d_coeffs, b, cudaMemcpyDeviceToHost, ctx->stream));
+  EON_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return EON_OK;
+}
+
+static int evals_on_coset_locked(eon_ctx* ctx, eon_handle h, unsigned log_size, const uint64_t shift[4], Fr* d_out) {
+  ProverMatrix pm;
+  EON_TRY(find_handle(ctx, h, &pm));
+  Fr s;
+  EON_TRY(check_shift(ctx, shift, &s));
+  if (log_size < pm.log_h)
+    return fail(ctx, EON_ERR_BAD_ARG, "evaluation domain smaller than the committed polynomial length");
+  EON_TRY(check_dims(ctx, log_size, pm.width));
+  if (pm.width == 0) return EON_OK;
+  if (!d_out) return fail(ctx, EON_ERR_BAD_ARG, "null output");
+  return ntt_forward(ctx, pm.d_coeffs, d_out, log_size, log_size - pm.log_h, pm.width, s, LAYOUT_NATURAL);
+}
+
+int eon_kzg_evals_on_coset_dev(eon_ctx* ctx, eon_handle h, unsigned log_size, const uint64_t shift[4],
+                               uint64_t* d_out) {
+  if (!ctx) return EON_ERR_BAD_ARG;
+  Lock lk(ctx);
+  EON_TRY(set_device(ctx));
+  return evals_on_coset_locked(ctx, h, log_size, shift, (Fr*)d_out);
+}
+
+int eon_kzg_evals_on_coset(eon_ctx* ctx, eon_handle h, unsigned log_size, const uint64_t shift[4], uint64_t* h_out) {
+  if (!ctx) return EON_ERR_BAD_ARG;
+  Lock lk(ctx);
+  EON_TRY(set_device(ctx));
+  ProverMatrix pm;
+  EON_TRY(find_handle(ctx, h, &pm));
+  if (log_size > 28) return fail(ctx, EON_ERR_TWO_ADICITY, "domain exceeds 2^28");
+  size_t b = mat_bytes(log_size, pm.width);
+  void* d_out = nullptr;
+  EON_TRY(scratch_get(ctx, SC_IO_B, b + 32, &d_out));
+  EON_TRY(evals_on_coset_locked(ctx, h, log_size, shift, (Fr*)d_out));
+  if (b) {
+    if (!h_out) return fail(ctx, EON_ERR_BAD_ARG, "null output");
+    EON_CUDA(ctx, cudaMemcpyAsync(h_out, d_out, b, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  EON_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return EON_OK;
+}
+
+int eon_quotient_and_eval_dev(eon_ctx* ctx, const uint64_t* d_coeffs, size_t h, size_t width, const uint64_t z[4],
+                              uint64_t* d_quot, uint64_t* h_values) {
+  if (!ctx) return EON_ERR_BAD_ARG;
+  Lock lk(ctx);
+  EON_TRY(set_device(ctx));
+  if (!z || !fr_wire_is_canonical(z)) return fail(ctx, EON_ERR_BAD_ARG, "z is not a canonical Fr");
+  if (width == 0) return EON_OK;
+  if ((h && (!d_coeffs || !d_quot)) || !h_values) return fail(ctx, EON_ERR_BAD_ARG, "null buffer");
+  void* d_vals = nullptr;
+  EON_TRY(scratch_get(ctx, SC_MSM_RESULT, width * sizeof(Fr) + 64, &d_vals));
+  EON_TRY(quotient_run(ctx, (const Fr*)d_coeffs, h, width, width, fr_from_wire(z), (Fr*)d_quot, (Fr*)d_vals));
+  EON_CUDA(ctx, cudaMemcpyAsync(h_values, d_vals, width * sizeof(Fr), cudaMemcpyDeviceToHost, ctx->stream));
+  EON_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return EON_OK;
+}
+
+int eon_kzg_open(eon_ctx* ctx, eon_handle h, const uint64_t* h_points, size_t npoints, uint64_t* h_values,
+                 uint64_t* h_witness_xy) {
+  if (!ctx) return EON_ERR_BAD_ARG;
+  Lock lk(ctx);
+  EON_TRY(set_device(ctx));
+  ProverMatrix pm;
+  EON_TRY(find_handle(ctx, h, &pm));
+  const size_t w = pm.width, rows = (size_t)1 << pm.log_h;
+  if (npoints == 0 || w == 0) return EON_OK;
+  if (!h_points || !h_values || !h_witness_xy) return fail(ctx, EON_ERR_BAD_ARG, "null buffer");
+  for (size_t p = 0; p < npoints; p++)
+    if (!fr_wire_is_canonical(h_points + 4 * p)) return fail(ctx, EON_ERR_BAD_ARG, "opening point is not canonical");
+  // the quotient of a length-h polynomial has h-1 coefficients: witness = MSM over srs[..h-1]
+  // (commit_column(&quotient), kzg/src/pcs.rs:316); degree guard as in util.rs:38
+  if (rows - 1 > ctx->srs_n) return fail(ctx, EON_ERR_SRS_TOO_SHORT, "DegreeTooLarge: quotient longer than the SRS");
+  const size_t ncols = npoints * w;
+  void *d_quot = nullptr, *d_vals = nullptr, *d_wit = nullptr;
+  EON_TRY(scratch_get(ctx, SC_QUOT, rows * ncols * sizeof(Fr) + 32, &d_quot));
+  EON_TRY(scratch_get(ctx, SC_IO_B, ncols * (sizeof(Fr) + sizeof(G1Affine)) + 64, &d_vals));
+  d_wit = (char*)d_vals + ncols * sizeof(Fr);
+  for (size_t p = 0; p < npoints; p++) {
+    Fr z = fr_from_wire(h_points + 4 * p);
+    EON_TRY(quotient_run(ctx, pm.d_coeffs, rows, w, ncols, z, (Fr*)d_quot + p * w, (Fr*)d_vals + p * w));
+  }
+  EON_TRY(msm_run(ctx, ctx->d_srs, (const Fr*)d_quot, rows - 1, ncols, ncols, (G1Affine*)d_wit));
+  EON_CUDA(ctx, cudaMemcpyAsync(h_values, d_vals, ncols * sizeof(Fr), cudaMemcpyDeviceToHost, ctx->stream));
+  EON_CUDA(ctx, cudaMemcpyAsync(h_witness_xy, d_wit, ncols * sizeof(G1Affine), cudaMemcpyDeviceToHost, ctx->stream));
+  EON_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return EON_OK;
+}
+
+// ---- measurement ---------------------------------------------------------------------------------
+int eon_bench_imad_peak(eon_ctx* ctx, int kind, double* out_tops) {
+  if (!ctx || !out_tops) return EON_ERR_BAD_ARG;
+  Lock lk(ctx);
+  EON_TRY(set_device(ctx));
+  return bench_imad(ctx, kind, out_tops);
+}
+int eon_bench_modmul(eon_ctx* ctx, int field, double* out_gmuls) {
+  if (!ctx || !out_gmuls) return EON_ERR_BAD_ARG;
+  Lock lk(ctx);
+  EON_TRY(set_device(ctx));
+  return bench_modmul(ctx, field, out_gmuls);
+}
+
+int eon_last_phase_ms(eon_ctx* ctx, int phase, float* out_ms) {
+  if (!ctx || !out_ms || phase < 0 || phase >= PH_COUNT) return EON_ERR_BAD_ARG;
+  Lock lk(ctx);
+  EON_TRY(set_device(ctx));
+  *out_ms = 0.f;
+  if (!ctx->ev_used[phase]) return EON_OK;
+  EON_CUDA(ctx, cudaEventSynchronize(ctx->ev[phase][1]));
+  EON_CUDA(ctx, cudaEventElapsedTime(out_ms, ctx->ev[phase][0], ctx->ev[phase][1]));
+  return EON_OK;
+}
+
+const char* eon_phase_name(int phase) {
+  static const char* names[PH_COUNT] = {"ntt_twiddle", "ntt_passes", "msm_digits", "msm_scan",
+                                         "msm_scatter", "msm_accumulate", "msm_reduce", "quotient"};
+  return (phase >= 0 && phase < PH_COUNT) ? names[phase] : "?";
+}
+
+}  // extern "C"

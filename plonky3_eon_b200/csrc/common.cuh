@@ -1,0 +1,201 @@
+// Shared host-side plumbing of libeon_kzg: context, error handling, workspace, caches.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/eon_kzg.h"
+#include "ec.cuh"
+
+namespace eon {
+
+enum Phase {
+  PH_NTT_TWIDDLE = 0,
+  PH_NTT_PASSES,
+  PH_MSM_DIGITS,
+  PH_MSM_SCAN,
+  PH_MSM_SCATTER,
+  PH_MSM_ACCUM,
+  PH_MSM_REDUCE,
+  PH_QUOTIENT,
+  PH_COUNT
+};
+
+struct TwiddleKey {
+  unsigned log_n;
+  int inverse;
+  u32 shift[8];
+  bool operator<(const TwiddleKey& o) const {
+    if (log_n != o.log_n) return log_n < o.log_n;
+    if (inverse != o.inverse) return inverse < o.inverse;
+    return memcmp(shift, o.shift, sizeof(shift)) < 0;
+  }
+};
+
+struct ProverMatrix {
+  Fr* d_coeffs;  // natural order, h x width
+  unsigned log_h;
+  size_t width;
+};
+
+// grow-only device scratch buffers, one per role, reused across calls (no allocation in steady state)
+struct Scratch {
+  void* ptr = nullptr;
+  size_t cap = 0;
+};
+
+enum ScratchId {
+  SC_NTT_TMP = 0,
+  SC_MSM_DIGITS,
+  SC_MSM_HIST,
+  SC_MSM_CURSOR,
+  SC_MSM_ENTRIES,
+  SC_MSM_BUCKETS,
+  SC_MSM_TASKS,
+  SC_MSM_TASKPART,
+  SC_MSM_PARTIALS,
+  SC_MSM_SEGSUM,
+  SC_MSM_RESULT,
+  SC_MSM_MISC,
+  SC_IO_A,
+  SC_IO_B,
+  SC_QUOT,
+  SC_QUOT_AUX,
+  SC_SMALL,
+  SC_COUNT
+};
+
+}  // namespace eon
+
+struct eon_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  int num_sms = 148;
+  std::string last_error;
+  uint64_t launches = 0;
+  std::mutex mu;  // callers may share a ctx across threads: one call at a time
+
+  eon::Scratch scratch[eon::SC_COUNT];
+  std::map<eon::TwiddleKey, eon::Fr*> twiddles;
+
+  eon::G1Affine* d_srs = nullptr;
+  size_t srs_n = 0;
+
+  std::map<eon_handle, eon::ProverMatrix> handles;
+  eon_handle next_handle = 1;
+
+  cudaEvent_t ev[eon::PH_COUNT][2];
+  bool ev_used[eon::PH_COUNT];
+  float phase_ms[eon::PH_COUNT];
+};
+
+namespace eon {
+
+inline int fail(eon_ctx* ctx, int code, const std::string& msg) {
+  if (ctx) ctx->last_error = msg;
+  return code;
+}
+
+#define EON_CUDA(ctx, expr)                                                                          \
+  do {                                                                                               \
+    cudaError_t _e = (expr);                                                                         \
+    if (_e != cudaSuccess) {                                                                         \
+      char _b[512];                                                                                  \
+      snprintf(_b, sizeof(_b), "%s:%d: %s failed: %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+      return eon::fail(ctx, _e == cudaErrorMemoryAllocation ? EON_ERR_OOM : EON_ERR_CUDA, _b);       \
+    }                                                                                                \
+  } while (0)
+
+#define EON_TRY(expr)              \
+  do {                             \
+    int _rc = (expr);              \
+    if (_rc != EON_OK) return _rc; \
+  } while (0)
+
+// after a kernel launch: count it and surface launch-configuration errors
+#define EON_LAUNCHED(ctx)                         \
+  do {                                            \
+    (ctx)->launches++;                            \
+    EON_CUDA(ctx, cudaPeekAtLastError());         \
+  } while (0)
+
+inline int scratch_get(eon_ctx* ctx, int id, size_t bytes, void** out) {
+  Scratch& s = ctx->scratch[id];
+  if (bytes > s.cap) {
+    if (s.ptr) {
+      // outstanding work on the stream may still use the old buffer
+      EON_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+      EON_CUDA(ctx, cudaFree(s.ptr));
+      s.ptr = nullptr;
+      s.cap = 0;
+    }
+    size_t cap = bytes + (bytes >> 3) + 256;
+    EON_CUDA(ctx, cudaMalloc(&s.ptr, cap));
+    s.cap = cap;
+  }
+  *out = s.ptr;
+  return EON_OK;
+}
+
+inline void phase_begin(eon_ctx* ctx, int ph) {
+  cudaEventRecord(ctx->ev[ph][0], ctx->stream);
+}
+inline void phase_end(eon_ctx* ctx, int ph) {
+  cudaEventRecord(ctx->ev[ph][1], ctx->stream);
+  ctx->ev_used[ph] = true;
+}
+
+// host-side Fr helpers (same arithmetic as the device, software carry flag)
+inline Fr fr_from_wire(const uint64_t w[4]) {
+  Fr r;
+  memcpy(r.v, w, 32);
+  return r;
+}
+inline bool fr_wire_is_canonical(const uint64_t w[4]) {
+  // lexicographic compare with the modulus, top limb first
+  const u32* v = reinterpret_cast<const u32*>(w);
+  for (int i = 7; i >= 0; i--) {
+    u32 m = FrParams::mod(i);
+    if (v[i] < m) return true;
+    if (v[i] > m) return false;
+  }
+  return false;
+}
+// two_adic_generator(bits): omega_28 squared (28 - bits) times.  Reference: field.rs:567-573.
+inline Fr fr_two_adic_generator(unsigned bits) {
+  const u32 w28[8] = EON_FR_OMEGA28;
+  Fr o;
+  memcpy(o.v, w28, 32);
+  for (unsigned i = bits; i < 28; i++) o = fp_sqr(o);
+  return o;
+}
+
+// ---- internal cross-file API (device pointers, ctx->mu held by the caller) ----------------
+enum Layout { LAYOUT_NATURAL = 0, LAYOUT_BITREV = 1 };
+
+// forward coset NTT of size 2^log_n from 2^(log_n-k) coefficient rows (zero-padded).
+int ntt_forward(eon_ctx* ctx, const Fr* d_src, Fr* d_dst, unsigned log_n, unsigned k, size_t width, const Fr& shift,
+                Layout src_layout);
+// inverse coset NTT of size 2^log_n: evaluations on shift*H (natural) -> coefficients.
+int ntt_inverse(eon_ctx* ctx, const Fr* d_src, Fr* d_dst, unsigned log_n, size_t width, const Fr& shift,
+                Layout dst_layout);
+
+// out[c] = sum_i scalars[i*ld + c] * bases[i], c < ncols.  d_out: ncols affine points (device).
+int msm_run(eon_ctx* ctx, const G1Affine* d_bases, const Fr* d_scalars, size_t n, size_t ncols, size_t ld,
+            G1Affine* d_out);
+int g1_sum_run(eon_ctx* ctx, const G1Affine* d_points, size_t n, G1Affine* d_out);
+int srs_generate(eon_ctx* ctx, const Fr& alpha, size_t n);
+
+int quotient_run(eon_ctx* ctx, const Fr* d_coeffs, size_t h, size_t width, size_t ld_out, const Fr& z, Fr* d_quot,
+                 Fr* d_values);
+
+int bench_imad(eon_ctx* ctx, int kind, double* out_tops);
+int bench_modmul(eon_ctx* ctx, int field, double* out_gmuls);
+
+}  // namespace eon

@@ -1,0 +1,456 @@
+// Batched G1 multi-scalar multiplication (signed-window Pippenger) on sm_100a.
+//
+// Replaces G1::multi_exp (bn254/src/curve.rs:158-180), i.e. the per-call `to_affine` of every
+// SRS point (curve.rs:170) followed by halo2curves::msm::msm_best (curve.rs:177), and the
+// per-column loops around it (kzg/src/pcs.rs:244-249,311-318).  All `ncols` columns of a
+// coefficient matrix share the resident affine bases and are processed by the same launches.
+//
+// Pipeline (segment = one (column, window) pair, NB = 2^(c-1) buckets per segment):
+//   1 digits     scalar: Montgomery -> canonical (x * 1 * R^-1), signed c-bit digits as int16,
+//                bucket histogram with global REDs
+//   2 scan       exclusive scan of each segment's histogram -> bucket start offsets
+//   3 scatter    counting sort: entries[seg][start[b]++] = point index | sign << 31
+//   4 accumulate one thread per bucket: XYZZ += +-base (mixed add, 8M+2S); buckets larger than
+//                a chunk are split into extra tasks so skewed scalars stay load-balanced
+//   5 reduce     per segment sum_b (b+1) * B_b by chunked running sums, tree-combined per block
+//   6 combine    per column Horner over windows (c doublings + 1 add each), to affine
+// The result is the canonical affine point, hence bit-identical to the reference whatever the
+// order of additions.
+#include "common.cuh"
+
+namespace eon {
+
+constexpr int MSM_THREADS = 256;
+constexpr u32 SIGN_BIT = 0x80000000u;
+
+struct MsmShape {
+  u32 c;        // window bits (2..16)
+  u32 W;        // windows = ceil(256 / c)
+  u32 NB;       // buckets per segment = 2^(c-1)
+  u32 chunk;    // buckets per reduction chunk
+  u32 nchunks;  // NB / chunk
+};
+
+static MsmShape msm_shape(size_t n) {
+  u32 lg = 0;
+  while (((size_t)1 << lg) < n) lg++;
+  int c = (int)lg - 3;
+  if (c < 2) c = 2;
+  if (c > 16) c = 16;
+  MsmShape s;
+  s.c = (u32)c;
+  s.W = (256 + s.c - 1) / s.c;
+  s.NB = 1u << (s.c - 1);
+  s.chunk = s.NB < 32 ? s.NB : 32;
+  s.nchunks = s.NB / s.chunk;
+  return s;
+}
+
+// ---- 1. digits + histogram ------------------------------------------------------------------
+// grid: (ceil(n / threads), ncols).  digits layout: [col][window][i] int16.
+__global__ void __launch_bounds__(MSM_THREADS)
+k_msm_digits(const Fr* __restrict__ scalars, size_t n, size_t ld, MsmShape sh, int16_t* __restrict__ digits,
+             u32* __restrict__ hist) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  u32 col = blockIdx.y;
+  const uint4* sp = reinterpret_cast<const uint4*>(scalars + i * ld + col);
+  uint4 lo = __ldg(sp), hi = __ldg(sp + 1);
+  Fr s;
+  s.v[0] = lo.x; s.v[1] = lo.y; s.v[2] = lo.z; s.v[3] = lo.w;
+  s.v[4] = hi.x; s.v[5] = hi.y; s.v[6] = hi.z; s.v[7] = hi.w;
+  u32 k[9];
+  fp_from_mont(k, s);
+  k[8] = 0;
+  const u32 c = sh.c;
+  const u32 mask = (1u << c) - 1;
+  const u32 half = 1u << (c - 1);
+  u32 carry = 0;
+  for (u32 w = 0; w < sh.W; w++) {
+    u32 bit = w * c;
+    u32 limb = bit >> 5, off = bit & 31;
+    u32 raw;
+    if (limb >= 8) {
+      raw = 0;
+    } else {
+      u64 two = (u64)k[limb] | ((u64)k[limb + 1] << 32);
+      raw = (u32)(two >> off) & mask;
+    }
+    raw += carry;
+    int d;
+    if (raw >= half) {
+      d = (int)raw - (int)(1u << c);
+      carry = 1;
+    } else {
+      d = (int)raw;
+      carry = 0;
+    }
+    size_t seg = (size_t)col * sh.W + w;
+    digits[seg * n + i] = (int16_t)d;
+    if (d != 0) {
+      u32 b = (u32)(d < 0 ? -d : d) - 1;
+      atomicAdd(&hist[seg * sh.NB + b], 1u);
+    }
+  }
+}
+
+// ---- 2. exclusive scan per segment ----------------------------------------------------------
+// one block per segment; hist -> starts (in place), cursor = copy of starts
+__global__ void __launch_bounds__(1024) k_msm_scan(u32* __restrict__ hist, u32* __restrict__ cursor, u32 NB) {
+  __shared__ u32 warp_sums[32];
+  __shared__ u32 s_carry;
+  u32* h = hist + (size_t)blockIdx.x * NB;
+  u32* cur = cursor + (size_t)blockIdx.x * NB;
+  const u32 tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  if (tid == 0) s_carry = 0;
+  __syncthreads();
+  for (u32 base = 0; base < NB; base += 1024) {
+    u32 idx = base + tid;
+    u32 v = idx < NB ? h[idx] : 0;
+    u32 x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      u32 y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= (u32)o) x += y;
+    }
+    if (lane == 31) warp_sums[wid] = x;
+    __syncthreads();
+    if (wid == 0) {
+      u32 ws = warp_sums[lane];
+      u32 z = ws;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        u32 y = __shfl_up_sync(0xffffffffu, z, o);
+        if (lane >= (u32)o) z += y;
+      }
+      warp_sums[lane] = z - ws;  // exclusive
+    }
+    __syncthreads();
+    u32 carry = s_carry;
+    u32 excl = carry + warp_sums[wid] + x - v;
+    if (idx < NB) {
+      h[idx] = excl;
+      cur[idx] = excl;
+    }
+    __syncthreads();
+    if (tid == 1023) s_carry = excl + v;
+    __syncthreads();
+  }
+}
+
+// ---- 3. scatter (counting sort by bucket) ----------------------------------------------------
+// grid: (ceil(n / threads), nseg)
+__global__ void __launch_bounds__(MSM_THREADS)
+k_msm_scatter(const int16_t* __restrict__ digits, size_t n, u32 NB, u32* __restrict__ cursor, u32* __restrict__ entries) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  size_t seg = blockIdx.y;
+  int d = digits[seg * n + i];
+  if (d == 0) return;
+  u32 b = (u32)(d < 0 ? -d : d) - 1;
+  u32 pos = atomicAdd(&cursor[seg * NB + b], 1u);
+  entries[seg * n + pos] = (u32)i | (d < 0 ? SIGN_BIT : 0u);
+}
+
+// ---- 4. bucket accumulation --------------------------------------------------------------------
+struct MsmTask {
+  u32 bucket;  // global bucket id = seg * NB + b
+  u32 seg;
+  u32 begin, end;  // entry range inside the segment
+};
+
+__device__ __forceinline__ G1Affine load_base(const G1Affine* __restrict__ bases, u32 idx) {
+  const uint4* p = reinterpret_cast<const uint4*>(bases + idx);
+  uint4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2), d = __ldg(p + 3);
+  G1Affine r;
+  r.x.v[0] = a.x; r.x.v[1] = a.y; r.x.v[2] = a.z; r.x.v[3] = a.w;
+  r.x.v[4] = b.x; r.x.v[5] = b.y; r.x.v[6] = b.z; r.x.v[7] = b.w;
+  r.y.v[0] = c.x; r.y.v[1] = c.y; r.y.v[2] = c.z; r.y.v[3] = c.w;
+  r.y.v[4] = d.x; r.y.v[5] = d.y; r.y.v[6] = d.z; r.y.v[7] = d.w;
+  return r;
+}
+
+__device__ __forceinline__ G1Xyzz accumulate_range(const G1Affine* __restrict__ bases, const u32* __restrict__ ent,
+                                                   u32 begin, u32 end) {
+  G1Xyzz acc = G1Xyzz::identity();
+  for (u32 e = begin; e < end; e++) {
+    u32 v = __ldg(ent + e);
+    G1Affine p = load_base(bases, v & ~SIGN_BIT);
+    if (v & SIGN_BIT) p.y = fp_neg(p.y);
+    g1_add_mixed(acc, p);
+  }
+  return acc;
+}
+
+__device__ __forceinline__ void store_xyzz(G1Xyzz* dst, const G1Xyzz& p) { *dst = p; }
+
+// one thread per bucket; starts[] = bucket begin, cursor[] = bucket end (after the scatter)
+__global__ void __launch_bounds__(MSM_THREADS)
+k_msm_accumulate(const G1Affine* __restrict__ bases, const u32* __restrict__ entries, size_t n,
+                 const u32* __restrict__ starts, const u32* __restrict__ ends, u32 NB, size_t total_buckets,
+                 u32 chunk_min, G1Xyzz* __restrict__ buckets, MsmTask* __restrict__ tasks, u32* __restrict__ ntasks,
+                 u32 max_tasks) {
+  size_t g = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (g >= total_buckets) return;
+  u32 seg = (u32)(g / NB);
+  u32 begin = starts[g], end = ends[g];
+  u32 cnt = end - begin;
+  u32 my_end = end;
+  if (cnt > chunk_min) {
+    // split: at most 512 chunks per bucket, each at least chunk_min entries
+    u32 ch = (cnt + 511) / 512;
+    if (ch < chunk_min) ch = chunk_min;
+    u32 extra = (cnt + ch - 1) / ch - 1;
+    u32 slot = atomicAdd(ntasks, extra);
+    if (slot + extra <= max_tasks) {
+      for (u32 t = 0; t < extra; t++) {
+        MsmTask tk;
+        tk.bucket = (u32)g;
+        tk.seg = seg;
+        tk.begin = begin + (t + 1) * ch;
+        tk.end = min(end, begin + (t + 2) * ch);
+        tasks[slot + t] = tk;
+      }
+      my_end = begin + ch;
+    }
+    // else: task buffer exhausted (cannot happen with the sizing in msm_run); fall back to serial
+  }
+  const u32* ent = entries + (size_t)seg * n;
+  G1Xyzz acc = accumulate_range(bases, ent, begin, my_end);
+  store_xyzz(buckets + g, acc);
+}
+
+// extra chunks of oversized buckets -> partial sums
+__global__ void __launch_bounds__(MSM_THREADS)
+k_msm_accumulate_tasks(const G1Affine* __restrict__ bases, const u32* __restrict__ entries, size_t n,
+                       const MsmTask* __restrict__ tasks, const u32* __restrict__ ntasks, u32 max_tasks,
+                       G1Xyzz* __restrict__ partial) {
+  u32 nt = min(*ntasks, max_tasks);
+  for (u32 t = blockIdx.x * blockDim.x + threadIdx.x; t < nt; t += gridDim.x * blockDim.x) {
+    MsmTask tk = tasks[t];
+    G1Xyzz acc = accumulate_range(bases, entries + (size_t)tk.seg * n, tk.begin, tk.end);
+    partial[t] = acc;
+  }
+}
+
+// fold the partial sums of each split bucket back into the bucket (tasks of one bucket are contiguous)
+__global__ void __launch_bounds__(MSM_THREADS)
+k_msm_fold_tasks(const MsmTask* __restrict__ tasks, const u32* __restrict__ ntasks, u32 max_tasks,
+                 const G1Xyzz* __restrict__ partial, G1Xyzz* __restrict__ buckets) {
+  u32 nt = min(*ntasks, max_tasks);
+  for (u32 t = blockIdx.x * blockDim.x + threadIdx.x; t < nt; t += gridDim.x * blockDim.x) {
+    u32 b = tasks[t].bucket;
+    if (t > 0 && tasks[t - 1].bucket == b) continue;  // not the first task of its bucket
+    G1Xyzz acc = buckets[b];
+    for (u32 u = t; u < nt && tasks[u].bucket == b; u++) g1_add(acc, partial[u]);
+    buckets[b] = acc;
+  }
+}
+
+// ---- 5. bucket reduction ----------------------------------------------------------------------
+// thread per (segment, chunk): running sums over `chunk` consecutive buckets.
+//   S = sum B_b,  T = sum (b - lo + 1) * B_b   =>   contribution = T + lo * S
+__global__ void __launch_bounds__(MSM_THREADS)
+k_msm_reduce_chunks(const G1Xyzz* __restrict__ buckets, MsmShape sh, size_t nseg, G1Xyzz* __restrict__ partials) {
+  size_t g = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (g >= nseg * sh.nchunks) return;
+  size_t seg = g / sh.nchunks;
+  u32 ch = (u32)(g % sh.nchunks);
+  u32 lo = ch * sh.chunk;
+  const G1Xyzz* B = buckets + seg * sh.NB + lo;
+  G1Xyzz S = G1Xyzz::identity(), T = G1Xyzz::identity();
+  for (int b = (int)sh.chunk - 1; b >= 0; b--) {
+    G1Xyzz x = B[b];
+    g1_add(S, x);
+    g1_add(T, S);
+  }
+  if (lo) {
+    G1Xyzz ls = g1_mul_u32(S, lo);
+    g1_add(T, ls);
+  }
+  partials[g] = T;
+}
+
+// block per segment: sum its nchunks partials (serial per thread, then shared-memory tree)
+__global__ void __launch_bounds__(128)
+k_msm_reduce_segment(const G1Xyzz* __restrict__ partials, u32 nchunks, G1Xyzz* __restrict__ segsum) {
+  __shared__ G1Xyzz sh[128];
+  const G1Xyzz* P = partials + (size_t)blockIdx.x * nchunks;
+  G1Xyzz acc = G1Xyzz::identity();
+  for (u32 i = threadIdx.x; i < nchunks; i += blockDim.x) g1_add(acc, P[i]);
+  sh[threadIdx.x] = acc;
+  __syncthreads();
+  for (u32 s = blockDim.x / 2; s > 0; s >>= 1) {
+    if (threadIdx.x < s) {
+      G1Xyzz a = sh[threadIdx.x];
+      g1_add(a, sh[threadIdx.x + s]);
+      sh[threadIdx.x] = a;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) segsum[blockIdx.x] = sh[0];
+}
+
+// ---- 6. window combination + to-affine ----------------------------------------------------------
+__global__ void k_msm_combine(const G1Xyzz* __restrict__ segsum, MsmShape sh, size_t ncols, G1Affine* __restrict__ out) {
+  size_t col = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (col >= ncols) return;
+  const G1Xyzz* S = segsum + col * sh.W;
+  G1Xyzz acc = S[sh.W - 1];
+  for (int w = (int)sh.W - 2; w >= 0; w--) {
+    for (u32 i = 0; i < sh.c; i++) acc = g1_dbl(acc);
+    g1_add(acc, S[w]);
+  }
+  out[col] = g1_to_affine(acc);
+}
+
+__global__ void k_fill_identity(G1Affine* out, size_t n) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i < n) out[i] = G1Affine::identity();
+}
+
+// sum of n affine points -> 1 affine point (n is small: per-GPU partial sums)
+__global__ void k_g1_sum(const G1Affine* __restrict__ pts, size_t n, G1Affine* __restrict__ out) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    G1Xyzz acc = G1Xyzz::identity();
+    for (size_t i = 0; i < n; i++) g1_add_mixed(acc, pts[i]);
+    *out = g1_to_affine(acc);
+  }
+}
+
+int g1_sum_run(eon_ctx* ctx, const G1Affine* d_points, size_t n, G1Affine* d_out) {
+  k_g1_sum<<<1, 32, 0, ctx->stream>>>(d_points, n, d_out);
+  EON_LAUNCHED(ctx);
+  return EON_OK;
+}
+
+// ---- orchestration -----------------------------------------------------------------------------
+static int msm_batch(eon_ctx* ctx, const G1Affine* d_bases, const Fr* d_scalars, size_t n, size_t ncols, size_t ld,
+                     G1Affine* d_out) {
+  const MsmShape sh = msm_shape(n);
+  const size_t nseg = ncols * sh.W;
+  const size_t total_buckets = nseg * sh.NB;
+  const u32 chunk_min = 256;
+  size_t max_tasks_sz = (nseg * n) / chunk_min + 1024;
+  if (max_tasks_sz > 0x7fffffffull) max_tasks_sz = 0x7fffffffull;
+  const u32 max_tasks = (u32)max_tasks_sz;
+
+  void *p_dig, *p_hist, *p_cur, *p_ent, *p_bkt, *p_tasks, *p_tpart, *p_part, *p_seg, *p_misc;
+  EON_TRY(scratch_get(ctx, SC_MSM_DIGITS, nseg * n * sizeof(int16_t), &p_dig));
+  EON_TRY(scratch_get(ctx, SC_MSM_HIST, total_buckets * sizeof(u32), &p_hist));
+  EON_TRY(scratch_get(ctx, SC_MSM_CURSOR, total_buckets * sizeof(u32), &p_cur));
+  EON_TRY(scratch_get(ctx, SC_MSM_ENTRIES, nseg * n * sizeof(u32), &p_ent));
+  EON_TRY(scratch_get(ctx, SC_MSM_BUCKETS, total_buckets * sizeof(G1Xyzz), &p_bkt));
+  EON_TRY(scratch_get(ctx, SC_MSM_TASKS, (size_t)max_tasks * sizeof(MsmTask), &p_tasks));
+  EON_TRY(scratch_get(ctx, SC_MSM_TASKPART, (size_t)max_tasks * sizeof(G1Xyzz), &p_tpart));
+  EON_TRY(scratch_get(ctx, SC_MSM_PARTIALS, nseg * sh.nchunks * sizeof(G1Xyzz), &p_part));
+  EON_TRY(scratch_get(ctx, SC_MSM_SEGSUM, nseg * sizeof(G1Xyzz), &p_seg));
+  EON_TRY(scratch_get(ctx, SC_MSM_MISC, 256, &p_misc));
+  u32* d_ntasks = (u32*)p_misc;
+  cudaStream_t st = ctx->stream;
+
+  phase_begin(ctx, PH_MSM_DIGITS);
+  EON_CUDA(ctx, cudaMemsetAsync(p_hist, 0, total_buckets * sizeof(u32), st));
+  EON_CUDA(ctx, cudaMemsetAsync(d_ntasks, 0, sizeof(u32), st));
+  {
+    dim3 grid((unsigned)((n + MSM_THREADS - 1) / MSM_THREADS), (unsigned)ncols);
+    k_msm_digits<<<grid, MSM_THREADS, 0, st>>>(d_scalars, n, ld, sh, (int16_t*)p_dig, (u32*)p_hist);
+    EON_LAUNCHED(ctx);
+  }
+  phase_end(ctx, PH_MSM_DIGITS);
+
+  phase_begin(ctx, PH_MSM_SCAN);
+  k_msm_scan<<<(unsigned)nseg, 1024, 0, st>>>((u32*)p_hist, (u32*)p_cur, sh.NB);
+  EON_LAUNCHED(ctx);
+  phase_end(ctx, PH_MSM_SCAN);
+
+  phase_begin(ctx, PH_MSM_SCATTER);
+  {
+    dim3 grid((unsigned)((n + MSM_THREADS - 1) / MSM_THREADS), (unsigned)nseg);
+    k_msm_scatter<<<grid, MSM_THREADS, 0, st>>>((const int16_t*)p_dig, n, sh.NB, (u32*)p_cur, (u32*)p_ent);
+    EON_LAUNCHED(ctx);
+  }
+  phase_end(ctx, PH_MSM_SCATTER);
+
+  phase_begin(ctx, PH_MSM_ACCUM);
+  {
+    unsigned blocks = (unsigned)((total_buckets + MSM_THREADS - 1) / MSM_THREADS);
+    k_msm_accumulate<<<blocks, MSM_THREADS, 0, st>>>(d_bases, (const u32*)p_ent, n, (const u32*)p_hist,
+                                                     (const u32*)p_cur, sh.NB, total_buckets, chunk_min,
+                                                     (G1Xyzz*)p_bkt, (MsmTask*)p_tasks, d_ntasks, max_tasks);
+    EON_LAUNCHED(ctx);
+    unsigned tb = (unsigned)ctx->num_sms * 8;
+    k_msm_accumulate_tasks<<<tb, MSM_THREADS, 0, st>>>(d_bases, (const u32*)p_ent, n, (const MsmTask*)p_tasks,
+                                                       d_ntasks, max_tasks, (G1Xyzz*)p_tpart);
+    EON_LAUNCHED(ctx);
+    k_msm_fold_tasks<<<tb, MSM_THREADS, 0, st>>>((const MsmTask*)p_tasks, d_ntasks, max_tasks,
+                                                 (const G1Xyzz*)p_tpart, (G1Xyzz*)p_bkt);
+    EON_LAUNCHED(ctx);
+  }
+  phase_end(ctx, PH_MSM_ACCUM);
+
+  phase_begin(ctx, PH_MSM_REDUCE);
+  {
+    size_t threads = nseg * sh.nchunks;
+    unsigned blocks = (unsigned)((threads + MSM_THREADS - 1) / MSM_THREADS);
+    k_msm_reduce_chunks<<<blocks, MSM_THREADS, 0, st>>>((const G1Xyzz*)p_bkt, sh, nseg, (G1Xyzz*)p_part);
+    EON_LAUNCHED(ctx);
+    k_msm_reduce_segment<<<(unsigned)nseg, 128, 0, st>>>((const G1Xyzz*)p_part, sh.nchunks, (G1Xyzz*)p_seg);
+    EON_LAUNCHED(ctx);
+    k_msm_combine<<<(unsigned)((ncols + 31) / 32), 32, 0, st>>>((const G1Xyzz*)p_seg, sh, ncols, d_out);
+    EON_LAUNCHED(ctx);
+  }
+  phase_end(ctx, PH_MSM_REDUCE);
+  return EON_OK;
+}
+
+int msm_run(eon_ctx* ctx, const G1Affine* d_bases, const Fr* d_scalars, size_t n, size_t ncols, size_t ld,
+            G1Affine* d_out) {
+  if (ncols == 0) return EON_OK;
+  if (n == 0) {  // empty MSM -> identity (curve.rs:165-167)
+    k_fill_identity<<<(unsigned)((ncols + 255) / 256), 256, 0, ctx->stream>>>(d_out, ncols);
+    EON_LAUNCHED(ctx);
+    return EON_OK;
+  }
+  if (n >= 0x7fffffffull) return fail(ctx, EON_ERR_BAD_ARG, "msm: more than 2^31 - 1 points");
+  // column batches: bound the sort workspace (digits + entries = 6 bytes per (point, window))
+  const MsmShape sh = msm_shape(n);
+  size_t per_col = n * sh.W * 6 + (size_t)sh.W * sh.NB * (sizeof(G1Xyzz) + 8);
+  size_t budget = (size_t)12 << 30;
+  size_t batch = budget / per_col;
+  if (batch < 1) batch = 1;
+  if (batch > 64) batch = 64;
+  for (size_t c0 = 0; c0 < ncols; c0 += batch) {
+    size_t nc = std::min(batch, ncols - c0);
+    EON_TRY(msm_batch(ctx, d_bases, d_scalars + c0, n, nc, ld, d_out + c0));
+  }
+  return EON_OK;
+}
+
+// ---- synthetic SRS: g1_powers[i] = alpha^i * G (init_srs_unsafe, kzg/src/params.rs:123-139) ----
+__global__ void __launch_bounds__(128) k_srs_generate(G1Affine* out, size_t n, Fr alpha) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Fr s = fp_pow_u64(alpha, (u64)i);
+  u32 k[8];
+  fp_from_mont(k, s);
+  G1Xyzz p = g1_mul_canonical(G1Affine::generator(), k);
+  out[i] = g1_to_affine(p);
+}
+
+int srs_generate(eon_ctx* ctx, const Fr& alpha, size_t n) {
+  if (ctx->d_srs) {
+    EON_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    EON_CUDA(ctx, cudaFree(ctx->d_srs));
+    ctx->d_srs = nullptr;
+    ctx->srs_n = 0;
+  }
+  if (n == 0) return EON_OK;
+  EON_CUDA(ctx, cudaMalloc(&ctx->d_srs, n * sizeof(G1Affine)));
+  k_srs_generate<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(ctx->d_srs, n, alpha);
+  EON_LAUNCHED(ctx);
+  ctx->srs_n = n;
+  return EON_OK;
+}
+
+}  // namespace eon

@@ -1,0 +1,393 @@
+// Batched coset NTT over BN254 Fr on row-major matrices (sm_100a).
+//
+// Replaces the reference's CPU transforms behind TwoAdicSubgroupDft<Fr>:
+//   Radix2Dit::dft_batch            dft/src/radix_2_dit.rs:64-122   (log2(h) full-matrix passes)
+//   trait defaults                  dft/src/traits.rs:83-91,111-122,144-153,226-249
+//   divide_by_height / coset_shift  dft/src/util.rs:15-36
+//   reverse_matrix_index_bits       matrix/src/util.rs:36-56
+// with 2-3 HBM passes per transform: every pass stages a tile of 2^r rows x cv columns in
+// shared memory, runs r butterfly layers there and writes the tile back.  Bit-reversal,
+// zero-padding (as replication through the first added_bits layers), the coset shift (baked
+// into per-layer twiddles) and the 1/h scale are all fused into those passes.
+//
+// Forward transform  = DIT network, layers ascending, input in bit-reversed position order:
+//     (a, b) -> (a + t*b, a - t*b),  t = TW_l[j] = shift^(n/2^(l+1)) * omega_(2^(l+1))^j
+// Inverse transform  = the exact inverse network, layers descending, output bit-reversed:
+//     (u, v) -> (u + v, (u - v) * TW_l[j]^-1),  then one multiply by 1/n on the final store.
+// Both are exact field arithmetic, so results equal the reference's canonical limbs.
+#include "common.cuh"
+
+namespace eon {
+
+// ---- 16-byte unit helpers ---------------------------------------------------------------
+__device__ __forceinline__ Fr fr_from_units(const uint4& lo, const uint4& hi) {
+  Fr r;
+  r.v[0] = lo.x; r.v[1] = lo.y; r.v[2] = lo.z; r.v[3] = lo.w;
+  r.v[4] = hi.x; r.v[5] = hi.y; r.v[6] = hi.z; r.v[7] = hi.w;
+  return r;
+}
+__device__ __forceinline__ void fr_to_units(const Fr& a, uint4& lo, uint4& hi) {
+  lo = make_uint4(a.v[0], a.v[1], a.v[2], a.v[3]);
+  hi = make_uint4(a.v[4], a.v[5], a.v[6], a.v[7]);
+}
+__device__ __forceinline__ Fr fr_ldg(const uint4* p) {
+  uint4 lo = __ldg(p), hi = __ldg(p + 1);
+  return fr_from_units(lo, hi);
+}
+
+// ---- twiddle tables ---------------------------------------------------------------------
+// tw[(1<<l) - 1 + j] = base[l] * gen[l]^j   for l < log_n, j < 2^l
+__global__ void k_gen_twiddles(Fr* tw, u32 log_n, const Fr* __restrict__ base, const Fr* __restrict__ gen) {
+  u64 total = (1ull << log_n) - 1;
+  for (u64 idx = blockIdx.x * (u64)blockDim.x + threadIdx.x; idx < total; idx += (u64)gridDim.x * blockDim.x) {
+    u32 l = 63 - __clzll((long long)(idx + 1));
+    u64 j = idx + 1 - (1ull << l);
+    Fr g = gen[l];
+    Fr r = fp_mul(base[l], fp_pow_u64(g, j));
+    tw[idx] = r;
+  }
+}
+
+static int get_twiddles(eon_ctx* ctx, unsigned log_n, const Fr& shift, int inverse, const Fr** out) {
+  TwiddleKey key;
+  key.log_n = log_n;
+  key.inverse = inverse;
+  memcpy(key.shift, shift.v, 32);
+  auto it = ctx->twiddles.find(key);
+  if (it != ctx->twiddles.end()) {
+    *out = it->second;
+    return EON_OK;
+  }
+  if (log_n == 0) {
+    *out = nullptr;
+    return EON_OK;
+  }
+  phase_begin(ctx, PH_NTT_TWIDDLE);
+  // host: per-layer base and generator
+  std::vector<Fr> hb(2 * log_n);
+  Fr s = inverse ? fp_inv(shift) : shift;
+  std::vector<Fr> sq(log_n);
+  sq[0] = s;
+  for (unsigned i = 1; i < log_n; i++) sq[i] = fp_sqr(sq[i - 1]);
+  for (unsigned l = 0; l < log_n; l++) {
+    hb[l] = sq[log_n - 1 - l];
+    Fr g = fr_two_adic_generator(l + 1);
+    hb[log_n + l] = inverse ? fp_inv(g) : g;
+  }
+  Fr* d_tab = nullptr;
+  size_t entries = ((size_t)1 << log_n) - 1;
+  EON_CUDA(ctx, cudaMalloc(&d_tab, (entries + 1) * sizeof(Fr)));
+  void* d_small = nullptr;
+  EON_TRY(scratch_get(ctx, SC_SMALL, 2 * 32 * sizeof(Fr), &d_small));
+  EON_CUDA(ctx, cudaMemcpyAsync(d_small, hb.data(), hb.size() * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
+  // the host vector must outlive the async copy from pageable memory: cudaMemcpyAsync from
+  // pageable memory is staged before returning, so this is safe.
+  unsigned blocks = (unsigned)std::min<size_t>((entries + 255) / 256, (size_t)ctx->num_sms * 16);
+  if (blocks == 0) blocks = 1;
+  k_gen_twiddles<<<blocks, 256, 0, ctx->stream>>>(d_tab, log_n, (const Fr*)d_small, (const Fr*)d_small + log_n);
+  EON_LAUNCHED(ctx);
+  phase_end(ctx, PH_NTT_TWIDDLE);
+  ctx->twiddles[key] = d_tab;
+  *out = d_tab;
+  return EON_OK;
+}
+
+// ---- one HBM pass: r butterfly layers on a shared-memory tile -----------------------------
+struct PassParams {
+  const uint4* src;
+  uint4* dst;
+  const uint4* tw;
+  u64 V;        // virtual width = 2^l0 * w elements between consecutive tile rows
+  u64 tiles_v;  // ceil(V / cv)
+  u32 log_n, w;
+  int w_shift;  // log2(w) if w is a power of two, else -1
+  u32 l0, r;
+  u32 log_cv;
+  u32 k;        // source has 2^(log_n - k) rows; position p reads source row (p >> k)
+  int in_rev;   // ... bit-reversed over (log_n - k) bits
+  int out_rev;  // destination row = bitrev_{log_n}(position)   (only with l0 == 0)
+  int dif;      // 0: forward DIT butterflies, layers ascending; 1: inverse butterflies, descending
+  int scale;    // multiply every output by scale_c
+  Fr scale_c;
+};
+
+constexpr int NTT_THREADS = 256;
+constexpr u32 NTT_TILE_ELEMS = 2048;  // 64 KiB of shared memory per CTA -> 3 CTAs per SM
+
+__device__ __forceinline__ void split_vidx(const PassParams& p, u64 vidx, u64& lo, u32& col) {
+  if (p.w_shift >= 0) {
+    lo = vidx >> p.w_shift;
+    col = (u32)(vidx & (p.w - 1));
+  } else {
+    lo = vidx / p.w;
+    col = (u32)(vidx - lo * p.w);
+  }
+}
+
+__global__ void __launch_bounds__(NTT_THREADS, 3) k_ntt_pass(const PassParams p) {
+  extern __shared__ uint4 smem[];
+  const u32 R = 1u << p.r;
+  const u32 cv = 1u << p.log_cv;
+  const u32 tile_elems = R << p.log_cv;
+  uint4* s_lo = smem;
+  uint4* s_hi = smem + tile_elems;
+  const u32 tid = threadIdx.x;
+
+  const u64 tile = blockIdx.x;
+  const u64 vt = tile % p.tiles_v;
+  const u64 hi = tile / p.tiles_v;
+  const u64 v0 = vt << p.log_cv;
+  const u32 ncv = (u32)min((u64)cv, p.V - v0);
+  const u64 row_base = hi << p.r;  // tile row m is matrix "row group" row_base + m
+
+  // ---- load tile (16-byte units, consecutive threads -> consecutive units) ----
+  const bool plain_in = (p.k == 0 && !p.in_rev);
+  for (u32 u = tid; u < tile_elems * 2; u += NTT_THREADS) {
+    u32 e = u >> 1, half = u & 1;
+    u32 m = e >> p.log_cv, vc = e & (cv - 1);
+    if (vc >= ncv) continue;
+    u64 vidx = v0 + vc;
+    u64 src_elem;
+    if (plain_in) {
+      src_elem = (row_base + m) * p.V + vidx;
+    } else {
+      u64 lo;
+      u32 col;
+      split_vidx(p, vidx, lo, col);
+      u64 pos = ((row_base + m) << p.l0) + lo;
+      u64 srow = pos >> p.k;
+      if (p.in_rev) {
+        u32 bits = p.log_n - p.k;
+        srow = bits ? (u64)(__brev((u32)srow) >> (32 - bits)) : 0;
+      }
+      src_elem = srow * p.w + col;
+    }
+    uint4 val = p.src[src_elem * 2 + half];
+    (half ? s_hi : s_lo)[e] = val;
+  }
+  __syncthreads();
+
+  // ---- butterfly layers ----
+  const u32 nbf = tile_elems >> 1;
+  for (u32 step = 0; step < p.r; step++) {
+    const u32 t = p.dif ? (p.r - 1 - step) : step;
+    const u32 tmask = (1u << t) - 1;
+    const u64 tw_base = (1ull << (p.l0 + t)) - 1;
+    for (u32 idx = tid; idx < nbf; idx += NTT_THREADS) {
+      u32 vc = idx & (cv - 1);
+      if (vc >= ncv) continue;
+      u32 b = idx >> p.log_cv;
+      u32 i0 = ((b >> t) << (t + 1)) | (b & tmask);
+      u32 e0 = (i0 << p.log_cv) + vc;
+      u32 e1 = e0 + ((1u << t) << p.log_cv);
+      u64 j = (u64)(b & tmask) << p.l0;
+      if (p.l0) {
+        u64 lo;
+        u32 col;
+        split_vidx(p, v0 + vc, lo, col);
+        j += lo;
+      }
+      Fr tw = fr_ldg(p.tw + (tw_base + j) * 2);
+      Fr a = fr_from_units(s_lo[e0], s_hi[e0]);
+      Fr bb = fr_from_units(s_lo[e1], s_hi[e1]);
+      Fr o0, o1;
+      if (!p.dif) {
+        Fr x = fp_mul(bb, tw);
+        o0 = fp_add(a, x);
+        o1 = fp_sub(a, x);
+      } else {
+        o0 = fp_add(a, bb);
+        o1 = fp_mul(fp_sub(a, bb), tw);
+      }
+      fr_to_units(o0, s_lo[e0], s_hi[e0]);
+      fr_to_units(o1, s_lo[e1], s_hi[e1]);
+    }
+    __syncthreads();
+  }
+
+  // ---- store tile ----
+  if (!p.scale) {
+    for (u32 u = tid; u < tile_elems * 2; u += NTT_THREADS) {
+      u32 e = u >> 1, half = u & 1;
+      u32 m = e >> p.log_cv, vc = e & (cv - 1);
+      if (vc >= ncv) continue;
+      u64 vidx = v0 + vc;
+      u64 dst_elem;
+      if (p.out_rev) {
+        u64 pos = row_base + m;  // l0 == 0, V == w
+        u64 drow = p.log_n ? (u64)(__brev((u32)pos) >> (32 - p.log_n)) : 0;
+        dst_elem = drow * p.w + vidx;
+      } else {
+        dst_elem = (row_base + m) * p.V + vidx;
+      }
+      p.dst[dst_elem * 2 + half] = (half ? s_hi : s_lo)[e];
+    }
+  } else {
+    for (u32 e = tid; e < tile_elems; e += NTT_THREADS) {
+      u32 m = e >> p.log_cv, vc = e & (cv - 1);
+      if (vc >= ncv) continue;
+      u64 vidx = v0 + vc;
+      u64 dst_elem;
+      if (p.out_rev) {
+        u64 pos = row_base + m;
+        u64 drow = p.log_n ? (u64)(__brev((u32)pos) >> (32 - p.log_n)) : 0;
+        dst_elem = drow * p.w + vidx;
+      } else {
+        dst_elem = (row_base + m) * p.V + vidx;
+      }
+      Fr x = fp_mul(fr_from_units(s_lo[e], s_hi[e]), p.scale_c);
+      uint4 lo, hi4;
+      fr_to_units(x, lo, hi4);
+      p.dst[dst_elem * 2] = lo;
+      p.dst[dst_elem * 2 + 1] = hi4;
+    }
+  }
+}
+
+// ---- pass planning ------------------------------------------------------------------------
+struct PassPlan {
+  u32 l0, r, log_cv;
+};
+
+static u32 log_cv_for(u64 V) {
+  u32 lc = 0;
+  while (lc < 4 && (1ull << lc) < V) lc++;
+  return lc;  // cv = min(16, next_pow2(V))
+}
+static u32 ilog2_u32(u32 x) {
+  u32 l = 0;
+  while ((1u << (l + 1)) <= x) l++;
+  return l;
+}
+
+// split layers [first, last) into passes (ascending l0)
+static std::vector<PassPlan> plan_passes(u32 first, u32 last, size_t w) {
+  std::vector<PassPlan> out;
+  const u32 tile_log = ilog2_u32(NTT_TILE_ELEMS);
+  auto rmax_at = [&](u32 l0) {
+    u64 V = ((u64)w) << l0;
+    return tile_log - log_cv_for(V);
+  };
+  if (last <= first) {
+    out.push_back({first, 0, log_cv_for(((u64)w) << first)});
+    return out;
+  }
+  // greedy count
+  u32 n = 0;
+  for (u32 l = first; l < last; n++) l += std::min(rmax_at(l), last - l);
+  // even distribution subject to per-pass maxima
+  u32 l = first;
+  for (u32 i = 0; i < n; i++) {
+    u32 remaining = last - l;
+    u32 target = (remaining + (n - i) - 1) / (n - i);
+    u32 r = std::min(std::min(rmax_at(l), target), remaining);
+    out.push_back({l, r, log_cv_for(((u64)w) << l)});
+    l += r;
+  }
+  if (l < last) {  // distribution fell short because of a small early maximum: finish greedily
+    while (l < last) {
+      u32 r = std::min(rmax_at(l), last - l);
+      out.push_back({l, r, log_cv_for(((u64)w) << l)});
+      l += r;
+    }
+  }
+  return out;
+}
+
+static bool g_attr_set = false;
+
+static int launch_pass(eon_ctx* ctx, PassParams& p, const PassPlan& pl, unsigned log_n, size_t w) {
+  p.log_n = log_n;
+  p.w = (u32)w;
+  p.w_shift = (w & (w - 1)) == 0 ? (int)ilog2_u32((u32)w) : -1;
+  p.l0 = pl.l0;
+  p.r = pl.r;
+  p.log_cv = pl.log_cv;
+  p.V = ((u64)w) << pl.l0;
+  u64 cv = 1ull << pl.log_cv;
+  p.tiles_v = (p.V + cv - 1) / cv;
+  u64 tiles_hi = 1ull << (log_n - pl.l0 - pl.r);
+  u64 grid = tiles_hi * p.tiles_v;
+  if (grid == 0 || grid > 0x7fffffffull) return fail(ctx, EON_ERR_BAD_ARG, "ntt: grid too large");
+  size_t smem = ((size_t)1 << (pl.r + pl.log_cv)) * 32;
+  if (!g_attr_set) {
+    EON_CUDA(ctx, cudaFuncSetAttribute(k_ntt_pass, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)(NTT_TILE_ELEMS * 32)));
+    g_attr_set = true;
+  }
+  k_ntt_pass<<<(unsigned)grid, NTT_THREADS, smem, ctx->stream>>>(p);
+  EON_LAUNCHED(ctx);
+  return EON_OK;
+}
+
+int ntt_forward(eon_ctx* ctx, const Fr* d_src, Fr* d_dst, unsigned log_n, unsigned k, size_t width, const Fr& shift,
+                Layout src_layout) {
+  if (width == 0) return EON_OK;
+  if (log_n > 28) return fail(ctx, EON_ERR_TWO_ADICITY, "transform size exceeds 2^28 (Fr::TWO_ADICITY)");
+  if (k > log_n) return fail(ctx, EON_ERR_BAD_ARG, "ntt_forward: added bits exceed transform size");
+  if (width > 0xffffffffull) return fail(ctx, EON_ERR_BAD_ARG, "ntt: width too large");
+  const Fr* tw = nullptr;
+  EON_TRY(get_twiddles(ctx, log_n, shift, 0, &tw));
+  std::vector<PassPlan> plan = plan_passes(k, log_n, width);
+  phase_begin(ctx, PH_NTT_PASSES);
+  for (size_t i = 0; i < plan.size(); i++) {
+    PassParams p;
+    memset(&p, 0, sizeof(p));
+    p.tw = (const uint4*)tw;
+    p.dif = 0;
+    if (i == 0) {
+      p.src = (const uint4*)d_src;
+      p.k = k;
+      p.in_rev = (src_layout == LAYOUT_NATURAL) ? 1 : 0;
+    } else {
+      p.src = (const uint4*)d_dst;
+    }
+    p.dst = (uint4*)d_dst;
+    EON_TRY(launch_pass(ctx, p, plan[i], log_n, width));
+  }
+  phase_end(ctx, PH_NTT_PASSES);
+  return EON_OK;
+}
+
+int ntt_inverse(eon_ctx* ctx, const Fr* d_src, Fr* d_dst, unsigned log_n, size_t width, const Fr& shift,
+                Layout dst_layout) {
+  if (width == 0) return EON_OK;
+  if (log_n > 28) return fail(ctx, EON_ERR_TWO_ADICITY, "transform size exceeds 2^28 (Fr::TWO_ADICITY)");
+  if (width > 0xffffffffull) return fail(ctx, EON_ERR_BAD_ARG, "ntt: width too large");
+  const Fr* tw = nullptr;
+  EON_TRY(get_twiddles(ctx, log_n, shift, 1, &tw));
+  std::vector<PassPlan> plan = plan_passes(0, log_n, width);
+  const size_t np = plan.size();
+  const bool out_rev = (dst_layout == LAYOUT_NATURAL);
+  Fr* work = d_dst;
+  if (np > 1 && out_rev) {
+    void* tmp = nullptr;
+    EON_TRY(scratch_get(ctx, SC_NTT_TMP, ((size_t)width << log_n) * sizeof(Fr), &tmp));
+    work = (Fr*)tmp;
+  }
+  Fr n_inv = Fr::one();
+  if (log_n) n_inv = fp_inv(fp_from_u64<FrParams>(1ull << log_n));
+  phase_begin(ctx, PH_NTT_PASSES);
+  for (size_t s = 0; s < np; s++) {
+    const PassPlan& pl = plan[np - 1 - s];  // descending layers
+    PassParams p;
+    memset(&p, 0, sizeof(p));
+    p.tw = (const uint4*)tw;
+    p.dif = 1;
+    const bool last = (s == np - 1);
+    p.src = (const uint4*)(s == 0 ? d_src : work);
+    p.dst = (uint4*)(last ? d_dst : work);
+    if (last) {
+      p.out_rev = out_rev ? 1 : 0;
+      if (log_n) {
+        p.scale = 1;
+        p.scale_c = n_inv;
+      }
+    }
+    EON_TRY(launch_pass(ctx, p, pl, log_n, width));
+  }
+  phase_end(ctx, PH_NTT_PASSES);
+  return EON_OK;
+}
+
+}  // namespace eon

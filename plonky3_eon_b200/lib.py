@@ -1,0 +1,207 @@
+"""ctypes binding of libeon_kzg.so (the C ABI in include/eon_kzg.h).
+
+This is the Python equivalent of the `extern "C"` block a Rust `-sys` crate would hold
+(INTEGRATION.md shows that Rust form).  There is NO CPU fallback: if the library is missing
+or no sm_100 device is usable, everything raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libeon_kzg.so")
+
+EON_OK = 0
+EON_ERR_BAD_ARG = -1
+EON_ERR_SRS_TOO_SHORT = -2
+EON_ERR_CUDA = -3
+EON_ERR_OOM = -4
+EON_ERR_BAD_HANDLE = -5
+EON_ERR_TWO_ADICITY = -6
+
+_u64p = C.c_void_p  # all buffers are passed as raw addresses
+_SIGS = {
+    "eon_version": (C.c_char_p, []),
+    "eon_ctx_create": (C.c_int, [C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "eon_ctx_destroy": (None, [C.c_void_p]),
+    "eon_last_error": (C.c_char_p, [C.c_void_p]),
+    "eon_ctx_sync": (C.c_int, [C.c_void_p]),
+    "eon_ctx_launch_count": (C.c_uint64, [C.c_void_p]),
+    "eon_dev_alloc": (C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]),
+    "eon_dev_free": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "eon_h2d": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "eon_d2h": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "eon_dft_batch_dev": (C.c_int, [C.c_void_p, _u64p, _u64p, C.c_uint, C.c_size_t]),
+    "eon_coset_dft_batch_dev": (C.c_int, [C.c_void_p, _u64p, _u64p, C.c_uint, C.c_size_t, _u64p]),
+    "eon_idft_batch_dev": (C.c_int, [C.c_void_p, _u64p, _u64p, C.c_uint, C.c_size_t]),
+    "eon_coset_idft_batch_dev": (C.c_int, [C.c_void_p, _u64p, _u64p, C.c_uint, C.c_size_t, _u64p]),
+    "eon_coset_lde_batch_dev": (C.c_int, [C.c_void_p, _u64p, _u64p, C.c_uint, C.c_size_t, C.c_uint, _u64p]),
+    "eon_dft_batch": (C.c_int, [C.c_void_p, _u64p, _u64p, C.c_uint, C.c_size_t]),
+    "eon_coset_dft_batch": (C.c_int, [C.c_void_p, _u64p, _u64p, C.c_uint, C.c_size_t, _u64p]),
+    "eon_idft_batch": (C.c_int, [C.c_void_p, _u64p, _u64p, C.c_uint, C.c_size_t]),
+    "eon_coset_idft_batch": (C.c_int, [C.c_void_p, _u64p, _u64p, C.c_uint, C.c_size_t, _u64p]),
+    "eon_coset_lde_batch": (C.c_int, [C.c_void_p, _u64p, _u64p, C.c_uint, C.c_size_t, C.c_uint, _u64p]),
+    "eon_srs_load_affine": (C.c_int, [C.c_void_p, _u64p, C.c_size_t]),
+    "eon_srs_generate_unsafe": (C.c_int, [C.c_void_p, _u64p, C.c_size_t]),
+    "eon_srs_size": (C.c_size_t, [C.c_void_p]),
+    "eon_srs_read": (C.c_int, [C.c_void_p, C.c_size_t, C.c_size_t, _u64p]),
+    "eon_msm_srs_dev": (C.c_int, [C.c_void_p, _u64p, C.c_size_t, C.c_size_t, C.c_size_t, _u64p]),
+    "eon_msm_srs": (C.c_int, [C.c_void_p, _u64p, C.c_size_t, C.c_size_t, C.c_size_t, _u64p]),
+    "eon_msm_points": (C.c_int, [C.c_void_p, _u64p, _u64p, C.c_size_t, _u64p]),
+    "eon_msm_srs_range_dev": (C.c_int, [C.c_void_p, _u64p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t, _u64p]),
+    "eon_g1_sum": (C.c_int, [C.c_void_p, _u64p, C.c_size_t, _u64p]),
+    "eon_kzg_commit": (C.c_int, [C.c_void_p, _u64p, C.c_uint, C.c_size_t, _u64p, _u64p, C.POINTER(C.c_uint64)]),
+    "eon_kzg_commit_dev": (C.c_int, [C.c_void_p, _u64p, C.c_uint, C.c_size_t, _u64p, _u64p, C.POINTER(C.c_uint64)]),
+    "eon_kzg_read_coeffs": (C.c_int, [C.c_void_p, C.c_uint64, _u64p]),
+    "eon_kzg_evals_on_coset": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint, _u64p, _u64p]),
+    "eon_kzg_evals_on_coset_dev": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint, _u64p, _u64p]),
+    "eon_kzg_open": (C.c_int, [C.c_void_p, C.c_uint64, _u64p, C.c_size_t, _u64p, _u64p]),
+    "eon_handle_dims": (C.c_int, [C.c_void_p, C.c_uint64, C.POINTER(C.c_uint), C.POINTER(C.c_size_t)]),
+    "eon_handle_free": (C.c_int, [C.c_void_p, C.c_uint64]),
+    "eon_quotient_and_eval_dev": (C.c_int, [C.c_void_p, _u64p, C.c_size_t, C.c_size_t, _u64p, _u64p, _u64p]),
+    "eon_bench_imad_peak": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_double)]),
+    "eon_bench_modmul": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_double)]),
+    "eon_last_phase_ms": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_float)]),
+    "eon_phase_name": (C.c_char_p, [C.c_int]),
+}
+
+EXPORTED_SYMBOLS = tuple(_SIGS)
+_lib = None
+
+
+class EonError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"eon_kzg error {code}: {msg}")
+        self.code = code
+
+
+class DegreeTooLarge(EonError):
+    """KzgError::DegreeTooLarge (kzg/src/params.rs:164-173); the reference's prover unwraps it
+    into a panic (kzg/src/pcs.rs:238-240)."""
+
+
+def load():
+    """Load libeon_kzg.so; raises if it has not been built (no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a).  There is no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in _SIGS.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def ptr(x):
+    """Raw address of a numpy array / int / None."""
+    if x is None:
+        return None
+    if isinstance(x, np.ndarray):
+        assert x.flags["C_CONTIGUOUS"], "buffer must be C-contiguous"
+        return x.ctypes.data
+    return int(x)
+
+
+class Context:
+    """One eon_ctx (one GPU).  Mirrors the process-global state the reference keeps inside
+    Radix2Dit (twiddle cache) and KzgPcs (SRS)."""
+
+    def __init__(self, device=0, stream=None):
+        self.lib = load()
+        h = C.c_void_p()
+        rc = self.lib.eon_ctx_create(int(device), C.c_void_p(stream or 0), C.byref(h))
+        if rc != EON_OK or not h.value:
+            raise EonError(rc, "eon_ctx_create failed: no usable sm_100 CUDA device (there is no CPU fallback)")
+        self.h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "h", None) is not None and self.h.value:
+            self.lib.eon_ctx_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def check(self, rc):
+        if rc == EON_OK:
+            return
+        msg = self.lib.eon_last_error(self.h).decode()
+        if rc == EON_ERR_SRS_TOO_SHORT:
+            raise DegreeTooLarge(rc, msg)
+        raise EonError(rc, msg)
+
+    def call(self, name, *args):
+        """Call an ABI function.  numpy arrays may be passed directly: they are converted to raw
+        addresses here and kept alive (via `args`) until the call returns."""
+        conv = []
+        for a in args:
+            if isinstance(a, np.ndarray):
+                assert a.flags["C_CONTIGUOUS"], "buffer must be C-contiguous"
+                conv.append(C.c_void_p(a.ctypes.data))
+            else:
+                conv.append(a)
+        self.check(getattr(self.lib, name)(self.h, *conv))
+
+    # -- tiny conveniences -----------------------------------------------------------------
+    def sync(self):
+        self.call("eon_ctx_sync")
+
+    def launch_count(self):
+        return int(self.lib.eon_ctx_launch_count(self.h))
+
+    def srs_size(self):
+        return int(self.lib.eon_srs_size(self.h))
+
+    def dev_alloc(self, nbytes):
+        p = C.c_void_p()
+        self.call("eon_dev_alloc", nbytes, C.byref(p))
+        return p.value
+
+    def dev_free(self, p):
+        self.call("eon_dev_free", C.c_void_p(p))
+
+    def h2d(self, dptr, arr):
+        self.call("eon_h2d", C.c_void_p(dptr), arr, arr.nbytes)
+
+    def d2h(self, arr, dptr):
+        self.call("eon_d2h", arr, C.c_void_p(dptr), arr.nbytes)
+
+    def phase_ms(self):
+        out = {}
+        v = C.c_float()
+        for ph in range(8):
+            self.call("eon_last_phase_ms", ph, C.byref(v))
+            out[self.lib.eon_phase_name(ph).decode()] = float(v.value)
+        return out
+
+    def imad_peak_tops(self, kind=0):
+        v = C.c_double()
+        self.call("eon_bench_imad_peak", kind, C.byref(v))
+        return float(v.value)
+
+    def modmul_gmuls(self, field=1):
+        v = C.c_double()
+        self.call("eon_bench_modmul", field, C.byref(v))
+        return float(v.value)
+
+
+_default_ctx = {}
+
+
+def default_context(device=0):
+    """Lazily-created per-device context (TwoAdicSubgroupDft: Clone + Default needs a
+    process-global, SURVEY §7 hard part 7)."""
+    if device not in _default_ctx:
+        _default_ctx[device] = Context(device)
+    return _default_ctx[device]

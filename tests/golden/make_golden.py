@@ -1,0 +1,65 @@
+"""Generates tests/golden/kzg_small.npz from the big-int oracle (oracle/), which is itself pinned
+to the reference's known-answer tests (tests/test_oracle.py).  The reference is Rust and cannot be
+built in this image, so these are oracle-generated fixtures, not outputs of the reference binary.
+
+    python tests/golden/make_golden.py
+
+Shapes follow the reference's own tests: DFT conformance h = 16, w = 3, shift = GENERATOR
+(field-testing/src/dft_testing.rs:9-112); KZG with SRS 1024-style alpha = 12345
+(eon-uni-stark/tests/fib_air.rs:112-136) on an 8 x 2 trace, opened at zeta and zeta*omega.
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle import dft, fr, g1, kzg  # noqa: E402
+
+
+def main():
+    rng = np.random.default_rng(1)
+    out = {}
+    # ---- DFT family, h = 16, w = 3 --------------------------------------------------------
+    h, w = 16, 3
+    x_w = fr.random_wire(rng, h * w).reshape(h, w, 4)
+    x = dft.mat_from_wire(x_w)
+    s = fr.GENERATOR
+    out["dft_in"] = x_w
+    out["dft_out"] = dft.mat_to_wire(dft.dft_batch(x))
+    out["coset_dft_out"] = dft.mat_to_wire(dft.coset_dft_batch(x, s))
+    out["idft_out"] = dft.mat_to_wire(dft.idft_batch(x))
+    out["coset_idft_out"] = dft.mat_to_wire(dft.coset_idft_batch(x, s))
+    out["coset_lde1_out"] = dft.mat_to_wire(dft.coset_lde_batch(x, 1, s))
+    out["lde2_out"] = dft.mat_to_wire(dft.lde_batch(x, 2))
+    # ---- KZG, 8 x 2, alpha = 12345 ---------------------------------------------------------
+    alpha = 12345
+    srs = kzg.init_srs_unsafe(15, alpha)
+    out["srs"] = g1.to_wire(srs)
+    ev_w = fr.random_wire(rng, 8 * 2).reshape(8, 2, 4)
+    ev = dft.mat_from_wire(ev_w)
+    dom = (1, 3)
+    commits, pdata = kzg.commit(srs, [(dom, ev)], fast=False)
+    out["kzg_evals"] = ev_w
+    out["kzg_coeffs"] = dft.mat_to_wire(pdata[0]["coeffs"])
+    out["kzg_commit"] = g1.to_wire(commits[0])
+    zeta = fr.from_wire(fr.random_wire(rng, 1))[0]
+    zeta_next = zeta * fr.two_adic_generator(3) % fr.P
+    opened, wits = kzg.open_(srs, [(pdata, [[zeta, zeta_next]])])
+    out["kzg_points"] = fr.to_wire([zeta, zeta_next])
+    out["kzg_opened"] = np.stack([fr.to_wire(v) for v in opened[0][0]])
+    out["kzg_witness"] = np.stack([g1.to_wire(p) for p in wits[0][0]])
+    qdom = (fr.GENERATOR, 4)
+    out["kzg_evals_on_quotient_domain"] = dft.mat_to_wire(kzg.get_evaluations_on_domain(pdata[0], qdom))
+    # shifted-domain commit (quotient chunk style): shift = 5 * omega_16
+    sh = fr.GENERATOR * fr.two_adic_generator(4) % fr.P
+    commits2, pdata2 = kzg.commit(srs, [((sh, 3), ev)], fast=False)
+    out["kzg_shift"] = fr.to_wire([sh])
+    out["kzg_commit_shifted"] = g1.to_wire(commits2[0])
+    np.savez_compressed(os.path.join(os.path.dirname(os.path.abspath(__file__)), "kzg_small.npz"), **out)
+    print("wrote kzg_small.npz:", {k: v.shape for k, v in out.items()})
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,70 @@
+// Host-compiled view of csrc/fp.cuh + ec.cuh (software carry flag) so that the field and
+// curve arithmetic shipped in the CUDA library can be checked against the oracle without a GPU.
+#include "../../plonky3_eon_b200/csrc/ec.cuh"
+#include <string.h>
+using namespace eon;
+
+template <class F> static F ld(const uint32_t* p) { F x; memcpy(x.v, p, 32); return x; }
+template <class F> static void st(uint32_t* p, const F& x) { memcpy(p, x.v, 32); }
+
+extern "C" {
+// which: 0 = Fr, 1 = Fq.  op: 0 mul, 1 add, 2 sub, 3 neg, 4 inv, 5 from_mont, 6 to_mont, 7 sqr
+void host_fp_op(int which, int op, const uint32_t* a, const uint32_t* b, uint32_t* r, int n) {
+  for (int i = 0; i < n; i++, a += 8, b += 8, r += 8) {
+    if (which == 0) {
+      Fr x = ld<Fr>(a), y = ld<Fr>(b), z;
+      switch (op) {
+        case 0: z = fp_mul(x, y); break;
+        case 1: z = fp_add(x, y); break;
+        case 2: z = fp_sub(x, y); break;
+        case 3: z = fp_neg(x); break;
+        case 4: z = fp_inv(x); break;
+        case 5: fp_from_mont(z.v, x); break;
+        case 6: z = fp_to_mont<FrParams>(x.v); break;
+        default: z = fp_sqr(x);
+      }
+      st(r, z);
+    } else {
+      Fq x = ld<Fq>(a), y = ld<Fq>(b), z;
+      switch (op) {
+        case 0: z = fp_mul(x, y); break;
+        case 1: z = fp_add(x, y); break;
+        case 2: z = fp_sub(x, y); break;
+        case 3: z = fp_neg(x); break;
+        case 4: z = fp_inv(x); break;
+        case 5: fp_from_mont(z.v, x); break;
+        case 6: z = fp_to_mont<FqParams>(x.v); break;
+        default: z = fp_sqr(x);
+      }
+      st(r, z);
+    }
+  }
+}
+
+static G1Affine lda(const uint32_t* p) { G1Affine a; memcpy(a.x.v, p, 32); memcpy(a.y.v, p + 8, 32); return a; }
+static void sta(uint32_t* p, const G1Affine& a) { memcpy(p, a.x.v, 32); memcpy(p + 8, a.y.v, 32); }
+
+// r = sum of n affine points, via mixed adds (exercises identity / doubling / inverse branches)
+void host_g1_sum(const uint32_t* pts, int n, uint32_t* r) {
+  G1Xyzz acc = G1Xyzz::identity();
+  for (int i = 0; i < n; i++) g1_add_mixed(acc, lda(pts + 16 * i));
+  sta(r, g1_to_affine(acc));
+}
+// r = (a0 + a1) + (b0 + b1) using the full XYZZ+XYZZ addition
+void host_g1_add_full(const uint32_t* a0, const uint32_t* a1, const uint32_t* b0, const uint32_t* b1, uint32_t* r) {
+  G1Xyzz A = G1Xyzz::identity(), B = G1Xyzz::identity();
+  g1_add_mixed(A, lda(a0)); g1_add_mixed(A, lda(a1));
+  g1_add_mixed(B, lda(b0)); g1_add_mixed(B, lda(b1));
+  g1_add(A, B);
+  sta(r, g1_to_affine(A));
+}
+// r = k * p, k canonical 256-bit
+void host_g1_mul(const uint32_t* p, const uint32_t* k, uint32_t* r) {
+  sta(r, g1_to_affine(g1_mul_canonical(lda(p), k)));
+}
+void host_g1_mul_u32(const uint32_t* p, uint32_t k, uint32_t* r) {
+  G1Xyzz P = G1Xyzz::from_affine(lda(p));
+  P = g1_dbl(P);  // make it non-trivially projective: computes k * (2p)
+  sta(r, g1_to_affine(g1_mul_u32(P, k)));
+}
+}

@@ -1,0 +1,301 @@
+"""GPU parity: G1::multi_exp, SRS generation and the KzgPcs commit / evaluate / open path through the
+C ABI vs the oracle.  Bit-exact (affine G1 wire points and canonical Fr limbs compared directly).
+
+Mirrors bn254/src/curve.rs:597-628 (multi_exp KATs), kzg/src/tests.rs:19-171 (KZG vectors) and
+the shapes of eon-uni-stark/tests/fib_air.rs:112-136 (heights 1 and 8, alpha = 12345).
+"""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import dft as odft
+from oracle import fr, g1, kzg as okzg
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "kzg_small.npz")
+P = fr.P
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from plonky3_eon_b200 import Context
+    c = Context(0)
+    yield c
+    c.close()
+
+
+def pcs_new(ctx, max_degree, alpha):
+    from plonky3_eon_b200 import GpuKzgPcs
+    return GpuKzgPcs.new(max_degree, alpha, ctx=ctx)
+
+
+def pt(wire):
+    return g1.from_wire(np.asarray(wire).reshape(1, 8))[0]
+
+
+def kG(k):
+    return g1.mul(g1.G, k)
+
+
+# ---- bn254/src/curve.rs:597-628 ----------------------------------------------------------------
+def test_multi_exp_kats(ctx):
+    from plonky3_eon_b200 import GpuKzgPcs
+    pcs = GpuKzgPcs(ctx)
+    assert pt(pcs.multi_exp(np.zeros((0, 8), np.uint64), np.zeros((0, 4), np.uint64))) is None
+    assert pt(pcs.multi_exp(g1.to_wire([g1.G]), fr.to_wire([5]))) == kG(5)
+    assert pt(pcs.multi_exp(g1.to_wire([g1.G, g1.G]), fr.to_wire([2, 3]))) == kG(5)
+    assert pt(pcs.multi_exp(g1.to_wire([kG(7), kG(11)]), fr.to_wire([3, 5]))) == kG(76)
+    with pytest.raises(AssertionError):
+        pcs.multi_exp(g1.to_wire([g1.G]), fr.to_wire([1, 2]))
+
+
+def test_multi_exp_edge_cases(ctx):
+    from plonky3_eon_b200 import GpuKzgPcs
+    pcs = GpuKzgPcs(ctx)
+    A, B = kG(1234567), kG(987654321)
+    cases = [
+        ([A, g1.neg(A)], [9, 9], None),                          # P + (-P)
+        ([A, A, A], [1, 1, 1], g1.mul(A, 3)),                    # doubling inside one bucket
+        ([A, B], [0, 0], None),                                  # zero scalars
+        ([None, A, None], [5, 7, 9], g1.mul(A, 7)),              # identity points
+        ([A, B], [P - 1, 1], g1.add(g1.neg(A), B)),              # -1 scalar (top signed digits)
+        ([A], [(1 << 253) + 12345], g1.mul(A, (1 << 253) + 12345)),
+        ([A, B], [0xFFFF, 0x8000], g1.add(g1.mul(A, 0xFFFF), g1.mul(B, 0x8000))),  # digit carry edges
+    ]
+    for pts, sc, want in cases:
+        got = pt(pcs.multi_exp(g1.to_wire(pts), fr.to_wire(sc)))
+        assert got == want, (sc,)
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 17, 64, 100, 257])
+def test_multi_exp_random_small(ctx, n):
+    from plonky3_eon_b200 import GpuKzgPcs
+    pcs = GpuKzgPcs(ctx)
+    rng = np.random.default_rng(n)
+    dl = [int.from_bytes(rng.bytes(32), "little") % P for _ in range(n)]
+    pts = [kG(d) for d in dl]
+    scw = fr.random_wire(rng, n)
+    sc = fr.from_wire(scw)
+    assert pt(pcs.multi_exp(g1.to_wire(pts), scw)) == g1.msm_via_dlog(dl, sc)
+
+
+# ---- SRS generation (kzg/src/params.rs:123-139) -------------------------------------------------
+def test_srs_generate_matches_oracle(ctx):
+    pcs = pcs_new(ctx, 40, 12345)
+    assert pcs.max_degree == 40
+    got = g1.from_wire(pcs.g1_powers())
+    assert got == okzg.init_srs_unsafe(40, 12345)
+    pcs0 = pcs_new(ctx, 3, 0)  # alpha = 0: [G, O, O, O]
+    assert g1.from_wire(pcs0.g1_powers()) == [g1.G, None, None, None]
+
+
+# ---- MSM over the SRS at scale, checked with the discrete-log shortcut -----------------------------
+@pytest.mark.parametrize("log_n,ncols", [(10, 3), (13, 2), (16, 2), (18, 1)])
+def test_msm_srs_dlog_shortcut(ctx, log_n, ncols):
+    n = 1 << log_n
+    alpha = 987654321
+    pcs = pcs_new(ctx, n - 1, alpha)
+    rng = np.random.default_rng(log_n)
+    sc = fr.random_wire(rng, n * ncols).reshape(n, ncols, 4)
+    out = np.zeros((ncols, 8), dtype=np.uint64)
+    ctx.call("eon_msm_srs", sc, n, ncols, ncols, out)
+    dl = okzg.srs_dlogs(n - 1, alpha)
+    for c in range(ncols):
+        col = fr.from_wire(sc[:, c, :])
+        assert pt(out[c]) == g1.msm_via_dlog(dl, col), c
+
+
+@pytest.mark.parametrize("kind", ["zeros", "ones", "equal", "one_bit", "small64", "fib", "few_buckets"])
+def test_msm_skewed_scalars(ctx, kind):
+    # SURVEY §7 hard part 4: structured traces concentrate in few buckets (oversized-bucket path)
+    n = 1 << 14
+    alpha = 31337
+    pcs = pcs_new(ctx, n - 1, alpha)
+    rng = np.random.default_rng(5)
+    if kind == "zeros":
+        vals = [0] * n
+    elif kind == "ones":
+        vals = [1] * n
+    elif kind == "equal":
+        vals = [int.from_bytes(rng.bytes(31), "little")] * n
+    elif kind == "one_bit":
+        vals = [1 << int(b) for b in rng.integers(0, 253, size=n)]
+    elif kind == "small64":
+        vals = [int(v) for v in rng.integers(0, 1 << 63, size=n)]
+    elif kind == "fib":
+        vals, a, b = [], 0, 1
+        for _ in range(n):
+            vals.append(a)
+            a, b = b, (a + b) % P
+    else:
+        vals = [int(v) * 0x10001 for v in rng.integers(1, 4, size=n)]
+    out = pcs.commit_column(fr.to_wire(vals))
+    assert pt(out) == g1.msm_via_dlog(okzg.srs_dlogs(n - 1, alpha), vals)
+
+
+# ---- kzg/src/tests.rs ---------------------------------------------------------------------------
+def test_kzg_batch_verification_vectors(ctx):
+    # tests.rs:73-137: alpha = 42
+    pcs = pcs_new(ctx, 16, 42)
+    assert pt(pcs.commit_column(fr.to_wire([1, 2, 3]))) == kG(5377)
+    assert pt(pcs.commit_column(fr.to_wire([5, 7, 11]))) == kG(19703)
+    assert pt(pcs.commit_column(fr.to_wire([8, 3]))) == kG(134)
+    assert pt(pcs.commit_column(fr.to_wire([40, 11]))) == kG(502)
+    # tests.rs:149-171: alpha = 999
+    pcs = pcs_new(ctx, 8, 999)
+    assert pt(pcs.commit_column(fr.to_wire([1, 2]))) == kG(1999)
+    assert pt(pcs.commit_column(fr.to_wire([2]))) == kG(2)
+    assert pt(pcs.commit_column(np.zeros((0, 4), np.uint64))) is None
+
+
+def test_pcs_roundtrip_vector(ctx):
+    # tests.rs:19-48: alpha = 7, evals x + 1 on the size-8 subgroup, opened at 2
+    from plonky3_eon_b200 import TwoAdicMultiplicativeCoset
+    pcs = pcs_new(ctx, 8, 7)
+    dom = TwoAdicMultiplicativeCoset(1, 3)
+    evals = odft.mat_to_wire([[(x + 1) % P] for x in okzg.coset_points(1, 3)])
+    commit, pdata = pcs.commit([(dom, evals)])
+    assert odft.mat_from_wire(pdata[0].coeffs()) == [[1], [1]] + [[0]] * 6
+    assert pt(commit[0][0]) == kG(8)
+    opened, proof = pcs.open([(pdata, [[2]])])
+    assert fr.from_wire(opened[0][0][0]) == [3]
+    assert pt(proof[0][0][0][0]) == g1.G
+    # degree guard: pcs.rs:238-240 / params.rs:164-173
+    from plonky3_eon_b200 import DegreeTooLarge
+    big = odft.mat_to_wire([[1]] * 16)
+    with pytest.raises(DegreeTooLarge):
+        pcs.commit([(TwoAdicMultiplicativeCoset(1, 4), big)])
+    with pytest.raises(AssertionError):  # pcs.rs:233-237
+        pcs.commit([(TwoAdicMultiplicativeCoset(1, 2), evals)])
+
+
+def test_golden_fixture(ctx):
+    from plonky3_eon_b200 import GpuKzgPcs, TwoAdicMultiplicativeCoset
+    g = np.load(GOLD)
+    pcs = GpuKzgPcs.from_srs(g["srs"], ctx=ctx)
+    dom = TwoAdicMultiplicativeCoset(1, 3)
+    commit, pdata = pcs.commit([(dom, g["kzg_evals"])])
+    assert np.array_equal(commit[0], g["kzg_commit"])
+    assert np.array_equal(pdata[0].coeffs(), g["kzg_coeffs"])
+    opened, proof = pcs.open([(pdata, [[g["kzg_points"][0], g["kzg_points"][1]]])])
+    assert np.array_equal(np.stack(opened[0][0]), g["kzg_opened"])
+    assert np.array_equal(np.stack(proof[0][0]), g["kzg_witness"])
+    qdom = dom.create_disjoint_domain(16)
+    assert (qdom.shift, qdom.log_size) == (fr.GENERATOR, 4)
+    assert np.array_equal(pcs.get_evaluations_on_domain(pdata, 0, qdom), g["kzg_evals_on_quotient_domain"])
+    assert np.array_equal(pcs.get_evaluations_on_domain(pdata, 0, dom), g["kzg_evals"])
+    sh = fr.from_wire(g["kzg_shift"])[0]
+    commit2, _ = pcs.commit([(TwoAdicMultiplicativeCoset(sh, 3), g["kzg_evals"])])
+    assert np.array_equal(commit2[0], g["kzg_commit_shifted"])
+
+
+@pytest.mark.parametrize("log_h,w", [(0, 2), (1, 1), (3, 3), (6, 4)])
+def test_commit_open_vs_oracle(ctx, log_h, w):
+    # heights 1 and 8 are the reference's end-to-end shapes (eon-uni-stark/tests/fib_air.rs:127-131)
+    from plonky3_eon_b200 import TwoAdicMultiplicativeCoset
+    h = 1 << log_h
+    alpha = 12345
+    pcs = pcs_new(ctx, max(h - 1, 1), alpha)
+    srs = okzg.init_srs_unsafe(max(h - 1, 1), alpha)
+    rng = np.random.default_rng(log_h * 10 + w)
+    evw = fr.random_wire(rng, h * w).reshape(h, w, 4)
+    ev = odft.mat_from_wire(evw)
+    dom = TwoAdicMultiplicativeCoset(1, log_h)
+    commit, pdata = pcs.commit([(dom, evw)])
+    ocommit, opdata = okzg.commit(srs, [((1, log_h), ev)])
+    assert g1.from_wire(commit[0]) == ocommit[0]
+    assert odft.mat_from_wire(pdata[0].coeffs()) == opdata[0]["coeffs"]
+    zeta = int.from_bytes(rng.bytes(31), "little")
+    pts = [zeta, dom.next_point(zeta)]
+    opened, proof = pcs.open([(pdata, [pts])])
+    oopened, owits = okzg.open_(srs, [(opdata, [pts])])
+    for i in range(2):
+        assert fr.from_wire(opened[0][0][i]) == oopened[0][0][i]
+        assert g1.from_wire(proof[0][0][i]) == owits[0][0][i]
+    qdom = dom.create_disjoint_domain(2 * h)
+    got = pcs.get_evaluations_on_domain(pdata, 0, qdom)
+    assert odft.mat_from_wire(got) == okzg.get_evaluations_on_domain(opdata[0], (qdom.shift, qdom.log_size))
+    pdata[0].free()
+
+
+def test_commit_quotient_chunks(ctx):
+    # commit/src/pcs.rs:82-102 + commit/src/domain.rs:174-221
+    from plonky3_eon_b200 import TwoAdicMultiplicativeCoset
+    alpha = 12345
+    pcs = pcs_new(ctx, 15, alpha)
+    srs = okzg.init_srs_unsafe(15, alpha)
+    rng = np.random.default_rng(77)
+    qdom = TwoAdicMultiplicativeCoset(fr.GENERATOR, 4)
+    qw = fr.random_wire(rng, 16).reshape(16, 1, 4)
+    q = odft.mat_from_wire(qw)
+    commit, pdata = pcs.commit_quotient(qdom, qw, 2)
+    doms = okzg.split_domains((fr.GENERATOR, 4), 2)
+    subs = okzg.split_evals(2, q)
+    ocommit, _ = okzg.commit(srs, list(zip(doms, subs)))
+    assert len(commit) == 2
+    for m in range(2):
+        assert (pdata[m].domain.shift, pdata[m].domain.log_size) == doms[m]
+        assert g1.from_wire(commit[m]) == ocommit[m]
+
+
+def test_quotient_scan_large(ctx):
+    # quotient_and_eval (kzg/src/util.rs:100-111) at a size that exercises all three scan levels
+    h, w = (1 << 17) + 0, 3
+    rng = np.random.default_rng(4)
+    cw = fr.random_wire(rng, h * w).reshape(h, w, 4)
+    z = int.from_bytes(rng.bytes(31), "little")
+    d_c = ctx.dev_alloc(cw.nbytes)
+    d_q = ctx.dev_alloc(cw.nbytes)
+    ctx.h2d(d_c, cw)
+    vals = np.zeros((w, 4), dtype=np.uint64)
+    zw = fr.to_wire([z])[0].copy()
+    ctx.call("eon_quotient_and_eval_dev", d_c, h, w, zw, d_q, vals)
+    qw = np.zeros_like(cw)
+    ctx.d2h(qw, d_q)
+    ctx.dev_free(d_c)
+    ctx.dev_free(d_q)
+    for c in range(w):
+        coeffs = fr.from_wire(cw[:, c, :])
+        q, v = okzg.quotient_and_eval(coeffs, z)
+        assert fr.from_wire(vals[c])[0] == v
+        assert fr.from_wire(qw[:h - 1, c, :]) == q
+        assert not qw[h - 1, c].any()
+
+
+def test_config2_shape_commit_and_open_properties(ctx):
+    """2^20 x 16 (BASELINE config 2): commitments checked through the discrete-log shortcut on
+    every column; one opening checked as witness == (f(alpha) - f(z)) / (alpha - z) * G."""
+    from plonky3_eon_b200 import TwoAdicMultiplicativeCoset
+    log_h, w = 20, 16
+    h = 1 << log_h
+    alpha = 12345
+    pcs = pcs_new(ctx, h - 1, alpha)
+    rng = np.random.default_rng(2)
+    evw = fr.random_wire(rng, h * w).reshape(h, w, 4)
+    dom = TwoAdicMultiplicativeCoset(1, log_h)
+    commit, pdata = pcs.commit([(dom, evw)])
+    coeffs = pdata[0].coeffs()
+    # commitment[c] = f_c(alpha) * G
+    f_alpha = []
+    for c in range(w):
+        col = fr.from_wire(coeffs[:, c, :])
+        fa = okzg.eval_poly(col, alpha)
+        f_alpha.append(fa)
+        assert pt(commit[0][c]) == kG(fa), c
+    # coefficients really are the interpolation of the evaluations: spot-check f_c(omega^j) == evals[j][c]
+    g = fr.two_adic_generator(log_h)
+    col0 = fr.from_wire(coeffs[:, 0, :])
+    for j in (0, 1, h - 1, 777777):
+        assert okzg.eval_poly(col0, pow(g, j, P)) == fr.from_wire(evw[j, 0])[0]
+    # open all columns at one point; verify algebraically
+    z = int.from_bytes(rng.bytes(31), "little") % P
+    opened, proof = pcs.open([(pdata, [[z]])])
+    inv = pow((alpha - z) % P, -1, P)
+    for c in (0, 7, 15):
+        col = col0 if c == 0 else fr.from_wire(coeffs[:, c, :])
+        fz = okzg.eval_poly(col, z)
+        assert fr.from_wire(opened[0][0][0][c])[0] == fz
+        assert pt(proof[0][0][0][c]) == kG((f_alpha[c] - fz) * inv % P)
+    pdata[0].free()

@@ -1,0 +1,127 @@
+"""CPU check of the CUDA library's field/curve arithmetic (csrc/fp.cuh, ec.cuh) compiled for
+the host with a software carry flag, against the big-int oracle.  No GPU needed."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import fr, g1
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SRC = os.path.join(HERE, "host", "hostlib.cpp")
+LIB = os.path.join(HERE, "host", "libhosteon.so")
+
+
+@pytest.fixture(scope="module")
+def lib():
+    csrc = os.path.join(HERE, "..", "plonky3_eon_b200", "csrc")
+    deps = [SRC] + [os.path.join(csrc, f) for f in ("fp.cuh", "ec.cuh", "consts.cuh")]
+    if not os.path.exists(LIB) or any(os.path.getmtime(d) > os.path.getmtime(LIB) for d in deps):
+        subprocess.check_call(["g++", "-O2", "-shared", "-fPIC", "-o", LIB, SRC])
+    return ctypes.CDLL(LIB)
+
+
+def _ptr(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def to_int(row):
+    return sum(int(row[k]) << (64 * k) for k in range(4))
+
+
+def from_int(v):
+    return np.array([(v >> (64 * k)) & ((1 << 64) - 1) for k in range(4)], dtype=np.uint64)
+
+
+def rand_mont(rng, mod, n):
+    out = np.zeros((n, 4), dtype=np.uint64)
+    for i in range(n):
+        v = int.from_bytes(rng.bytes(40), "little") % mod
+        out[i] = from_int(v)
+    return out
+
+
+EDGE = lambda mod: [0, 1, 2, mod - 1, mod - 2, (1 << 256) % mod, (mod - 1) // 2, (1 << 253), mod >> 1]
+
+
+@pytest.mark.parametrize("which,mod", [(0, fr.P), (1, g1.Q)])
+def test_field_ops(lib, which, mod):
+    rng = np.random.default_rng(11 + which)
+    edge = EDGE(mod)
+    pairs = [(a, b) for a in edge for b in edge]
+    a = np.concatenate([np.array([from_int(x) for x, _ in pairs]), rand_mont(rng, mod, 300)])
+    b = np.concatenate([np.array([from_int(y) for _, y in pairs]), rand_mont(rng, mod, 300)])
+    n = len(a)
+    r = np.zeros_like(a)
+    Rinv = pow(1 << 256, -1, mod)
+    expect = {
+        0: lambda x, y: x * y * Rinv % mod,
+        1: lambda x, y: (x + y) % mod,
+        2: lambda x, y: (x - y) % mod,
+        3: lambda x, y: (-x) % mod,
+        5: lambda x, y: x * Rinv % mod,
+        6: lambda x, y: x * (1 << 256) % mod,
+        7: lambda x, y: x * x * Rinv % mod,
+    }
+    for op, fn in expect.items():
+        lib.host_fp_op(which, op, _ptr(a), _ptr(b), _ptr(r), n)
+        for i in range(n):
+            assert to_int(r[i]) == fn(to_int(a[i]), to_int(b[i])), (which, op, i)
+    # inverse: a * inv(a) == R (Montgomery one); inv(0) == 0
+    m = 24
+    lib.host_fp_op(which, 4, _ptr(a[-m:]), _ptr(b[-m:]), _ptr(r[-m:]), m)
+    for i in range(n - m, n):
+        x = to_int(a[i])
+        assert to_int(r[i]) * x * Rinv % mod == ((1 << 256) % mod if x else 0)
+
+
+def test_fr_mul_matches_reference_limb_algorithm(lib):
+    rng = np.random.default_rng(5)
+    a = fr.random_wire(rng, 64)
+    b = fr.random_wire(rng, 64)
+    r = np.zeros_like(a)
+    lib.host_fp_op(0, 0, _ptr(a), _ptr(b), _ptr(r), 64)
+    for i in range(64):
+        assert to_int(r[i]) == fr.monty_mul_limbs(to_int(a[i]), to_int(b[i]))
+
+
+def test_curve_ops(lib):
+    G = g1.G
+    pts = [g1.mul(G, k) for k in (1, 2, 3, 7, 11, 12345)]
+    out = np.zeros(8, dtype=np.uint64)
+
+    def gsum(lst):
+        w = g1.to_wire(lst)
+        lib.host_g1_sum(_ptr(w), len(lst), _ptr(out))
+        return g1.from_wire(out)[0]
+
+    assert gsum([]) is None
+    assert gsum([G]) == G
+    assert gsum([G, G]) == g1.mul(G, 2)                 # doubling branch
+    assert gsum([G, g1.neg(G)]) is None                 # inverse branch
+    assert gsum([G, g1.neg(G), pts[3]]) == pts[3]       # restart from identity
+    assert gsum([None, G, None, G, G]) == g1.mul(G, 3)  # identity inputs
+    assert gsum(pts) == g1.mul(G, 1 + 2 + 3 + 7 + 11 + 12345)
+    # full addition incl. equal / opposite operands
+    def full(a0, a1, b0, b1):
+        ws = [g1.to_wire([p]) for p in (a0, a1, b0, b1)]
+        lib.host_g1_add_full(*[_ptr(w) for w in ws], _ptr(out))
+        return g1.from_wire(out)[0]
+    assert full(pts[0], pts[1], pts[2], pts[3]) == g1.mul(G, 13)
+    assert full(pts[0], pts[1], pts[1], pts[0]) == g1.mul(G, 6)            # A == B -> doubling
+    assert full(pts[0], pts[1], g1.neg(pts[0]), g1.neg(pts[1])) is None     # A == -B
+    assert full(pts[0], g1.neg(pts[0]), pts[2], pts[3]) == g1.mul(G, 10)    # A identity
+    assert full(pts[2], pts[3], pts[0], g1.neg(pts[0])) == g1.mul(G, 10)    # B identity
+    # scalar multiplication
+    rng = np.random.default_rng(2)
+    for k in [0, 1, 2, 5, fr.P - 1, fr.P, int.from_bytes(rng.bytes(31), "little")]:
+        kw = from_int(k)
+        pw = g1.to_wire([pts[4]])
+        lib.host_g1_mul(_ptr(pw), _ptr(kw), _ptr(out))
+        assert g1.from_wire(out)[0] == g1.mul(pts[4], k)
+    for k in [0, 1, 3, 32767, 65535]:
+        pw = g1.to_wire([pts[2]])
+        lib.host_g1_mul_u32(_ptr(pw), k, _ptr(out))
+        assert g1.from_wire(out)[0] == g1.mul(pts[2], 2 * k)
