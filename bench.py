@@ -1,0 +1,371 @@
+#!/usr/bin/env python
+"""bench.py — BN254 KZG commit + coset LDE throughput (BASELINE.json metric) on N B200s.
+
+One "step" = the hot path over one synthetic trace of 2^20 rows x 16 columns per GPU
+(BASELINE.json configs[1]):
+    KzgPcs::commit                 = coset iDFT (2^20 x 16) + 16 G1 MSMs of 2^20 points   (kzg/src/pcs.rs:223-265)
+    get_evaluations_on_domain      = zero-pad + coset NTT onto the 2^21-point coset 5*K      (blow-up 2)
+value = cols*rows / s with the trace resident in HBM (CUDA events on the launch stream).
+e2e   = the same through the host-buffer C ABI: pinned host trace -> H2D -> commit -> LDE -> D2H.
+N > 1: column sharding, every rank owns its own 2^20 x 16 slab of a 2^20 x (16 N) trace ("weak"); the
+only exchange is an all_gather of the 16 commitments (1 KiB) per rank.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl eon|reference] [--log-rows 20] [--cols 16]
+
+--impl reference times the CPU port of the reference path (oracle/c, OpenMP, all host threads) on a
+bounded sample of the same workload; the reference itself is Rust + halo2curves and cannot be built here.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "kzg_commit_lde_cols_rows_per_s"
+UNIT = "cols*rows/s"
+ALPHA = 12345          # kzg-example/examples/fibonacci_kzg.rs:79
+SHIFT_LDE = 5          # Fr::GENERATOR: quotient domain 5*K (commit/src/domain.rs:167)
+IMAD_PER_MODMUL = 272  # 136 32-bit limb MACs, lo + hi
+MODMUL_PER_MIXED_ADD = 10
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, dev):
+        self.dev = dev
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i",
+                 str(self.dev)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        # under load = samples at or above the median
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def synth_trace(seed, rows, cols):
+    """Uniform Fr in Montgomery form exactly like the reference sampler (bn254/src/field.rs:534-551):
+    random 256 bits, top 2 bits cleared, rejected if >= P, used AS the Montgomery limbs."""
+    from plonky3_eon_b200 import field
+    rng = np.random.default_rng(seed)
+    n = rows * cols
+    out = rng.integers(0, 1 << 64, size=(n, 4), dtype=np.uint64)
+    out[:, 3] &= np.uint64((1 << 62) - 1)
+    pl = [(field.P >> (64 * i)) & ((1 << 64) - 1) for i in range(4)]
+    while True:
+        lt = np.zeros(n, dtype=bool)
+        eq = np.ones(n, dtype=bool)
+        for k in (3, 2, 1, 0):
+            lt |= eq & (out[:, k] < np.uint64(pl[k]))
+            eq &= out[:, k] == np.uint64(pl[k])
+        bad = np.nonzero(~lt)[0]
+        if len(bad) == 0:
+            break
+        rep = rng.integers(0, 1 << 64, size=(len(bad), 4), dtype=np.uint64)
+        rep[:, 3] &= np.uint64((1 << 62) - 1)
+        out[bad] = rep
+    return out.reshape(rows, cols, 4)
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_sample(log_rows, cols, sample_cols, srs=None, repeats=1):
+    """The CPU port (oracle/c) on a bounded sample: full iDFT + LDE of the rows x cols trace, MSM on
+    `sample_cols` of the columns (scaled to `cols`).  Returns (value, seconds_estimated, detail)."""
+    from oracle import cport
+    rows = 1 << log_rows
+    ev = synth_trace(1, rows, cols)
+    if srs is None:
+        srs = cport.srs_generate(ALPHA, rows)
+    best = None
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        commits, coeffs = cport.kzg_commit(ev, 1, srs, ncols_msm=0)           # coset iDFT only
+        t1 = time.perf_counter()
+        cport.msm(srs, coeffs, ncols=sample_cols, ld=cols)                       # sample of the MSMs
+        t2 = time.perf_counter()
+        pad = np.zeros((2 * rows, cols, 4), dtype=np.uint64)
+        pad[:rows] = coeffs
+        t3 = time.perf_counter()
+        cport.coset_dft_batch(pad, SHIFT_LDE)                                    # zero-pad + coset DFT (2^21)
+        t4 = time.perf_counter()
+        est = (t1 - t0) + (t2 - t1) * (cols / sample_cols) + (t4 - t3)
+        d = {"idft_s": t1 - t0, "msm_sample_s": t2 - t1, "lde_s": t4 - t3}
+        if best is None or est < best[0]:
+            best = (est, d)
+    est, d = best
+    return rows * cols / est, est, d
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import cport
+    cores = cport.num_threads()
+    sample_cols = 2 if args.cols >= 2 else 1
+    rows = 1 << args.log_rows
+    t_setup = time.perf_counter()
+    srs = cport.srs_generate(ALPHA, rows)
+    t_setup = time.perf_counter() - t_setup
+    vals = []
+    steps = max(1, min(args.steps, 3))
+    for i in range(args.warmup_ref + steps):
+        v, est, d = cpu_reference_sample(args.log_rows, args.cols, sample_cols, srs=srs)
+        if i >= args.warmup_ref:
+            vals.append((v, est, d))
+    v = float(np.median([x[0] for x in vals]))
+    est = float(np.median([x[1] for x in vals]))
+    sample = (f"full coset iDFT 2^{args.log_rows}x{args.cols} + coset LDE to 2^{args.log_rows + 1} rows on all "
+              f"{args.cols} columns; MSM on {sample_cols} of {args.cols} columns, scaled x{args.cols // sample_cols}; "
+              f"affine SRS normalised once (no per-call to_affine, bn254/src/curve.rs:170)")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": args.warmup_ref, "ms_per_step": est * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u256 (4x64-bit Montgomery, BN254 Fr/Fq)", "data": "synthetic",
+        "config": {"workload": f"KZG commit + blow-up-2 coset LDE, 2^{args.log_rows} rows x {args.cols} cols, "
+                               "CPU port of the reference path (oracle/c, OpenMP)",
+                   "srs_setup_s": t_setup},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                         "detail": vals[-1][2]},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+def run_eon(args):
+    import ctypes as C
+
+    import torch
+    import torch.distributed as dist
+
+    import plonky3_eon_b200 as eon
+    from plonky3_eon_b200 import field
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the eon arm has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    n_gpus = world
+    rows, cols, log_rows = 1 << args.log_rows, args.cols, args.log_rows
+
+    stream = torch.cuda.current_stream()
+    ctx = eon.Context(local, stream=stream.cuda_stream)
+    pcs = eon.GpuKzgPcs.new(rows - 1, ALPHA, ctx=ctx)           # synthetic SRS alpha^i * G on the device
+    shift_one = field.to_wire(1)
+    shift_lde = field.to_wire(SHIFT_LDE)
+
+    # synthetic trace, pinned on the host and resident on the device
+    host_np = synth_trace(1 + rank, rows, cols)
+    host_pin = torch.from_numpy(host_np.view(np.int64)).pin_memory()
+    host_pin_np = host_pin.numpy().view(np.uint64)
+    d_evals = host_pin.to("cuda", non_blocking=False)
+    d_lde = torch.empty((2 * rows, cols, 4), dtype=torch.int64, device="cuda")
+    lde_pin = torch.empty((2 * rows, cols, 4), dtype=torch.int64).pin_memory()
+    lde_pin_np = lde_pin.numpy().view(np.uint64)
+    commits = np.zeros((cols, 8), dtype=np.uint64)
+    gathered = [torch.empty(cols * 8, dtype=torch.int64, device="cuda") for _ in range(world)] if world > 1 else None
+
+    def step_device():
+        h = C.c_uint64(0)
+        ctx.call("eon_kzg_commit_dev", C.c_void_p(d_evals.data_ptr()), log_rows, cols, shift_one, commits,
+                 C.byref(h))
+        ctx.call("eon_kzg_evals_on_coset_dev", h, log_rows + 1, shift_lde, C.c_void_p(d_lde.data_ptr()))
+        ctx.call("eon_handle_free", h)
+        if world > 1:
+            t = torch.from_numpy(commits.view(np.int64).reshape(-1)).cuda()
+            dist.all_gather(gathered, t)
+
+    def step_e2e():
+        h = C.c_uint64(0)
+        ctx.call("eon_kzg_commit", host_pin_np, log_rows, cols, shift_one, commits, C.byref(h))
+        ctx.call("eon_kzg_evals_on_coset", h, log_rows + 1, shift_lde, lde_pin_np)
+        ctx.call("eon_handle_free", h)
+        if world > 1:
+            t = torch.from_numpy(commits.view(np.int64).reshape(-1)).cuda()
+            dist.all_gather(gathered, t)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps):
+            fn()
+        e1.record(stream)
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    for _ in range(args.warmup):
+        step_device()
+    ctx.phase_reset()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = ctx.launch_count()
+    ms_dev = timed(step_device, args.steps)
+    launches = ctx.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    phases = ctx.phase_ms()          # summed over the timed steps
+    commits_device = commits.copy()
+
+    for _ in range(max(1, min(args.warmup, 2))):
+        step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+    assert np.array_equal(commits, commits_device), "e2e and device-resident commitments differ"
+
+    units = rows * cols * n_gpus * args.steps
+    value = units / (ms_dev * 1e-3)
+    e2e_value = units / (ms_e2e * 1e-3)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (MSM bucket accumulation: integer pipe) -----------------
+    imad_peak = max(ctx.imad_peak_tops(0), ctx.imad_peak_tops(1))       # T IMAD/s, measured now
+    imad_wide = ctx.imad_peak_tops(2)
+    modmul_g = ctx.modmul_gmuls(1)
+    W = 16                                                              # c = 16 windows at 2^20 points
+    adds = rows * cols * W                                              # one mixed add per (point, window, column)
+    acc_ms = phases["msm_accumulate"] / args.steps
+    achieved = adds * MODMUL_PER_MIXED_ADD * IMAD_PER_MODMUL / (acc_ms * 1e-3) / 1e12
+    hbm_peak, peak_src = peaks()
+    ntt_ms = phases["ntt_passes"] / args.steps
+    ntt_bytes = 3 * 2 * (rows * cols * 32) + 3 * 2 * (2 * rows * cols * 32) - (rows * cols * 32)
+    roofline = {
+        "kernel": "k_msm_accumulate (XYZZ mixed adds, one thread per bucket)",
+        "bound": "imad", "achieved": achieved, "peak": imad_peak, "unit": "TIMAD/s", "frac": achieved / imad_peak,
+        "traffic": None,
+        "algorithmic_ops_per_launch": adds * MODMUL_PER_MIXED_ADD * IMAD_PER_MODMUL,
+        "launch_ms": acc_ms,
+        "peak_source": "eon_bench_imad_peak in this run (mad.lo/mad.hi.u32, 16 independent chains/thread)",
+        "note": "the dominant kernel is integer-pipe bound (SURVEY §8d), so the roofline is IMAD, not HBM/tensor; "
+                "mad.wide peak (counted as 2 ops) and measured Fq modmul rate are given beside it",
+        "imad_wide_tops": imad_wide, "fq_modmul_gmul_s": modmul_g,
+        "modmul_equiv_tops": modmul_g * 1e9 * IMAD_PER_MODMUL / 1e12,
+    }
+    roofline_ntt = {
+        "kernel": "k_ntt_pass (3 HBM passes for the 2^20 iDFT + 3 for the 2^21 LDE)",
+        "bound": "hbm", "achieved": ntt_bytes / (ntt_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+        "frac": ntt_bytes / (ntt_ms * 1e-3) / 1e9 / hbm_peak, "traffic": None, "launch_ms_total": ntt_ms,
+        "peak_source": peak_src,
+        "imad_frac": ((rows // 2) * log_rows * cols + rows * log_rows * cols + rows * cols) * IMAD_PER_MODMUL
+        / (ntt_ms * 1e-3) / 1e12 / imad_peak,
+    }
+
+    # ---- CPU baseline: the port on the host cores, bounded sample (N = 1 only) -------------------
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        from oracle import cport
+        srs_host = pcs.g1_powers()                      # same SRS, read back (setup, untimed)
+        sample_cols = 2 if cols >= 2 else 1
+        v, est, d = cpu_reference_sample(log_rows, cols, sample_cols, srs=srs_host)
+        cpu = {"value": v, "unit": UNIT, "cores": cport.num_threads(), "kind": "port",
+               "sample": f"full coset iDFT + LDE of 2^{log_rows}x{cols}; MSM on {sample_cols}/{cols} columns scaled; "
+                         f"est. {est:.2f} s per step", "detail": d}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u256 (8x32-bit Montgomery limbs, BN254 Fr/Fq)", "data": "synthetic",
+        "config": {"workload": f"KZG commit (coset iDFT + {cols} MSM) + blow-up-2 coset LDE, 2^{log_rows} rows x "
+                               f"{cols} cols per GPU (BASELINE configs[1]); column-sharded {cols * n_gpus} cols total",
+                   "rows": rows, "cols_per_gpu": cols, "srs_points": rows, "msm_window_bits": 16,
+                   "l2": "inputs (512 MiB trace, 1 GiB LDE, 1 GiB sort workspace) exceed the 126 MB L2",
+                   "parallelism": f"columns x{n_gpus}"},
+        "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
+                "h2d_bytes_per_step": rows * cols * 32, "d2h_bytes_per_step": 2 * rows * cols * 32 + cols * 64},
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "phase_ms_per_step": {k: v / args.steps for k, v in phases.items()},
+        "roofline": roofline, "roofline_ntt": roofline_ntt, "cpu_baseline": cpu,
+        "msm_points_per_s": rows * cols / (sum(phases[k] for k in phases if k.startswith("msm_")) / args.steps * 1e-3),
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="eon", choices=["eon", "reference"])
+    ap.add_argument("--log-rows", type=int, default=20)
+    ap.add_argument("--cols", type=int, default=16)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--warmup-ref", type=int, default=0)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_eon(args)
+
+
+if __name__ == "__main__":
+    main()

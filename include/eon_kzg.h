@@ -163,8 +163,10 @@ int eon_quotient_and_eval_dev(eon_ctx* ctx, const uint64_t* d_coeffs, size_t h, 
 int eon_bench_imad_peak(eon_ctx* ctx, int kind, double* out_tops);
 /* Montgomery-product throughput (independent chains), in 1e9 modmul/s.  field: 0 Fr, 1 Fq. */
 int eon_bench_modmul(eon_ctx* ctx, int field, double* out_gmuls);
-/* per-phase device time (ms) of the last MSM / NTT call on this ctx; names via eon_phase_name */
+/* per-phase device time (ms, CUDA events on the ctx stream) summed over every call since the last
+ * eon_phase_reset; names via eon_phase_name (phases 0..7) */
 int eon_last_phase_ms(eon_ctx* ctx, int phase, float* out_ms);
+int eon_phase_reset(eon_ctx* ctx);
 const char* eon_phase_name(int phase);
 
 #ifdef __cplusplus

@@ -107,8 +107,8 @@ static inline void imr(const field_t* F, u64 acc0, const u64 acc[4], u64 res[4])
   }
 }
 
-/* helpers.rs:188-205 */
-static inline void f_mul(const field_t* F, fe* r, const fe* a, const fe* b) {
+/* helpers.rs:188-205 — literal restatement (4 rounds of multiply-accumulate + subtracting IMR) */
+static inline void f_mul_ref(const field_t* F, fe* r, const fe* a, const fe* b) {
   u64 acc[4], res[4];
   u64 a0 = mul_small_acc(a->v, b->v[0], NULL, acc);
   imr(F, a0, acc, res);
@@ -117,6 +117,56 @@ static inline void f_mul(const field_t* F, fe* r, const fe* a, const fe* b) {
     imr(F, a0, acc, res);
   }
   memcpy(r->v, res, 32);
+}
+
+/* Same product (the canonical value a*b*2^-256 mod p is unique), computed with the adding form of
+ * the interleaved reduction (m = t0 * (-p^-1), t += m*p) fully unrolled so gcc emits mulx/adc
+ * chains: this is what keeps the CPU baseline honest (~2.5x faster than f_mul_ref here).
+ * Valid because both moduli are < 2^254 (no carry out of the top limb). */
+static inline void f_mul(const field_t* F, fe* r, const fe* a, const fe* b) {
+  const u64 p0 = F->mod[0], p1 = F->mod[1], p2 = F->mod[2], p3 = F->mod[3];
+  const u64 ninv = (u64)0 - F->mu;
+  u64 t0 = 0, t1 = 0, t2 = 0, t3 = 0;
+#define EON_ROUND(bi)                                           \
+  do {                                                          \
+    u128 x = (u128)a->v[0] * (bi) + t0;                         \
+    u64 lo = (u64)x, A = (u64)(x >> 64);                        \
+    u64 m = lo * ninv;                                          \
+    u128 y = (u128)m * p0 + lo;                                 \
+    u64 Cc = (u64)(y >> 64);                                    \
+    x = (u128)a->v[1] * (bi) + t1 + A;                          \
+    A = (u64)(x >> 64);                                         \
+    y = (u128)m * p1 + (u64)x + Cc;                             \
+    t0 = (u64)y; Cc = (u64)(y >> 64);                           \
+    x = (u128)a->v[2] * (bi) + t2 + A;                          \
+    A = (u64)(x >> 64);                                         \
+    y = (u128)m * p2 + (u64)x + Cc;                             \
+    t1 = (u64)y; Cc = (u64)(y >> 64);                           \
+    x = (u128)a->v[3] * (bi) + t3 + A;                          \
+    A = (u64)(x >> 64);                                         \
+    y = (u128)m * p3 + (u64)x + Cc;                             \
+    t2 = (u64)y; Cc = (u64)(y >> 64);                           \
+    t3 = Cc + A;                                                \
+  } while (0)
+  EON_ROUND(b->v[0]);
+  EON_ROUND(b->v[1]);
+  EON_ROUND(b->v[2]);
+  EON_ROUND(b->v[3]);
+#undef EON_ROUND
+  /* t < 2p: one conditional subtraction */
+  u64 s0, s1, s2, s3, bw;
+  u128 d = (u128)t0 - p0;
+  s0 = (u64)d; bw = (u64)(d >> 64) & 1;
+  d = (u128)t1 - p1 - bw;
+  s1 = (u64)d; bw = (u64)(d >> 64) & 1;
+  d = (u128)t2 - p2 - bw;
+  s2 = (u64)d; bw = (u64)(d >> 64) & 1;
+  d = (u128)t3 - p3 - bw;
+  s3 = (u64)d; bw = (u64)(d >> 64) & 1;
+  r->v[0] = bw ? t0 : s0;
+  r->v[1] = bw ? t1 : s1;
+  r->v[2] = bw ? t2 : s2;
+  r->v[3] = bw ? t3 : s3;
 }
 
 static inline int ge_mod(const field_t* F, const u64 a[4]) {
@@ -208,7 +258,7 @@ static void f_from_u64(const field_t* F, fe* r, u64 x) {
   f_mul(F, r, &r2, &t); /* Fr::new: monty_mul(R^2, [v,0,0,0]), field.rs:110-116 */
 }
 
-/* exported element-wise ops for tests: which 0 = Fr, 1 = Fq; op 0 mul 1 add 2 sub 3 inv */
+/* exported element-wise ops for tests: which 0 = Fr, 1 = Fq; op 0 mul 1 add 2 sub 3 inv 4 mul (literal) */
 void oc_field_op(int which, int op, const u64* a, const u64* b, u64* r, size_t n) {
   oc_init();
   const field_t* F = which ? &FQm : &FR;
@@ -217,6 +267,7 @@ void oc_field_op(int which, int op, const u64* a, const u64* b, u64* r, size_t n
     const fe* y = (const fe*)(b + 4 * i);
     fe* z = (fe*)(r + 4 * i);
     if (op == 0) f_mul(F, z, x, y);
+    else if (op == 4) f_mul_ref(F, z, x, y);
     else if (op == 1) f_add(F, z, x, y);
     else if (op == 2) f_sub(F, z, x, y);
     else f_inv(F, z, x);
@@ -619,6 +670,7 @@ static void msm_serial(const aff* pts, const u64* scalars, size_t ld, size_t n, 
  * Threads split the (column, point-chunk) space like halo2curves' per-thread chunking. */
 void oc_msm(const u64* points_xy, const u64* scalars, size_t n, size_t ncols, size_t ld, u64* out_xy) {
   oc_init();
+  if (ncols == 0) return;
   const aff* pts = (const aff*)points_xy;
 #ifdef _OPENMP
   int nt = omp_get_max_threads();

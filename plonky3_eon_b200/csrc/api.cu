@@ -66,12 +66,6 @@ int eon_ctx_create(int device, void* stream, eon_ctx** out) {
   ctx->device = device;
   ctx->stream = (cudaStream_t)stream;
   ctx->num_sms = prop.multiProcessorCount;
-  for (int p = 0; p < PH_COUNT; p++) {
-    cudaEventCreate(&ctx->ev[p][0]);
-    cudaEventCreate(&ctx->ev[p][1]);
-    ctx->ev_used[p] = false;
-    ctx->phase_ms[p] = 0.f;
-  }
   *out = ctx;
   return EON_OK;
 }
@@ -84,11 +78,9 @@ void eon_ctx_destroy(eon_ctx* ctx) {
     if (s.ptr) cudaFree(s.ptr);
   for (auto& kv : ctx->twiddles) cudaFree(kv.second);
   for (auto& kv : ctx->handles) cudaFree(kv.second.d_coeffs);
+  for (auto& kv : ctx->coeff_pool) cudaFree(kv.second);
   if (ctx->d_srs) cudaFree(ctx->d_srs);
-  for (int p = 0; p < PH_COUNT; p++) {
-    cudaEventDestroy(ctx->ev[p][0]);
-    cudaEventDestroy(ctx->ev[p][1]);
-  }
+  for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
   delete ctx;
 }
 
@@ -398,7 +390,19 @@ static int kzg_commit_locked(eon_ctx* ctx, const uint64_t* d_evals, unsigned log
   }
   if (width && (!d_evals || !h_commit_xy)) return fail(ctx, EON_ERR_BAD_ARG, "null buffer");
   Fr* d_coeffs = nullptr;
-  EON_CUDA(ctx, cudaMalloc(&d_coeffs, mat_bytes(log_h, width) + 32));
+  size_t need = mat_bytes(log_h, width) + 32, cap = 0;
+  for (size_t i = 0; i < ctx->coeff_pool.size(); i++) {
+    if (ctx->coeff_pool[i].first >= need && ctx->coeff_pool[i].first <= 2 * need) {
+      cap = ctx->coeff_pool[i].first;
+      d_coeffs = (Fr*)ctx->coeff_pool[i].second;
+      ctx->coeff_pool.erase(ctx->coeff_pool.begin() + i);
+      break;
+    }
+  }
+  if (!d_coeffs) {
+    EON_CUDA(ctx, cudaMalloc(&d_coeffs, need));
+    cap = need;
+  }
   int rc = ntt_inverse(ctx, (const Fr*)d_evals, d_coeffs, log_h, width, s, LAYOUT_NATURAL);
   if (rc == EON_OK) rc = msm_to_host(ctx, ctx->d_srs, d_coeffs, h, width, width, h_commit_xy);
   if (rc != EON_OK) {
@@ -409,6 +413,7 @@ static int kzg_commit_locked(eon_ctx* ctx, const uint64_t* d_evals, unsigned log
   pm.d_coeffs = d_coeffs;
   pm.log_h = log_h;
   pm.width = width;
+  pm.cap = cap;
   eon_handle id = ctx->next_handle++;
   ctx->handles[id] = pm;
   *out_handle = id;
@@ -460,9 +465,14 @@ int eon_handle_free(eon_ctx* ctx, eon_handle h) {
   EON_TRY(set_device(ctx));
   ProverMatrix pm;
   EON_TRY(find_handle(ctx, h, &pm));
+  ctx->handles.erase(h);
+  if (ctx->coeff_pool.size() < 4) {
+    // stream order makes reuse safe: later work on this buffer is queued behind earlier readers
+    ctx->coeff_pool.push_back(std::make_pair(pm.cap, (void*)pm.d_coeffs));
+    return EON_OK;
+  }
   EON_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   EON_CUDA(ctx, cudaFree(pm.d_coeffs));
-  ctx->handles.erase(h);
   return EON_OK;
 }
 
@@ -586,9 +596,21 @@ int eon_last_phase_ms(eon_ctx* ctx, int phase, float* out_ms) {
   Lock lk(ctx);
   EON_TRY(set_device(ctx));
   *out_ms = 0.f;
-  if (!ctx->ev_used[phase]) return EON_OK;
-  EON_CUDA(ctx, cudaEventSynchronize(ctx->ev[phase][1]));
-  EON_CUDA(ctx, cudaEventElapsedTime(out_ms, ctx->ev[phase][0], ctx->ev[phase][1]));
+  for (auto& pr : ctx->ev_pairs[phase]) {
+    float ms = 0.f;
+    EON_CUDA(ctx, cudaEventSynchronize(pr.second));
+    EON_CUDA(ctx, cudaEventElapsedTime(&ms, pr.first, pr.second));
+    *out_ms += ms;
+  }
+  return EON_OK;
+}
+
+int eon_phase_reset(eon_ctx* ctx) {
+  if (!ctx) return EON_ERR_BAD_ARG;
+  Lock lk(ctx);
+  EON_TRY(set_device(ctx));
+  EON_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  phase_reset(ctx);
   return EON_OK;
 }
 

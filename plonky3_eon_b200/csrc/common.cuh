@@ -42,6 +42,7 @@ struct ProverMatrix {
   Fr* d_coeffs;  // natural order, h x width
   unsigned log_h;
   size_t width;
+  size_t cap;    // bytes allocated behind d_coeffs
 };
 
 // grow-only device scratch buffers, one per role, reused across calls (no allocation in steady state)
@@ -89,10 +90,16 @@ struct eon_ctx {
 
   std::map<eon_handle, eon::ProverMatrix> handles;
   eon_handle next_handle = 1;
+  // freed coefficient buffers kept for the next commit of a similar size (a prover commits and
+  // frees matrices of the same shape over and over; cudaMalloc/cudaFree would synchronise)
+  std::vector<std::pair<size_t, void*>> coeff_pool;
 
-  cudaEvent_t ev[eon::PH_COUNT][2];
-  bool ev_used[eon::PH_COUNT];
-  float phase_ms[eon::PH_COUNT];
+  // per-phase device timing: every phase_begin/phase_end pair since the last eon_phase_reset
+  // is kept; eon_last_phase_ms sums them (events are pooled and reused)
+  std::vector<cudaEvent_t> ev_pool;
+  size_t ev_next = 0;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pairs[eon::PH_COUNT];
+  cudaEvent_t ev_open[eon::PH_COUNT];
 };
 
 namespace eon {
@@ -143,12 +150,28 @@ inline int scratch_get(eon_ctx* ctx, int id, size_t bytes, void** out) {
   return EON_OK;
 }
 
+inline cudaEvent_t phase_event(eon_ctx* ctx) {
+  if (ctx->ev_next == ctx->ev_pool.size()) {
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    ctx->ev_pool.push_back(e);
+  }
+  return ctx->ev_pool[ctx->ev_next++];
+}
+inline void phase_reset(eon_ctx* ctx) {
+  ctx->ev_next = 0;
+  for (int p = 0; p < PH_COUNT; p++) ctx->ev_pairs[p].clear();
+}
 inline void phase_begin(eon_ctx* ctx, int ph) {
-  cudaEventRecord(ctx->ev[ph][0], ctx->stream);
+  if (ctx->ev_next > 4096) phase_reset(ctx);  // nobody is reading: do not grow without bound
+  cudaEvent_t e = phase_event(ctx);
+  cudaEventRecord(e, ctx->stream);
+  ctx->ev_open[ph] = e;
 }
 inline void phase_end(eon_ctx* ctx, int ph) {
-  cudaEventRecord(ctx->ev[ph][1], ctx->stream);
-  ctx->ev_used[ph] = true;
+  cudaEvent_t e = phase_event(ctx);
+  cudaEventRecord(e, ctx->stream);
+  ctx->ev_pairs[ph].push_back(std::make_pair(ctx->ev_open[ph], e));
 }
 
 // host-side Fr helpers (same arithmetic as the device, software carry flag)

@@ -63,6 +63,7 @@ _SIGS = {
     "eon_bench_imad_peak": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_double)]),
     "eon_bench_modmul": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_double)]),
     "eon_last_phase_ms": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_float)]),
+    "eon_phase_reset": (C.c_int, [C.c_void_p]),
     "eon_phase_name": (C.c_char_p, [C.c_int]),
 }
 
@@ -176,6 +177,9 @@ class Context:
 
     def d2h(self, arr, dptr):
         self.call("eon_d2h", arr, C.c_void_p(dptr), arr.nbytes)
+
+    def phase_reset(self):
+        self.call("eon_phase_reset")
 
     def phase_ms(self):
         out = {}

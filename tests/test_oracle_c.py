@@ -19,7 +19,8 @@ def test_field_ops():
         Rinv = pow(1 << 256, -1, mod)
         ia = [sum(int(r[k]) << (64 * k) for k in range(4)) for r in a]
         ib = ia[::-1]
-        for op, fn in ((0, lambda x, y: x * y * Rinv % mod), (1, lambda x, y: (x + y) % mod),
+        for op, fn in ((0, lambda x, y: x * y * Rinv % mod), (4, lambda x, y: x * y * Rinv % mod),
+                       (1, lambda x, y: (x + y) % mod),
                        (2, lambda x, y: (x - y) % mod)):
             r = cport.field_op(which, op, a, b)
             for i in range(len(ia)):
