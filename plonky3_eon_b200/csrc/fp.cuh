@@ -15,7 +15,7 @@
 // which performs the divide-by-2^32 without moving registers.
 //
 // The same source compiles for the host (g++/nvcc host pass) with the carry flag emulated
-// in software; tests/host/ uses that to check the arithmetic against the oracle on CPU.
+// in software; tests/host/ uses that to check the arithmetic on CPU (no GPU needed).
 #pragma once
 #include <stdint.h>
 #include "consts.cuh"

@@ -1,0 +1,106 @@
+"""Multi-GPU sharding of the KZG hot path (one process per GPU, torch.distributed for plumbing).
+
+The reference has no distributed layer; the path shards along two independent axes
+(SURVEY §8e), neither of which needs a data-path collective:
+
+  * columns      every column's iDFT / LDE / MSM is independent (kzg/src/pcs.rs:244-249):
+                 rank r owns columns column_shard(width, world, r); the SRS is replicated.
+                 The only exchange is an all_gather of the per-column commitments (64 B each).
+  * point index  one big MSM: rank r holds SRS[index_shard(n, world, r)] and the matching scalar
+                 rows, produces ONE partial affine point per column; partial sums are
+                 all-gathered (world x ncols x 64 B) and added on every rank
+                 (EC addition is not an NCCL reduction op).
+
+`backend` is anything with the two methods of `GpuBackend` below; tests/test_dist_gloo.py runs the
+same logic at world_size 2 on CPU (gloo) with an oracle-backed stand-in, since only the
+sharding/gather logic is being exercised there.
+"""
+import numpy as np
+
+
+def column_shard(width, world, rank):
+    """Contiguous, balanced column range [c0, c1) of rank `rank` (first `width % world` ranks get one more)."""
+    base, extra = divmod(width, world)
+    c0 = rank * base + min(rank, extra)
+    return c0, c0 + base + (1 if rank < extra else 0)
+
+
+def index_shard(n, world, rank):
+    """Contiguous, balanced point-index range (first, count) of rank `rank`."""
+    c0, c1 = column_shard(n, world, rank)
+    return c0, c1 - c0
+
+
+class GpuBackend:
+    """The C-ABI calls the sharded algorithms need (see include/eon_kzg.h)."""
+
+    def __init__(self, ctx):
+        self.ctx = ctx
+
+    def msm_srs_range(self, scalars, first, n, ncols):
+        """scalars: uint64 [n, ncols, 4] host rows [first, first+n) -> uint64 [ncols, 8]."""
+        import ctypes as C
+        s = np.ascontiguousarray(scalars, dtype=np.uint64)
+        out = np.zeros((ncols, 8), dtype=np.uint64)
+        d = self.ctx.dev_alloc(max(s.nbytes, 32))
+        try:
+            if s.nbytes:
+                self.ctx.h2d(d, s)
+            self.ctx.call("eon_msm_srs_range_dev", C.c_void_p(d), first, n, ncols, ncols, out)
+        finally:
+            self.ctx.dev_free(d)
+        return out
+
+    def g1_sum(self, points):
+        p = np.ascontiguousarray(points, dtype=np.uint64).reshape(-1, 8)
+        out = np.zeros(8, dtype=np.uint64)
+        self.ctx.call("eon_g1_sum", p, p.shape[0], out)
+        return out
+
+
+def _all_gather_u64(arr, group=None, device=None):
+    """all_gather of a uint64 numpy array (same shape on every rank) -> list of arrays, rank order."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    t = torch.from_numpy(np.ascontiguousarray(arr).view(np.int64).reshape(-1).copy())
+    if device is not None:
+        t = t.to(device)
+    outs = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(outs, t, group=group)
+    return [o.cpu().numpy().view(np.uint64).reshape(arr.shape) for o in outs]
+
+
+def sharded_msm(backend, scalars_local, first, n_local, ncols, group=None, device=None):
+    """Index-range sharded MSM.  Every rank passes its own scalar rows [first, first + n_local) and
+    gets the full result [ncols, 8] (identical on all ranks)."""
+    partial = backend.msm_srs_range(scalars_local, first, n_local, ncols)
+    parts = _all_gather_u64(partial, group, device)            # world x [ncols, 8]
+    out = np.zeros((ncols, 8), dtype=np.uint64)
+    for c in range(ncols):
+        out[c] = backend.g1_sum(np.stack([p[c] for p in parts]))
+    return out
+
+
+def gather_column_commitments(local_commit, width, group=None, device=None):
+    """Column-sharded commit: every rank committed its column_shard(); returns the [width, 8]
+    commitment of the whole matrix in column order on every rank."""
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    widths = [column_shard(width, world, r) for r in range(world)]
+    maxw = max(c1 - c0 for c0, c1 in widths)
+    pad = np.zeros((maxw, 8), dtype=np.uint64)
+    pad[:local_commit.shape[0]] = local_commit
+    parts = _all_gather_u64(pad, group, device)
+    out = np.zeros((width, 8), dtype=np.uint64)
+    for r, (c0, c1) in enumerate(widths):
+        out[c0:c1] = parts[r][:c1 - c0]
+    return out
+
+
+def sharded_commit(pcs, domain, evals_local, width, group=None, device=None):
+    """KzgPcs::commit of one h x width matrix whose columns are sharded: `evals_local` holds this
+    rank's columns column_shard(width, world, rank) as [h, local_w, 4].  Returns
+    (commitment [width, 8] on every rank, this rank's MatrixProverData)."""
+    commit, pdata = pcs.commit([(domain, evals_local)])
+    return gather_column_commitments(commit[0], width, group, device), pdata[0]
