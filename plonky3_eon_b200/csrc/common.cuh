@@ -64,6 +64,7 @@ enum ScratchId {
   SC_MSM_SEGSUM,
   SC_MSM_RESULT,
   SC_MSM_MISC,
+  SC_MSM_ORDER,
   SC_IO_A,
   SC_IO_B,
   SC_QUOT,

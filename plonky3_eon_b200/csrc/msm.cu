@@ -152,6 +152,42 @@ k_msm_scatter(const int16_t* __restrict__ digits, size_t n, u32 NB, u32* __restr
   entries[seg * n + pos] = (u32)i | (d < 0 ? SIGN_BIT : 0u);
 }
 
+// ---- 3b. bucket order: largest buckets first, equal sizes adjacent --------------------------------
+// One thread accumulates one bucket, so a warp runs as long as its fullest bucket: with ~32 +- 6
+// entries per bucket (uniform scalars) 28 % of the lanes idle (ncu: 22.97 active threads/inst).
+// Sorting the bucket ids of every segment by entry count (counting sort, 256 bins, descending)
+// gives every warp buckets of (nearly) one size.  One block per segment.
+constexpr u32 ORDER_BINS = 256;
+__global__ void __launch_bounds__(1024)
+k_msm_order(const u32* __restrict__ starts, const u32* __restrict__ ends, u32 NB, u32* __restrict__ order) {
+  __shared__ u32 bin_count[ORDER_BINS];
+  __shared__ u32 bin_pos[ORDER_BINS];
+  const size_t seg = blockIdx.x;
+  const u32* st = starts + seg * NB;
+  const u32* en = ends + seg * NB;
+  u32* ord = order + seg * NB;
+  for (u32 i = threadIdx.x; i < ORDER_BINS; i += blockDim.x) bin_count[i] = 0;
+  __syncthreads();
+  for (u32 b = threadIdx.x; b < NB; b += blockDim.x) {
+    u32 cnt = en[b] - st[b];
+    atomicAdd(&bin_count[min(cnt, ORDER_BINS - 1)], 1u);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    u32 acc = 0;
+    for (int k = ORDER_BINS - 1; k >= 0; k--) {  // descending size
+      bin_pos[k] = acc;
+      acc += bin_count[k];
+    }
+  }
+  __syncthreads();
+  for (u32 b = threadIdx.x; b < NB; b += blockDim.x) {
+    u32 cnt = en[b] - st[b];
+    u32 pos = atomicAdd(&bin_pos[min(cnt, ORDER_BINS - 1)], 1u);
+    ord[pos] = b;
+  }
+}
+
 // ---- 4. bucket accumulation --------------------------------------------------------------------
 struct MsmTask {
   u32 bucket;  // global bucket id = seg * NB + b
@@ -187,12 +223,13 @@ __device__ __forceinline__ void store_xyzz(G1Xyzz* dst, const G1Xyzz& p) { *dst 
 // one thread per bucket; starts[] = bucket begin, cursor[] = bucket end (after the scatter)
 __global__ void __launch_bounds__(MSM_THREADS)
 k_msm_accumulate(const G1Affine* __restrict__ bases, const u32* __restrict__ entries, size_t n,
-                 const u32* __restrict__ starts, const u32* __restrict__ ends, u32 NB, size_t total_buckets,
-                 u32 chunk_min, G1Xyzz* __restrict__ buckets, MsmTask* __restrict__ tasks, u32* __restrict__ ntasks,
-                 u32 max_tasks) {
-  size_t g = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-  if (g >= total_buckets) return;
-  u32 seg = (u32)(g / NB);
+                 const u32* __restrict__ starts, const u32* __restrict__ ends, const u32* __restrict__ order, u32 NB,
+                 size_t total_buckets, u32 chunk_min, G1Xyzz* __restrict__ buckets, MsmTask* __restrict__ tasks,
+                 u32* __restrict__ ntasks, u32 max_tasks) {
+  size_t slot = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (slot >= total_buckets) return;
+  u32 seg = (u32)(slot / NB);
+  size_t g = (size_t)seg * NB + order[slot];  // bucket handled by this thread
   u32 begin = starts[g], end = ends[g];
   u32 cnt = end - begin;
   u32 my_end = end;
@@ -250,7 +287,7 @@ k_msm_fold_tasks(const MsmTask* __restrict__ tasks, const u32* __restrict__ ntas
 // ---- 5. bucket reduction ----------------------------------------------------------------------
 // thread per (segment, chunk): running sums over `chunk` consecutive buckets.
 //   S = sum B_b,  T = sum (b - lo + 1) * B_b   =>   contribution = T + lo * S
-__global__ void __launch_bounds__(MSM_THREADS)
+__global__ void __launch_bounds__(128, 3)
 k_msm_reduce_chunks(const G1Xyzz* __restrict__ buckets, MsmShape sh, size_t nseg, G1Xyzz* __restrict__ partials) {
   size_t g = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   if (g >= nseg * sh.nchunks) return;
@@ -335,7 +372,8 @@ static int msm_batch(eon_ctx* ctx, const G1Affine* d_bases, const Fr* d_scalars,
   if (max_tasks_sz > 0x7fffffffull) max_tasks_sz = 0x7fffffffull;
   const u32 max_tasks = (u32)max_tasks_sz;
 
-  void *p_dig, *p_hist, *p_cur, *p_ent, *p_bkt, *p_tasks, *p_tpart, *p_part, *p_seg, *p_misc;
+  void *p_dig, *p_hist, *p_cur, *p_ent, *p_bkt, *p_tasks, *p_tpart, *p_part, *p_seg, *p_misc, *p_ord;
+  EON_TRY(scratch_get(ctx, SC_MSM_ORDER, total_buckets * sizeof(u32), &p_ord));
   EON_TRY(scratch_get(ctx, SC_MSM_DIGITS, nseg * n * sizeof(int16_t), &p_dig));
   EON_TRY(scratch_get(ctx, SC_MSM_HIST, total_buckets * sizeof(u32), &p_hist));
   EON_TRY(scratch_get(ctx, SC_MSM_CURSOR, total_buckets * sizeof(u32), &p_cur));
@@ -374,10 +412,13 @@ static int msm_batch(eon_ctx* ctx, const G1Affine* d_bases, const Fr* d_scalars,
 
   phase_begin(ctx, PH_MSM_ACCUM);
   {
+    k_msm_order<<<(unsigned)nseg, 1024, 0, st>>>((const u32*)p_hist, (const u32*)p_cur, sh.NB, (u32*)p_ord);
+    EON_LAUNCHED(ctx);
     unsigned blocks = (unsigned)((total_buckets + MSM_THREADS - 1) / MSM_THREADS);
     k_msm_accumulate<<<blocks, MSM_THREADS, 0, st>>>(d_bases, (const u32*)p_ent, n, (const u32*)p_hist,
-                                                     (const u32*)p_cur, sh.NB, total_buckets, chunk_min,
-                                                     (G1Xyzz*)p_bkt, (MsmTask*)p_tasks, d_ntasks, max_tasks);
+                                                     (const u32*)p_cur, (const u32*)p_ord, sh.NB, total_buckets,
+                                                     chunk_min, (G1Xyzz*)p_bkt, (MsmTask*)p_tasks, d_ntasks,
+                                                     max_tasks);
     EON_LAUNCHED(ctx);
     unsigned tb = (unsigned)ctx->num_sms * 8;
     k_msm_accumulate_tasks<<<tb, MSM_THREADS, 0, st>>>(d_bases, (const u32*)p_ent, n, (const MsmTask*)p_tasks,
@@ -392,8 +433,8 @@ static int msm_batch(eon_ctx* ctx, const G1Affine* d_bases, const Fr* d_scalars,
   phase_begin(ctx, PH_MSM_REDUCE);
   {
     size_t threads = nseg * sh.nchunks;
-    unsigned blocks = (unsigned)((threads + MSM_THREADS - 1) / MSM_THREADS);
-    k_msm_reduce_chunks<<<blocks, MSM_THREADS, 0, st>>>((const G1Xyzz*)p_bkt, sh, nseg, (G1Xyzz*)p_part);
+    unsigned blocks = (unsigned)((threads + 127) / 128);
+    k_msm_reduce_chunks<<<blocks, 128, 0, st>>>((const G1Xyzz*)p_bkt, sh, nseg, (G1Xyzz*)p_part);
     EON_LAUNCHED(ctx);
     k_msm_reduce_segment<<<(unsigned)nseg, 128, 0, st>>>((const G1Xyzz*)p_part, sh.nchunks, (G1Xyzz*)p_seg);
     EON_LAUNCHED(ctx);

@@ -130,7 +130,7 @@ __global__ void __launch_bounds__(NTT_THREADS, 3) k_ntt_pass(const PassParams p)
   const u32 cv = 1u << p.log_cv;
   const u32 tile_elems = R << p.log_cv;
   uint4* s_lo = smem;
-  uint4* s_hi = smem + tile_elems;
+  uint4* s_hi = smem + tile_elems + 4;  // +64 B: the two 16-byte planes of one element hit different banks
   const u32 tid = threadIdx.x;
 
   const u64 tile = blockIdx.x;
@@ -309,10 +309,10 @@ static int launch_pass(eon_ctx* ctx, PassParams& p, const PassPlan& pl, unsigned
   u64 tiles_hi = 1ull << (log_n - pl.l0 - pl.r);
   u64 grid = tiles_hi * p.tiles_v;
   if (grid == 0 || grid > 0x7fffffffull) return fail(ctx, EON_ERR_BAD_ARG, "ntt: grid too large");
-  size_t smem = ((size_t)1 << (pl.r + pl.log_cv)) * 32;
+  size_t smem = ((size_t)1 << (pl.r + pl.log_cv)) * 32 + 64;
   if (!g_attr_set) {
     EON_CUDA(ctx, cudaFuncSetAttribute(k_ntt_pass, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)(NTT_TILE_ELEMS * 32)));
+                                       (int)(NTT_TILE_ELEMS * 32 + 64)));
     g_attr_set = true;
   }
   k_ntt_pass<<<(unsigned)grid, NTT_THREADS, smem, ctx->stream>>>(p);
