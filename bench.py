@@ -289,7 +289,8 @@ def run_eon(args):
     imad_peak = max(ctx.imad_peak_tops(0), ctx.imad_peak_tops(1))       # T IMAD/s, measured now
     imad_wide = ctx.imad_peak_tops(2)
     modmul_g = ctx.modmul_gmuls(1)
-    W = 16                                                              # c = 16 windows at 2^20 points
+    c_bits = int(ctx.lib.eon_srs_window_bits(ctx.h)) or 16              # window tables in use (0 = plain c = 16)
+    W = (256 + c_bits - 1) // c_bits
     adds = rows * cols * W                                              # one mixed add per (point, window, column)
     acc_ms = phases["msm_accumulate"] / args.steps
     achieved = adds * MODMUL_PER_MIXED_ADD * IMAD_PER_MODMUL / (acc_ms * 1e-3) / 1e12
@@ -334,7 +335,7 @@ def run_eon(args):
         "dtype": "u256 (8x32-bit Montgomery limbs, BN254 Fr/Fq)", "data": "synthetic",
         "config": {"workload": f"KZG commit (coset iDFT + {cols} MSM) + blow-up-2 coset LDE, 2^{log_rows} rows x "
                                f"{cols} cols per GPU (BASELINE configs[1]); column-sharded {cols * n_gpus} cols total",
-                   "rows": rows, "cols_per_gpu": cols, "srs_points": rows, "msm_window_bits": 16,
+                   "rows": rows, "cols_per_gpu": cols, "srs_points": rows, "msm_window_bits": c_bits, "msm_windows": W,
                    "l2": "inputs (512 MiB trace, 1 GiB LDE, 1 GiB sort workspace) exceed the 126 MB L2",
                    "parallelism": f"columns x{n_gpus}"},
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,

@@ -107,6 +107,12 @@ int eon_srs_load_affine(eon_ctx* ctx, const uint64_t* h_xy, size_t n);
 int eon_srs_generate_unsafe(eon_ctx* ctx, const uint64_t alpha[4], size_t n);
 /* number of G1 powers resident (max_degree + 1), 0 if none */
 size_t eon_srs_size(const eon_ctx* ctx);
+/* Window tables for MSMs over the resident SRS: tab[t][i] = 2^(c t) * g1_powers[i] for
+ * t < ceil(256 / c), c = window_bits in [8, 20]; 0 drops the tables (plain per-window buckets).
+ * Costs ceil(256/c) x the SRS memory; built automatically (c = log2(n) - 2) by the two loaders
+ * above for n >= 2^14.  eon_srs_window_bits returns the c in use (0 = no tables). */
+int eon_srs_set_window_tables(eon_ctx* ctx, unsigned window_bits);
+unsigned eon_srs_window_bits(const eon_ctx* ctx);
 /* copy SRS points [first, first + n) back to the host as affine wire points */
 int eon_srs_read(eon_ctx* ctx, size_t first, size_t n, uint64_t* h_xy);
 

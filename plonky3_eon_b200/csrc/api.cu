@@ -80,6 +80,7 @@ void eon_ctx_destroy(eon_ctx* ctx) {
   for (auto& kv : ctx->handles) cudaFree(kv.second.d_coeffs);
   for (auto& kv : ctx->coeff_pool) cudaFree(kv.second);
   if (ctx->d_srs) cudaFree(ctx->d_srs);
+  if (ctx->d_srs_tab) cudaFree(ctx->d_srs_tab);
   for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
   delete ctx;
 }
@@ -264,12 +265,14 @@ int eon_srs_load_affine(eon_ctx* ctx, const uint64_t* h_xy, size_t n) {
     EON_CUDA(ctx, cudaFree(ctx->d_srs));
     ctx->d_srs = nullptr;
     ctx->srs_n = 0;
+    EON_TRY(srs_build_tables(ctx, 0));
   }
   if (n == 0) return EON_OK;
   EON_CUDA(ctx, cudaMalloc(&ctx->d_srs, n * sizeof(G1Affine)));
   EON_CUDA(ctx, cudaMemcpyAsync(ctx->d_srs, h_xy, n * sizeof(G1Affine), cudaMemcpyHostToDevice, ctx->stream));
-  EON_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   ctx->srs_n = n;
+  EON_TRY(srs_build_default_tables(ctx));
+  EON_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return EON_OK;
 }
 
@@ -284,6 +287,16 @@ int eon_srs_generate_unsafe(eon_ctx* ctx, const uint64_t alpha[4], size_t n) {
 }
 
 size_t eon_srs_size(const eon_ctx* ctx) { return ctx ? ctx->srs_n : 0; }
+
+int eon_srs_set_window_tables(eon_ctx* ctx, unsigned window_bits) {
+  if (!ctx) return EON_ERR_BAD_ARG;
+  Lock lk(ctx);
+  EON_TRY(set_device(ctx));
+  EON_TRY(srs_build_tables(ctx, window_bits));
+  EON_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return EON_OK;
+}
+unsigned eon_srs_window_bits(const eon_ctx* ctx) { return ctx ? ctx->srs_tab_c : 0; }
 
 int eon_srs_read(eon_ctx* ctx, size_t first, size_t n, uint64_t* h_xy) {
   if (!ctx) return EON_ERR_BAD_ARG;

@@ -53,7 +53,6 @@ struct Scratch {
 
 enum ScratchId {
   SC_NTT_TMP = 0,
-  SC_MSM_DIGITS,
   SC_MSM_HIST,
   SC_MSM_CURSOR,
   SC_MSM_ENTRIES,
@@ -88,6 +87,9 @@ struct eon_ctx {
 
   eon::G1Affine* d_srs = nullptr;
   size_t srs_n = 0;
+  // window tables tab[t][i] = 2^(c t) * srs[i] (t < ceil(256/c)), built once per SRS; null = none
+  eon::G1Affine* d_srs_tab = nullptr;
+  unsigned srs_tab_c = 0;
 
   std::map<eon_handle, eon::ProverMatrix> handles;
   eon_handle next_handle = 1;
@@ -215,6 +217,8 @@ int msm_run(eon_ctx* ctx, const G1Affine* d_bases, const Fr* d_scalars, size_t n
             G1Affine* d_out);
 int g1_sum_run(eon_ctx* ctx, const G1Affine* d_points, size_t n, G1Affine* d_out);
 int srs_generate(eon_ctx* ctx, const Fr& alpha, size_t n);
+int srs_build_tables(eon_ctx* ctx, unsigned window_bits);
+int srs_build_default_tables(eon_ctx* ctx);
 
 int quotient_run(eon_ctx* ctx, const Fr* d_coeffs, size_t h, size_t width, size_t ld_out, const Fr& z, Fr* d_quot,
                  Fr* d_values);

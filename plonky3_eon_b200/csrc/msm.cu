@@ -24,41 +24,64 @@ constexpr int MSM_THREADS = 256;
 constexpr u32 SIGN_BIT = 0x80000000u;
 
 struct MsmShape {
-  u32 c;        // window bits (2..16)
+  u32 c;        // window bits (2..20)
   u32 W;        // windows = ceil(256 / c)
-  u32 NB;       // buckets per segment = 2^(c-1)
+  u32 NB;       // buckets per bucket set = 2^(c-1)
+  u32 nsets;    // bucket sets per column: W (plain) or 1 (merged: windows share one set because
+                // window t reads the precomputed table 2^(c t) * P_i instead of P_i)
+  u32 merged;
   u32 chunk;    // buckets per reduction chunk
   u32 nchunks;  // NB / chunk
+  u64 tab_stride;  // merged: points per table level
+  u64 base_first;  // merged: index of this MSM's point 0 inside a table level
+  u64 seg_cap;     // entry slots per segment: n (plain) or n * W (merged)
 };
 
-static MsmShape msm_shape(size_t n) {
+static u32 ceil_log2(size_t n) {
   u32 lg = 0;
   while (((size_t)1 << lg) < n) lg++;
-  int c = (int)lg - 3;
+  return lg;
+}
+
+static MsmShape msm_shape_plain(size_t n) {
+  int c = (int)ceil_log2(n) - 3;
   if (c < 2) c = 2;
   if (c > 16) c = 16;
   MsmShape s;
+  memset(&s, 0, sizeof(s));
   s.c = (u32)c;
   s.W = (256 + s.c - 1) / s.c;
   s.NB = 1u << (s.c - 1);
+  s.nsets = s.W;
+  s.merged = 0;
   s.chunk = s.NB < 32 ? s.NB : 32;
   s.nchunks = s.NB / s.chunk;
+  s.seg_cap = n;
   return s;
 }
 
-// ---- 1. digits + histogram ------------------------------------------------------------------
-// grid: (ceil(n / threads), ncols).  digits layout: [col][window][i] int16.
-__global__ void __launch_bounds__(MSM_THREADS)
-k_msm_digits(const Fr* __restrict__ scalars, size_t n, size_t ld, MsmShape sh, int16_t* __restrict__ digits,
-             u32* __restrict__ hist) {
-  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  u32 col = blockIdx.y;
-  const uint4* sp = reinterpret_cast<const uint4*>(scalars + i * ld + col);
-  uint4 lo = __ldg(sp), hi = __ldg(sp + 1);
-  Fr s;
-  s.v[0] = lo.x; s.v[1] = lo.y; s.v[2] = lo.z; s.v[3] = lo.w;
-  s.v[4] = hi.x; s.v[5] = hi.y; s.v[6] = hi.z; s.v[7] = hi.w;
+static MsmShape msm_shape_merged(size_t n, u32 c, u64 tab_stride, u64 first) {
+  MsmShape s;
+  memset(&s, 0, sizeof(s));
+  s.c = c;
+  s.W = (256 + c - 1) / c;
+  s.NB = 1u << (c - 1);
+  s.nsets = 1;
+  s.merged = 1;
+  s.chunk = 32;
+  s.nchunks = s.NB / s.chunk;
+  s.tab_stride = tab_stride;
+  s.base_first = first;
+  s.seg_cap = (u64)n * s.W;
+  return s;
+}
+
+// ---- 1. scalar -> signed window digits --------------------------------------------------------
+// s * 1 * R^-1 gives the canonical integer (the reference hands halo2curves Montgomery scalars,
+// bn254/src/curve.rs:173-174).  Digits d_w in [-2^(c-1), 2^(c-1)) with sum d_w 2^(c w) = scalar;
+// W*c >= 256 > 254 + 2 guarantees the top window absorbs the last carry.  f(w, d) for d != 0.
+template <class F>
+__device__ __forceinline__ void for_each_digit(const Fr& s, const MsmShape& sh, F f) {
   u32 k[9];
   fp_from_mont(k, s);
   k[8] = 0;
@@ -69,10 +92,8 @@ k_msm_digits(const Fr* __restrict__ scalars, size_t n, size_t ld, MsmShape sh, i
   for (u32 w = 0; w < sh.W; w++) {
     u32 bit = w * c;
     u32 limb = bit >> 5, off = bit & 31;
-    u32 raw;
-    if (limb >= 8) {
-      raw = 0;
-    } else {
+    u32 raw = 0;
+    if (limb < 8) {
       u64 two = (u64)k[limb] | ((u64)k[limb + 1] << 32);
       raw = (u32)(two >> off) & mask;
     }
@@ -85,13 +106,31 @@ k_msm_digits(const Fr* __restrict__ scalars, size_t n, size_t ld, MsmShape sh, i
       d = (int)raw;
       carry = 0;
     }
-    size_t seg = (size_t)col * sh.W + w;
-    digits[seg * n + i] = (int16_t)d;
-    if (d != 0) {
-      u32 b = (u32)(d < 0 ? -d : d) - 1;
-      atomicAdd(&hist[seg * sh.NB + b], 1u);
-    }
+    if (d != 0) f(w, d);
   }
+}
+
+__device__ __forceinline__ Fr load_scalar(const Fr* __restrict__ scalars, size_t i, size_t ld, u32 col) {
+  const uint4* sp = reinterpret_cast<const uint4*>(scalars + i * ld + col);
+  uint4 lo = __ldg(sp), hi = __ldg(sp + 1);
+  Fr s;
+  s.v[0] = lo.x; s.v[1] = lo.y; s.v[2] = lo.z; s.v[3] = lo.w;
+  s.v[4] = hi.x; s.v[5] = hi.y; s.v[6] = hi.z; s.v[7] = hi.w;
+  return s;
+}
+
+// bucket histogram.  grid: (ceil(n / threads), ncols)
+__global__ void __launch_bounds__(MSM_THREADS)
+k_msm_hist(const Fr* __restrict__ scalars, size_t n, size_t ld, MsmShape sh, u32* __restrict__ hist) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  u32 col = blockIdx.y;
+  Fr s = load_scalar(scalars, i, ld, col);
+  for_each_digit(s, sh, [&](u32 w, int d) {
+    size_t seg = (size_t)col * sh.nsets + (sh.merged ? 0 : w);
+    u32 b = (u32)(d < 0 ? -d : d) - 1;
+    atomicAdd(&hist[seg * sh.NB + b], 1u);
+  });
 }
 
 // ---- 2. exclusive scan per segment ----------------------------------------------------------
@@ -139,17 +178,24 @@ __global__ void __launch_bounds__(1024) k_msm_scan(u32* __restrict__ hist, u32* 
 }
 
 // ---- 3. scatter (counting sort by bucket) ----------------------------------------------------
-// grid: (ceil(n / threads), nseg)
+// The digits are recomputed from the scalar (one modmul) instead of being stored by pass 1: that is
+// cheaper than writing and re-reading 2-4 bytes per (point, window).
+// entry = index of the base to add | sign << 31; merged mode indexes the table level of window w.
+// grid: (ceil(n / threads), ncols)
 __global__ void __launch_bounds__(MSM_THREADS)
-k_msm_scatter(const int16_t* __restrict__ digits, size_t n, u32 NB, u32* __restrict__ cursor, u32* __restrict__ entries) {
+k_msm_scatter(const Fr* __restrict__ scalars, size_t n, size_t ld, MsmShape sh, u32* __restrict__ cursor,
+              u32* __restrict__ entries) {
   size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   if (i >= n) return;
-  size_t seg = blockIdx.y;
-  int d = digits[seg * n + i];
-  if (d == 0) return;
-  u32 b = (u32)(d < 0 ? -d : d) - 1;
-  u32 pos = atomicAdd(&cursor[seg * NB + b], 1u);
-  entries[seg * n + pos] = (u32)i | (d < 0 ? SIGN_BIT : 0u);
+  u32 col = blockIdx.y;
+  Fr s = load_scalar(scalars, i, ld, col);
+  for_each_digit(s, sh, [&](u32 w, int d) {
+    size_t seg = (size_t)col * sh.nsets + (sh.merged ? 0 : w);
+    u32 b = (u32)(d < 0 ? -d : d) - 1;
+    u32 pos = atomicAdd(&cursor[seg * sh.NB + b], 1u);
+    u32 base = sh.merged ? (u32)(w * sh.tab_stride + sh.base_first + i) : (u32)i;
+    entries[seg * sh.seg_cap + pos] = base | (d < 0 ? SIGN_BIT : 0u);
+  });
 }
 
 // ---- 3b. bucket order: largest buckets first, equal sizes adjacent --------------------------------
@@ -222,7 +268,7 @@ __device__ __forceinline__ void store_xyzz(G1Xyzz* dst, const G1Xyzz& p) { *dst 
 
 // one thread per bucket; starts[] = bucket begin, cursor[] = bucket end (after the scatter)
 __global__ void __launch_bounds__(MSM_THREADS)
-k_msm_accumulate(const G1Affine* __restrict__ bases, const u32* __restrict__ entries, size_t n,
+k_msm_accumulate(const G1Affine* __restrict__ bases, const u32* __restrict__ entries, size_t seg_cap,
                  const u32* __restrict__ starts, const u32* __restrict__ ends, const u32* __restrict__ order, u32 NB,
                  size_t total_buckets, u32 chunk_min, G1Xyzz* __restrict__ buckets, MsmTask* __restrict__ tasks,
                  u32* __restrict__ ntasks, u32 max_tasks) {
@@ -252,20 +298,20 @@ k_msm_accumulate(const G1Affine* __restrict__ bases, const u32* __restrict__ ent
     }
     // else: task buffer exhausted (cannot happen with the sizing in msm_run); fall back to serial
   }
-  const u32* ent = entries + (size_t)seg * n;
+  const u32* ent = entries + (size_t)seg * seg_cap;
   G1Xyzz acc = accumulate_range(bases, ent, begin, my_end);
   store_xyzz(buckets + g, acc);
 }
 
 // extra chunks of oversized buckets -> partial sums
 __global__ void __launch_bounds__(MSM_THREADS)
-k_msm_accumulate_tasks(const G1Affine* __restrict__ bases, const u32* __restrict__ entries, size_t n,
+k_msm_accumulate_tasks(const G1Affine* __restrict__ bases, const u32* __restrict__ entries, size_t seg_cap,
                        const MsmTask* __restrict__ tasks, const u32* __restrict__ ntasks, u32 max_tasks,
                        G1Xyzz* __restrict__ partial) {
   u32 nt = min(*ntasks, max_tasks);
   for (u32 t = blockIdx.x * blockDim.x + threadIdx.x; t < nt; t += gridDim.x * blockDim.x) {
     MsmTask tk = tasks[t];
-    G1Xyzz acc = accumulate_range(bases, entries + (size_t)tk.seg * n, tk.begin, tk.end);
+    G1Xyzz acc = accumulate_range(bases, entries + (size_t)tk.seg * seg_cap, tk.begin, tk.end);
     partial[t] = acc;
   }
 }
@@ -287,7 +333,7 @@ k_msm_fold_tasks(const MsmTask* __restrict__ tasks, const u32* __restrict__ ntas
 // ---- 5. bucket reduction ----------------------------------------------------------------------
 // thread per (segment, chunk): running sums over `chunk` consecutive buckets.
 //   S = sum B_b,  T = sum (b - lo + 1) * B_b   =>   contribution = T + lo * S
-__global__ void __launch_bounds__(128, 3)
+__global__ void __launch_bounds__(MSM_THREADS)
 k_msm_reduce_chunks(const G1Xyzz* __restrict__ buckets, MsmShape sh, size_t nseg, G1Xyzz* __restrict__ partials) {
   size_t g = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   if (g >= nseg * sh.nchunks) return;
@@ -332,9 +378,9 @@ k_msm_reduce_segment(const G1Xyzz* __restrict__ partials, u32 nchunks, G1Xyzz* _
 __global__ void k_msm_combine(const G1Xyzz* __restrict__ segsum, MsmShape sh, size_t ncols, G1Affine* __restrict__ out) {
   size_t col = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   if (col >= ncols) return;
-  const G1Xyzz* S = segsum + col * sh.W;
-  G1Xyzz acc = S[sh.W - 1];
-  for (int w = (int)sh.W - 2; w >= 0; w--) {
+  const G1Xyzz* S = segsum + col * sh.nsets;
+  G1Xyzz acc = S[sh.nsets - 1];
+  for (int w = (int)sh.nsets - 2; w >= 0; w--) {
     for (u32 i = 0; i < sh.c; i++) acc = g1_dbl(acc);
     g1_add(acc, S[w]);
   }
@@ -363,21 +409,19 @@ int g1_sum_run(eon_ctx* ctx, const G1Affine* d_points, size_t n, G1Affine* d_out
 
 // ---- orchestration -----------------------------------------------------------------------------
 static int msm_batch(eon_ctx* ctx, const G1Affine* d_bases, const Fr* d_scalars, size_t n, size_t ncols, size_t ld,
-                     G1Affine* d_out) {
-  const MsmShape sh = msm_shape(n);
-  const size_t nseg = ncols * sh.W;
+                     const MsmShape& sh, G1Affine* d_out) {
+  const size_t nseg = ncols * sh.nsets;
   const size_t total_buckets = nseg * sh.NB;
   const u32 chunk_min = 256;
-  size_t max_tasks_sz = (nseg * n) / chunk_min + 1024;
+  size_t max_tasks_sz = (nseg * sh.seg_cap) / chunk_min + 1024;
   if (max_tasks_sz > 0x7fffffffull) max_tasks_sz = 0x7fffffffull;
   const u32 max_tasks = (u32)max_tasks_sz;
 
-  void *p_dig, *p_hist, *p_cur, *p_ent, *p_bkt, *p_tasks, *p_tpart, *p_part, *p_seg, *p_misc, *p_ord;
+  void *p_hist, *p_cur, *p_ent, *p_bkt, *p_tasks, *p_tpart, *p_part, *p_seg, *p_misc, *p_ord;
   EON_TRY(scratch_get(ctx, SC_MSM_ORDER, total_buckets * sizeof(u32), &p_ord));
-  EON_TRY(scratch_get(ctx, SC_MSM_DIGITS, nseg * n * sizeof(int16_t), &p_dig));
   EON_TRY(scratch_get(ctx, SC_MSM_HIST, total_buckets * sizeof(u32), &p_hist));
   EON_TRY(scratch_get(ctx, SC_MSM_CURSOR, total_buckets * sizeof(u32), &p_cur));
-  EON_TRY(scratch_get(ctx, SC_MSM_ENTRIES, nseg * n * sizeof(u32), &p_ent));
+  EON_TRY(scratch_get(ctx, SC_MSM_ENTRIES, nseg * sh.seg_cap * sizeof(u32), &p_ent));
   EON_TRY(scratch_get(ctx, SC_MSM_BUCKETS, total_buckets * sizeof(G1Xyzz), &p_bkt));
   EON_TRY(scratch_get(ctx, SC_MSM_TASKS, (size_t)max_tasks * sizeof(MsmTask), &p_tasks));
   EON_TRY(scratch_get(ctx, SC_MSM_TASKPART, (size_t)max_tasks * sizeof(G1Xyzz), &p_tpart));
@@ -386,15 +430,13 @@ static int msm_batch(eon_ctx* ctx, const G1Affine* d_bases, const Fr* d_scalars,
   EON_TRY(scratch_get(ctx, SC_MSM_MISC, 256, &p_misc));
   u32* d_ntasks = (u32*)p_misc;
   cudaStream_t st = ctx->stream;
+  const dim3 grid_pts((unsigned)((n + MSM_THREADS - 1) / MSM_THREADS), (unsigned)ncols);
 
   phase_begin(ctx, PH_MSM_DIGITS);
   EON_CUDA(ctx, cudaMemsetAsync(p_hist, 0, total_buckets * sizeof(u32), st));
   EON_CUDA(ctx, cudaMemsetAsync(d_ntasks, 0, sizeof(u32), st));
-  {
-    dim3 grid((unsigned)((n + MSM_THREADS - 1) / MSM_THREADS), (unsigned)ncols);
-    k_msm_digits<<<grid, MSM_THREADS, 0, st>>>(d_scalars, n, ld, sh, (int16_t*)p_dig, (u32*)p_hist);
-    EON_LAUNCHED(ctx);
-  }
+  k_msm_hist<<<grid_pts, MSM_THREADS, 0, st>>>(d_scalars, n, ld, sh, (u32*)p_hist);
+  EON_LAUNCHED(ctx);
   phase_end(ctx, PH_MSM_DIGITS);
 
   phase_begin(ctx, PH_MSM_SCAN);
@@ -403,11 +445,8 @@ static int msm_batch(eon_ctx* ctx, const G1Affine* d_bases, const Fr* d_scalars,
   phase_end(ctx, PH_MSM_SCAN);
 
   phase_begin(ctx, PH_MSM_SCATTER);
-  {
-    dim3 grid((unsigned)((n + MSM_THREADS - 1) / MSM_THREADS), (unsigned)nseg);
-    k_msm_scatter<<<grid, MSM_THREADS, 0, st>>>((const int16_t*)p_dig, n, sh.NB, (u32*)p_cur, (u32*)p_ent);
-    EON_LAUNCHED(ctx);
-  }
+  k_msm_scatter<<<grid_pts, MSM_THREADS, 0, st>>>(d_scalars, n, ld, sh, (u32*)p_cur, (u32*)p_ent);
+  EON_LAUNCHED(ctx);
   phase_end(ctx, PH_MSM_SCATTER);
 
   phase_begin(ctx, PH_MSM_ACCUM);
@@ -415,14 +454,15 @@ static int msm_batch(eon_ctx* ctx, const G1Affine* d_bases, const Fr* d_scalars,
     k_msm_order<<<(unsigned)nseg, 1024, 0, st>>>((const u32*)p_hist, (const u32*)p_cur, sh.NB, (u32*)p_ord);
     EON_LAUNCHED(ctx);
     unsigned blocks = (unsigned)((total_buckets + MSM_THREADS - 1) / MSM_THREADS);
-    k_msm_accumulate<<<blocks, MSM_THREADS, 0, st>>>(d_bases, (const u32*)p_ent, n, (const u32*)p_hist,
+    k_msm_accumulate<<<blocks, MSM_THREADS, 0, st>>>(d_bases, (const u32*)p_ent, sh.seg_cap, (const u32*)p_hist,
                                                      (const u32*)p_cur, (const u32*)p_ord, sh.NB, total_buckets,
                                                      chunk_min, (G1Xyzz*)p_bkt, (MsmTask*)p_tasks, d_ntasks,
                                                      max_tasks);
     EON_LAUNCHED(ctx);
     unsigned tb = (unsigned)ctx->num_sms * 8;
-    k_msm_accumulate_tasks<<<tb, MSM_THREADS, 0, st>>>(d_bases, (const u32*)p_ent, n, (const MsmTask*)p_tasks,
-                                                       d_ntasks, max_tasks, (G1Xyzz*)p_tpart);
+    k_msm_accumulate_tasks<<<tb, MSM_THREADS, 0, st>>>(d_bases, (const u32*)p_ent, sh.seg_cap,
+                                                       (const MsmTask*)p_tasks, d_ntasks, max_tasks,
+                                                       (G1Xyzz*)p_tpart);
     EON_LAUNCHED(ctx);
     k_msm_fold_tasks<<<tb, MSM_THREADS, 0, st>>>((const MsmTask*)p_tasks, d_ntasks, max_tasks,
                                                  (const G1Xyzz*)p_tpart, (G1Xyzz*)p_bkt);
@@ -433,8 +473,8 @@ static int msm_batch(eon_ctx* ctx, const G1Affine* d_bases, const Fr* d_scalars,
   phase_begin(ctx, PH_MSM_REDUCE);
   {
     size_t threads = nseg * sh.nchunks;
-    unsigned blocks = (unsigned)((threads + 127) / 128);
-    k_msm_reduce_chunks<<<blocks, 128, 0, st>>>((const G1Xyzz*)p_bkt, sh, nseg, (G1Xyzz*)p_part);
+    unsigned blocks = (unsigned)((threads + MSM_THREADS - 1) / MSM_THREADS);
+    k_msm_reduce_chunks<<<blocks, MSM_THREADS, 0, st>>>((const G1Xyzz*)p_bkt, sh, nseg, (G1Xyzz*)p_part);
     EON_LAUNCHED(ctx);
     k_msm_reduce_segment<<<(unsigned)nseg, 128, 0, st>>>((const G1Xyzz*)p_part, sh.nchunks, (G1Xyzz*)p_seg);
     EON_LAUNCHED(ctx);
@@ -454,18 +494,76 @@ int msm_run(eon_ctx* ctx, const G1Affine* d_bases, const Fr* d_scalars, size_t n
     return EON_OK;
   }
   if (n >= 0x7fffffffull) return fail(ctx, EON_ERR_BAD_ARG, "msm: more than 2^31 - 1 points");
-  // column batches: bound the sort workspace (digits + entries = 6 bytes per (point, window))
-  const MsmShape sh = msm_shape(n);
-  size_t per_col = n * sh.W * 6 + (size_t)sh.W * sh.NB * (sizeof(G1Xyzz) + 8);
+  MsmShape sh = msm_shape_plain(n);
+  const G1Affine* bases = d_bases;
+  // bases inside the resident SRS and window tables available: all windows share one bucket set
+  if (ctx->d_srs_tab && d_bases >= ctx->d_srs && d_bases + n <= ctx->d_srs + ctx->srs_n) {
+    MsmShape m = msm_shape_merged(n, ctx->srs_tab_c, ctx->srs_n, (u64)(d_bases - ctx->d_srs));
+    if ((u64)n * m.W >= 4ull * m.NB) {  // enough entries per bucket for the larger window to pay off
+      sh = m;
+      bases = ctx->d_srs_tab;
+    }
+  }
+  // column batches: bound the sort workspace
+  size_t per_col = sh.seg_cap * sh.nsets * 4 + (size_t)sh.nsets * sh.NB * (sizeof(G1Xyzz) + 16);
   size_t budget = (size_t)12 << 30;
   size_t batch = budget / per_col;
   if (batch < 1) batch = 1;
   if (batch > 64) batch = 64;
   for (size_t c0 = 0; c0 < ncols; c0 += batch) {
     size_t nc = std::min(batch, ncols - c0);
-    EON_TRY(msm_batch(ctx, d_bases, d_scalars + c0, n, nc, ld, d_out + c0));
+    EON_TRY(msm_batch(ctx, bases, d_scalars + c0, n, nc, ld, sh, d_out + c0));
   }
   return EON_OK;
+}
+
+// ---- window tables: tab[t][i] = 2^(c t) * P_i, affine -------------------------------------------
+// Static bases (the SRS never changes between calls, kzg/src/params.rs:57-77) let every window of a
+// scalar use its own pre-shifted copy of the point, so all W windows of a column fall into ONE set
+// of 2^(c-1) buckets: the bucket reduction shrinks W-fold and c can grow (fewer windows).
+__global__ void __launch_bounds__(128) k_srs_tables(const G1Affine* __restrict__ srs, size_t n, u32 c, u32 W,
+                                                    G1Affine* __restrict__ tab) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  G1Affine p = srs[i];
+  tab[i] = p;
+  G1Xyzz acc = G1Xyzz::from_affine(p);
+  for (u32 t = 1; t < W; t++) {
+    for (u32 k = 0; k < c; k++) acc = g1_dbl(acc);
+    tab[(size_t)t * n + i] = g1_to_affine(acc);
+  }
+}
+
+int srs_build_tables(eon_ctx* ctx, unsigned window_bits) {
+  if (ctx->d_srs_tab) {
+    EON_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    EON_CUDA(ctx, cudaFree(ctx->d_srs_tab));
+    ctx->d_srs_tab = nullptr;
+    ctx->srs_tab_c = 0;
+  }
+  const size_t n = ctx->srs_n;
+  if (n == 0 || window_bits == 0) return EON_OK;
+  if (window_bits < 8 || window_bits > 20) return fail(ctx, EON_ERR_BAD_ARG, "window bits must be in [8, 20]");
+  const u32 c = window_bits, W = (256 + c - 1) / c;
+  if ((u64)W * n >= 0x7fffffffull) return fail(ctx, EON_ERR_BAD_ARG, "SRS too large for window tables");
+  EON_CUDA(ctx, cudaMalloc(&ctx->d_srs_tab, (size_t)W * n * sizeof(G1Affine)));
+  k_srs_tables<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(ctx->d_srs, n, c, W, ctx->d_srs_tab);
+  EON_LAUNCHED(ctx);
+  ctx->srs_tab_c = c;
+  return EON_OK;
+}
+
+// default table policy after an SRS load: c = log2(n) - 2 (clamped to [12, 19]) when the SRS has at
+// least 2^14 points and the tables fit in 24 GiB; otherwise no tables (plain per-window buckets).
+int srs_build_default_tables(eon_ctx* ctx) {
+  const size_t n = ctx->srs_n;
+  if (n < ((size_t)1 << 14)) return srs_build_tables(ctx, 0);
+  int c = (int)ceil_log2(n) - 2;
+  if (c < 12) c = 12;
+  if (c > 19) c = 19;
+  u32 W = (256 + c - 1) / c;
+  if ((size_t)W * n * sizeof(G1Affine) > ((size_t)24 << 30)) return srs_build_tables(ctx, 0);
+  return srs_build_tables(ctx, (unsigned)c);
 }
 
 // ---- synthetic SRS: g1_powers[i] = alpha^i * G (init_srs_unsafe, kzg/src/params.rs:123-139) ----
@@ -485,13 +583,14 @@ int srs_generate(eon_ctx* ctx, const Fr& alpha, size_t n) {
     EON_CUDA(ctx, cudaFree(ctx->d_srs));
     ctx->d_srs = nullptr;
     ctx->srs_n = 0;
+    EON_TRY(srs_build_tables(ctx, 0));
   }
   if (n == 0) return EON_OK;
   EON_CUDA(ctx, cudaMalloc(&ctx->d_srs, n * sizeof(G1Affine)));
   k_srs_generate<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(ctx->d_srs, n, alpha);
   EON_LAUNCHED(ctx);
   ctx->srs_n = n;
-  return EON_OK;
+  return srs_build_default_tables(ctx);
 }
 
 }  // namespace eon

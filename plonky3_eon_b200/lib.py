@@ -46,6 +46,8 @@ _SIGS = {
     "eon_srs_generate_unsafe": (C.c_int, [C.c_void_p, _u64p, C.c_size_t]),
     "eon_srs_size": (C.c_size_t, [C.c_void_p]),
     "eon_srs_read": (C.c_int, [C.c_void_p, C.c_size_t, C.c_size_t, _u64p]),
+    "eon_srs_set_window_tables": (C.c_int, [C.c_void_p, C.c_uint]),
+    "eon_srs_window_bits": (C.c_uint, [C.c_void_p]),
     "eon_msm_srs_dev": (C.c_int, [C.c_void_p, _u64p, C.c_size_t, C.c_size_t, C.c_size_t, _u64p]),
     "eon_msm_srs": (C.c_int, [C.c_void_p, _u64p, C.c_size_t, C.c_size_t, C.c_size_t, _u64p]),
     "eon_msm_points": (C.c_int, [C.c_void_p, _u64p, _u64p, C.c_size_t, _u64p]),

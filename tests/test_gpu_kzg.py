@@ -135,6 +135,34 @@ def test_msm_skewed_scalars(ctx, kind):
     assert pt(out) == g1.msm_via_dlog(okzg.srs_dlogs(n - 1, alpha), vals)
 
 
+@pytest.mark.parametrize("log_n,bits", [(15, 0), (15, 8), (15, 13), (16, 17), (18, 20)])
+def test_window_tables_and_index_ranges(ctx, log_n, bits):
+    """MSMs over the resident SRS with explicit window tables (all windows share one bucket set) and
+    over index sub-ranges (the multi-GPU shard form) agree with the discrete-log shortcut."""
+    import ctypes as C
+    n = 1 << log_n
+    alpha = 55555
+    pcs = pcs_new(ctx, n - 1, alpha)
+    ctx.call("eon_srs_set_window_tables", bits)
+    assert int(ctx.lib.eon_srs_window_bits(ctx.h)) == bits
+    rng = np.random.default_rng(bits + log_n)
+    sc = fr.random_wire(rng, n * 2).reshape(n, 2, 4)
+    dl = okzg.srs_dlogs(n - 1, alpha)
+    out = np.zeros((2, 8), dtype=np.uint64)
+    ctx.call("eon_msm_srs", sc, n, 2, 2, out)
+    cols = [fr.from_wire(sc[:, c, :]) for c in range(2)]
+    for c in range(2):
+        assert pt(out[c]) == g1.msm_via_dlog(dl, cols[c]), c
+    # index range [first, first + m): scalars row r pairs with srs[first + r]
+    first, m = n // 3 + 1, n // 2 + 5
+    d = ctx.dev_alloc(m * 2 * 32)
+    ctx.h2d(d, np.ascontiguousarray(sc[:m]))
+    ctx.call("eon_msm_srs_range_dev", C.c_void_p(d), first, m, 2, 2, out)
+    ctx.dev_free(d)
+    for c in range(2):
+        assert pt(out[c]) == g1.msm_via_dlog(dl[first:first + m], cols[c][:m]), c
+
+
 # ---- kzg/src/tests.rs ---------------------------------------------------------------------------
 def test_kzg_batch_verification_vectors(ctx):
     # tests.rs:73-137: alpha = 42
