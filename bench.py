@@ -206,6 +206,8 @@ def run_eon(args):
     stream = torch.cuda.current_stream()
     ctx = eon.Context(local, stream=stream.cuda_stream)
     pcs = eon.GpuKzgPcs.new(rows - 1, ALPHA, ctx=ctx)           # synthetic SRS alpha^i * G on the device
+    if args.window_bits >= 0:                                    # default: the library's own table policy
+        ctx.call("eon_srs_set_window_tables", args.window_bits)
     shift_one = field.to_wire(1)
     shift_lde = field.to_wire(SHIFT_LDE)
 
@@ -361,6 +363,8 @@ def main():
     ap.add_argument("--cols", type=int, default=16)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--warmup-ref", type=int, default=0)
+    ap.add_argument("--window-bits", type=int, default=-1,
+                    help="MSM window tables: -1 library default, 0 none (plain c=16), 8..20 explicit")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
