@@ -292,7 +292,7 @@ def run_eon(args):
     imad_wide = ctx.imad_peak_tops(2)
     modmul_g = ctx.modmul_gmuls(1)
     c_bits = int(ctx.lib.eon_srs_window_bits(ctx.h)) or 16              # window tables in use (0 = plain c = 16)
-    W = (256 + c_bits - 1) // c_bits
+    W = (255 + c_bits - 1) // c_bits                                    # msm_windows() in csrc/msm.cu
     adds = rows * cols * W                                              # one mixed add per (point, window, column)
     acc_ms = phases["msm_accumulate"] / args.steps
     achieved = adds * MODMUL_PER_MIXED_ADD * IMAD_PER_MODMUL / (acc_ms * 1e-3) / 1e12

@@ -37,6 +37,10 @@ struct MsmShape {
   u64 seg_cap;     // entry slots per segment: n (plain) or n * W (merged)
 };
 
+// Windows needed for a canonical scalar (< r < 2^254) in signed c-bit digits: the top window must
+// absorb the last carry without wrapping, i.e. hold at most c - 1 scalar bits: W*c >= 255.
+static u32 msm_windows(u32 c) { return (255 + c - 1) / c; }
+
 static u32 ceil_log2(size_t n) {
   u32 lg = 0;
   while (((size_t)1 << lg) < n) lg++;
@@ -50,7 +54,7 @@ static MsmShape msm_shape_plain(size_t n) {
   MsmShape s;
   memset(&s, 0, sizeof(s));
   s.c = (u32)c;
-  s.W = (256 + s.c - 1) / s.c;
+  s.W = msm_windows(s.c);
   s.NB = 1u << (s.c - 1);
   s.nsets = s.W;
   s.merged = 0;
@@ -64,7 +68,7 @@ static MsmShape msm_shape_merged(size_t n, u32 c, u64 tab_stride, u64 first) {
   MsmShape s;
   memset(&s, 0, sizeof(s));
   s.c = c;
-  s.W = (256 + c - 1) / c;
+  s.W = msm_windows(c);
   s.NB = 1u << (c - 1);
   s.nsets = 1;
   s.merged = 1;
@@ -79,7 +83,8 @@ static MsmShape msm_shape_merged(size_t n, u32 c, u64 tab_stride, u64 first) {
 // ---- 1. scalar -> signed window digits --------------------------------------------------------
 // s * 1 * R^-1 gives the canonical integer (the reference hands halo2curves Montgomery scalars,
 // bn254/src/curve.rs:173-174).  Digits d_w in [-2^(c-1), 2^(c-1)) with sum d_w 2^(c w) = scalar;
-// W*c >= 256 > 254 + 2 guarantees the top window absorbs the last carry.  f(w, d) for d != 0.
+// The top window never wraps: W*c >= 255 leaves it at most c - 1 scalar bits, so raw + carry <=
+// 2^(c-1), which still has a bucket (index 2^(c-1) - 1).  f(w, d) for d != 0.
 template <class F>
 __device__ __forceinline__ void for_each_digit(const Fr& s, const MsmShape& sh, F f) {
   u32 k[9];
@@ -99,7 +104,7 @@ __device__ __forceinline__ void for_each_digit(const Fr& s, const MsmShape& sh, 
     }
     raw += carry;
     int d;
-    if (raw >= half) {
+    if (raw >= half && w + 1 < sh.W) {
       d = (int)raw - (int)(1u << c);
       carry = 1;
     } else {
@@ -557,7 +562,7 @@ int srs_build_tables(eon_ctx* ctx, unsigned window_bits) {
   const size_t n = ctx->srs_n;
   if (n == 0 || window_bits == 0) return EON_OK;
   if (window_bits < 8 || window_bits > 20) return fail(ctx, EON_ERR_BAD_ARG, "window bits must be in [8, 20]");
-  const u32 c = window_bits, W = (256 + c - 1) / c;
+  const u32 c = window_bits, W = msm_windows(c);
   if ((u64)W * n >= 0x7fffffffull) return fail(ctx, EON_ERR_BAD_ARG, "SRS too large for window tables");
   EON_CUDA(ctx, cudaMalloc(&ctx->d_srs_tab, (size_t)W * n * sizeof(G1Affine)));
   k_srs_tables<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(ctx->d_srs, n, c, W, ctx->d_srs_tab);
@@ -566,17 +571,24 @@ int srs_build_tables(eon_ctx* ctx, unsigned window_bits) {
   return EON_OK;
 }
 
-// default table policy after an SRS load: c = log2(n) - 2 (clamped to [12, 19]) when the SRS has at
-// least 2^14 points and the tables fit in 24 GiB; otherwise no tables (plain per-window buckets).
+// default table policy after an SRS load (n >= 2^14 points, tables within 24 GiB): the c in [10, 20]
+// that minimises  n * W(c) mixed additions (10 modmul)  +  2^(c-1) bucket-reduction steps (~60 modmul
+// with the chunk offsets); 2^20 points -> c = 17 (15 windows).  Otherwise plain per-window buckets.
 int srs_build_default_tables(eon_ctx* ctx) {
   const size_t n = ctx->srs_n;
   if (n < ((size_t)1 << 14)) return srs_build_tables(ctx, 0);
-  int c = (int)ceil_log2(n) - 2;
-  if (c < 12) c = 12;
-  if (c > 19) c = 19;
-  u32 W = (256 + c - 1) / c;
+  u32 best_c = 0;
+  double best = 0;
+  for (u32 c = 10; c <= 20; c++) {
+    double cost = (double)n * msm_windows(c) * 10.0 + (double)(1u << (c - 1)) * 60.0;
+    if (!best_c || cost < best) {
+      best_c = c;
+      best = cost;
+    }
+  }
+  u32 W = msm_windows(best_c);
   if ((size_t)W * n * sizeof(G1Affine) > ((size_t)24 << 30)) return srs_build_tables(ctx, 0);
-  return srs_build_tables(ctx, (unsigned)c);
+  return srs_build_tables(ctx, best_c);
 }
 
 // ---- synthetic SRS: g1_powers[i] = alpha^i * G (init_srs_unsafe, kzg/src/params.rs:123-139) ----
