@@ -353,7 +353,107 @@ def run_eon(args):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------------------------------------
+def run_msm(args):
+    """BASELINE configs[2]: standalone G1 Pippenger MSM, 2^log_n points x `cols` scalar columns with
+    random Fr scalars over the synthetic SRS.  N GPUs: point-index sharding ("strong": total points
+    fixed), per-rank partial sums all_gathered over NCCL and added with eon_g1_sum."""
+    import ctypes as C
+
+    import torch
+    import torch.distributed as dist
+
+    import plonky3_eon_b200 as eon
+    from plonky3_eon_b200 import dist as edist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the eon arm has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    n, cols = 1 << args.log_n, args.msm_cols
+    stream = torch.cuda.current_stream()
+    ctx = eon.Context(local, stream=stream.cuda_stream)
+    pcs = eon.GpuKzgPcs.new(n - 1, ALPHA, ctx=ctx)              # replicated SRS (every rank reads its slice)
+    if args.window_bits >= 0:
+        ctx.call("eon_srs_set_window_tables", args.window_bits)
+    first, cnt = edist.index_shard(n, world, rank)
+    host = synth_trace(42, cnt, cols)                            # seed 42: bn254/benches/bench_curve.rs:40
+    d_sc = torch.from_numpy(host.view(np.int64)).to(dev)
+    out = np.zeros((cols, 8), dtype=np.uint64)
+    gathered = [torch.empty(cols * 8, dtype=torch.int64, device=dev) for _ in range(world)] if world > 1 else None
+    total = np.zeros((cols, 8), dtype=np.uint64)
+
+    def step():
+        ctx.call("eon_msm_srs_range_dev", C.c_void_p(d_sc.data_ptr()), first, cnt, cols, cols, out)
+        if world > 1:
+            t = torch.from_numpy(out.view(np.int64).reshape(-1)).to(dev)
+            dist.all_gather(gathered, t)
+            parts = torch.stack(gathered).cpu().numpy().view(np.uint64).reshape(world, cols, 8)
+            for c in range(cols):
+                ctx.call("eon_g1_sum", np.ascontiguousarray(parts[:, c]), world, total[c])
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    ctx.phase_reset()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = ctx.launch_count()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        step()
+    e1.record(stream)
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item())
+    launches = ctx.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    phases = ctx.phase_ms()
+    if rank == 0:
+        imad_peak = max(ctx.imad_peak_tops(0), ctx.imad_peak_tops(1))
+        c_bits = int(ctx.lib.eon_srs_window_bits(ctx.h)) or min(16, max(2, (cnt - 1).bit_length() - 3))
+        W = (255 + c_bits - 1) // c_bits
+        acc_ms = phases["msm_accumulate"] / args.steps
+        ops = cnt * cols * W * MODMUL_PER_MIXED_ADD * IMAD_PER_MODMUL
+        line = {
+            "metric": "msm_points_per_s", "value": n * cols * args.steps / (ms * 1e-3), "unit": "points/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "u256 (8x32-bit Montgomery limbs, BN254 Fr/Fq)", "data": "synthetic",
+            "config": {"workload": f"standalone G1 MSM, 2^{args.log_n} points x {cols} scalar column(s), random Fr "
+                                   f"scalars (BASELINE configs[2]); point-index sharded over {world} GPU(s)",
+                       "points": n, "cols": cols, "msm_window_bits": c_bits, "msm_windows": W,
+                       "l2": f"scalars {cnt * cols * 32 >> 20} MiB + bases {cnt * W * 64 >> 20} MiB per GPU"},
+            "gpu_launches": launches, "clocks": clocks,
+            "phase_ms_per_step": {k: v / args.steps for k, v in phases.items()},
+            "roofline": {"kernel": "k_msm_accumulate", "bound": "imad", "achieved": ops / (acc_ms * 1e-3) / 1e12,
+                         "peak": imad_peak, "unit": "TIMAD/s", "frac": ops / (acc_ms * 1e-3) / 1e12 / imad_peak,
+                         "traffic": None, "algorithmic_ops_per_launch": ops, "launch_ms": acc_ms},
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
+    # keep stdout to the one JSON line: NCCL prints its version banner there at NCCL_DEBUG=VERSION
+    if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -365,9 +465,15 @@ def main():
     ap.add_argument("--warmup-ref", type=int, default=0)
     ap.add_argument("--window-bits", type=int, default=-1,
                     help="MSM window tables: -1 library default, 0 none (plain c=16), 8..20 explicit")
+    ap.add_argument("--workload", default="commit", choices=["commit", "msm"],
+                    help="commit: KZG commit + LDE (the headline metric); msm: standalone MSM (configs[2])")
+    ap.add_argument("--log-n", type=int, default=24, help="msm workload: log2 of the point count")
+    ap.add_argument("--msm-cols", type=int, default=1, help="msm workload: scalar columns sharing the bases")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "msm":
+        run_msm(args)
     else:
         run_eon(args)
 

@@ -108,9 +108,9 @@ int eon_srs_generate_unsafe(eon_ctx* ctx, const uint64_t alpha[4], size_t n);
 /* number of G1 powers resident (max_degree + 1), 0 if none */
 size_t eon_srs_size(const eon_ctx* ctx);
 /* Window tables for MSMs over the resident SRS: tab[t][i] = 2^(c t) * g1_powers[i] for
- * t < ceil(256 / c), c = window_bits in [8, 20]; 0 drops the tables (plain per-window buckets).
- * Costs ceil(256/c) x the SRS memory; built automatically (c = log2(n) - 2) by the two loaders
- * above for n >= 2^14.  eon_srs_window_bits returns the c in use (0 = no tables). */
+ * t < ceil(255 / c), c = window_bits in [8, 20]; 0 drops the tables (plain per-window buckets).
+ * Costs ceil(255/c) x the SRS memory; built automatically by the two loaders above for n >= 2^14
+ * (c chosen by a cost model: 17 for 2^20 points, 20 for 2^24), as long as they fit in 64 GiB.  eon_srs_window_bits returns the c in use (0 = no tables). */
 int eon_srs_set_window_tables(eon_ctx* ctx, unsigned window_bits);
 unsigned eon_srs_window_bits(const eon_ctx* ctx);
 /* copy SRS points [first, first + n) back to the host as affine wire points */
@@ -139,6 +139,15 @@ int eon_kzg_commit(eon_ctx* ctx, const uint64_t* h_evals, unsigned log_h, size_t
                    uint64_t* h_commit_xy, eon_handle* out_handle);
 int eon_kzg_commit_dev(eon_ctx* ctx, const uint64_t* d_evals, unsigned log_h, size_t width, const uint64_t shift[4],
                        uint64_t* h_commit_xy, eon_handle* out_handle);
+/* KzgMmcs::commit (kzg/src/mmcs.rs:155-190) for ONE matrix: the columns are taken as polynomials
+ * in COEFFICIENT form (no iDFT); `rows` may be any height (not only powers of two).
+ * commitment[c] = commit_column(matrix[:, c]) (mmcs.rs:155-165).  The matrix is kept on the device
+ * behind `*out_handle`, so eon_kzg_open on that handle is KzgMmcs::open_batch (mmcs.rs:192-237).
+ * Fails with EON_ERR_SRS_TOO_SHORT if rows - 1 > max_degree (mmcs.rs:177-179). */
+int eon_kzg_commit_coeffs(eon_ctx* ctx, const uint64_t* h_coeffs, size_t rows, size_t width, uint64_t* h_commit_xy,
+                          eon_handle* out_handle);
+int eon_kzg_commit_coeffs_dev(eon_ctx* ctx, const uint64_t* d_coeffs, size_t rows, size_t width,
+                              uint64_t* h_commit_xy, eon_handle* out_handle);
 /* copy the retained coefficient matrix (natural order, h x width) to the host */
 int eon_kzg_read_coeffs(eon_ctx* ctx, eon_handle h, uint64_t* h_out);
 /* get_evaluations_on_domain (pcs.rs:267-287) on the coset shift*<omega_{2^log_size}>,

@@ -143,3 +143,52 @@ def split_domains(domain, num_chunks):
 
 def split_evals(num_chunks, evals):
     return [[row[:] for row in evals[i::num_chunks]] for i in range(num_chunks)]
+
+
+# ---- KzgMmcs (kzg/src/mmcs.rs) ------------------------------------------------------------------
+def _log2_ceil(n):
+    """n.next_power_of_two().trailing_zeros() (mmcs.rs:203,209)."""
+    lg = 0
+    while (1 << lg) < n:
+        lg += 1
+    return lg
+
+
+def mmcs_commit(srs, matrices):
+    """mmcs.rs:155-190: every column of every matrix, taken as coefficients, through commit_column.
+    Returns commitments[matrix][col]."""
+    out = []
+    for m in matrices:
+        h = len(m)
+        deg = max(h - 1, 0)
+        if deg > len(srs) - 1:
+            raise DegreeTooLarge(f"degree {deg} > max {len(srs) - 1}")
+        w = len(m[0]) if h else 0
+        out.append([commit_column(srs, [m[r][c] for r in range(h)]) for c in range(w)])
+    return out
+
+
+def mmcs_local_index(index, height, log2_max_height):
+    """mmcs.rs:209-214."""
+    lg = _log2_ceil(height)
+    li = index >> (log2_max_height - lg) if log2_max_height >= lg else index
+    return li % height
+
+
+def mmcs_open_batch(srs, index, matrices):
+    """mmcs.rs:192-237.  Returns (opened_values[matrix][col], witnesses[matrix][col])."""
+    max_height = max((len(m) for m in matrices), default=0)
+    lmax = _log2_ceil(max_height)
+    opened, wits = [], []
+    for m in matrices:
+        h = len(m)
+        w = len(m[0]) if h else 0
+        point = mmcs_local_index(index, h, lmax)
+        row, mw = [], []
+        for c in range(w):
+            q, v = quotient_and_eval([m[r][c] for r in range(h)], point)
+            row.append(v)
+            mw.append(commit_column(srs, q))
+        opened.append(row)
+        wits.append(mw)
+    return opened, wits

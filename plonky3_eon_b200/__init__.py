@@ -8,4 +8,5 @@ Importing it does not require a GPU; creating a Context / running anything does.
 from .lib import Context, DegreeTooLarge, EonError, default_context, load  # noqa: F401
 from .dft import GpuDft  # noqa: F401
 from .pcs import GpuKzgPcs, TwoAdicMultiplicativeCoset  # noqa: F401
+from .mmcs import GpuKzgMmcs  # noqa: F401
 from . import field  # noqa: F401

@@ -388,6 +388,33 @@ int eon_g1_sum(eon_ctx* ctx, const uint64_t* h_points_xy, size_t n, uint64_t* h_
 }
 
 // ---- KZG ---------------------------------------------------------------------------------------
+// coefficient buffers come from a small pool of freed ones (see eon_handle_free)
+static int coeff_buffer_get(eon_ctx* ctx, size_t need, Fr** out, size_t* out_cap) {
+  for (size_t i = 0; i < ctx->coeff_pool.size(); i++) {
+    if (ctx->coeff_pool[i].first >= need && ctx->coeff_pool[i].first <= 2 * need) {
+      *out_cap = ctx->coeff_pool[i].first;
+      *out = (Fr*)ctx->coeff_pool[i].second;
+      ctx->coeff_pool.erase(ctx->coeff_pool.begin() + i);
+      return EON_OK;
+    }
+  }
+  EON_CUDA(ctx, cudaMalloc(out, need));
+  *out_cap = need;
+  return EON_OK;
+}
+
+static eon_handle handle_new(eon_ctx* ctx, Fr* d_coeffs, size_t rows, unsigned log_h, size_t width, size_t cap) {
+  ProverMatrix pm;
+  pm.d_coeffs = d_coeffs;
+  pm.rows = rows;
+  pm.log_h = log_h;
+  pm.width = width;
+  pm.cap = cap;
+  eon_handle id = ctx->next_handle++;
+  ctx->handles[id] = pm;
+  return id;
+}
+
 static int kzg_commit_locked(eon_ctx* ctx, const uint64_t* d_evals, unsigned log_h, size_t width,
                              const uint64_t shift[4], uint64_t* h_commit_xy, eon_handle* out_handle) {
   if (!out_handle) return fail(ctx, EON_ERR_BAD_ARG, "null handle pointer");
@@ -403,34 +430,71 @@ static int kzg_commit_locked(eon_ctx* ctx, const uint64_t* d_evals, unsigned log
   }
   if (width && (!d_evals || !h_commit_xy)) return fail(ctx, EON_ERR_BAD_ARG, "null buffer");
   Fr* d_coeffs = nullptr;
-  size_t need = mat_bytes(log_h, width) + 32, cap = 0;
-  for (size_t i = 0; i < ctx->coeff_pool.size(); i++) {
-    if (ctx->coeff_pool[i].first >= need && ctx->coeff_pool[i].first <= 2 * need) {
-      cap = ctx->coeff_pool[i].first;
-      d_coeffs = (Fr*)ctx->coeff_pool[i].second;
-      ctx->coeff_pool.erase(ctx->coeff_pool.begin() + i);
-      break;
-    }
-  }
-  if (!d_coeffs) {
-    EON_CUDA(ctx, cudaMalloc(&d_coeffs, need));
-    cap = need;
-  }
+  size_t cap = 0;
+  EON_TRY(coeff_buffer_get(ctx, mat_bytes(log_h, width) + 32, &d_coeffs, &cap));
   int rc = ntt_inverse(ctx, (const Fr*)d_evals, d_coeffs, log_h, width, s, LAYOUT_NATURAL);
   if (rc == EON_OK) rc = msm_to_host(ctx, ctx->d_srs, d_coeffs, h, width, width, h_commit_xy);
   if (rc != EON_OK) {
     cudaFree(d_coeffs);
     return rc;
   }
-  ProverMatrix pm;
-  pm.d_coeffs = d_coeffs;
-  pm.log_h = log_h;
-  pm.width = width;
-  pm.cap = cap;
-  eon_handle id = ctx->next_handle++;
-  ctx->handles[id] = pm;
-  *out_handle = id;
+  *out_handle = handle_new(ctx, d_coeffs, h, log_h, width, cap);
   return EON_OK;
+}
+
+// KzgMmcs::commit (kzg/src/mmcs.rs:155-190): the matrix columns ARE the coefficient vectors (no
+// iDFT), any height.  d_coeffs_in is copied into a pooled buffer that the handle owns.
+static int kzg_commit_coeffs_locked(eon_ctx* ctx, const uint64_t* src, bool src_is_host, size_t rows, size_t width,
+                                    uint64_t* h_commit_xy, eon_handle* out_handle) {
+  if (!out_handle) return fail(ctx, EON_ERR_BAD_ARG, "null handle pointer");
+  *out_handle = 0;
+  if (width > 0xffffffffull || (width && rows > (~(size_t)0) / (width * sizeof(Fr))))
+    return fail(ctx, EON_ERR_BAD_ARG, "matrix too large");
+  const size_t degree = rows ? rows - 1 : 0;  // ensure_supported(height.saturating_sub(1)), mmcs.rs:177-179
+  if (ctx->srs_n == 0 || degree > ctx->srs_n - 1) {
+    char b[128];
+    snprintf(b, sizeof(b), "DegreeTooLarge: degree %zu > max %zu", degree, ctx->srs_n ? ctx->srs_n - 1 : 0);
+    return fail(ctx, EON_ERR_SRS_TOO_SHORT, b);
+  }
+  const size_t bytes = rows * width * sizeof(Fr);
+  if (bytes && (!src || !h_commit_xy)) return fail(ctx, EON_ERR_BAD_ARG, "null buffer");
+  Fr* d_coeffs = nullptr;
+  size_t cap = 0;
+  EON_TRY(coeff_buffer_get(ctx, bytes + 32, &d_coeffs, &cap));
+  int rc = EON_OK;
+  if (bytes) {
+    cudaError_t e = cudaMemcpyAsync(d_coeffs, src, bytes, src_is_host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice,
+                                    ctx->stream);
+    if (e != cudaSuccess) rc = fail(ctx, EON_ERR_CUDA, std::string("copy of the coefficient matrix failed: ") + cudaGetErrorString(e));
+  }
+  if (rc == EON_OK) rc = msm_to_host(ctx, ctx->d_srs, d_coeffs, rows, width, width, h_commit_xy);
+  if (rc != EON_OK) {
+    cudaFree(d_coeffs);
+    return rc;
+  }
+  unsigned log_h = NOT_POW2;
+  if (rows && (rows & (rows - 1)) == 0) {
+    log_h = 0;
+    while (((size_t)1 << log_h) < rows) log_h++;
+  }
+  *out_handle = handle_new(ctx, d_coeffs, rows, log_h, width, cap);
+  return EON_OK;
+}
+
+int eon_kzg_commit_coeffs(eon_ctx* ctx, const uint64_t* h_coeffs, size_t rows, size_t width, uint64_t* h_commit_xy,
+                          eon_handle* out_handle) {
+  if (!ctx) return EON_ERR_BAD_ARG;
+  Lock lk(ctx);
+  EON_TRY(set_device(ctx));
+  return kzg_commit_coeffs_locked(ctx, h_coeffs, true, rows, width, h_commit_xy, out_handle);
+}
+
+int eon_kzg_commit_coeffs_dev(eon_ctx* ctx, const uint64_t* d_coeffs, size_t rows, size_t width,
+                              uint64_t* h_commit_xy, eon_handle* out_handle) {
+  if (!ctx) return EON_ERR_BAD_ARG;
+  Lock lk(ctx);
+  EON_TRY(set_device(ctx));
+  return kzg_commit_coeffs_locked(ctx, d_coeffs, false, rows, width, h_commit_xy, out_handle);
 }
 
 int eon_kzg_commit_dev(eon_ctx* ctx, const uint64_t* d_evals, unsigned log_h, size_t width, const uint64_t shift[4],
@@ -495,7 +559,7 @@ int eon_kzg_read_coeffs(eon_ctx* ctx, eon_handle h, uint64_t* h_out) {
   EON_TRY(set_device(ctx));
   ProverMatrix pm;
   EON_TRY(find_handle(ctx, h, &pm));
-  size_t b = mat_bytes(pm.log_h, pm.width);
+  size_t b = pm.rows * pm.width * sizeof(Fr);
   if (b == 0) return EON_OK;
   if (!h_out) return fail(ctx, EON_ERR_BAD_ARG, "null output");
   EON_CUDA(ctx, cudaMemcpyAsync(h_out, pm.d_coeffs, b, cudaMemcpyDeviceToHost, ctx->stream));
@@ -508,6 +572,8 @@ static int evals_on_coset_locked(eon_ctx* ctx, eon_handle h, unsigned log_size, 
   EON_TRY(find_handle(ctx, h, &pm));
   Fr s;
   EON_TRY(check_shift(ctx, shift, &s));
+  if (pm.log_h == NOT_POW2)
+    return fail(ctx, EON_ERR_BAD_ARG, "prover data has a non-power-of-two height (KzgMmcs matrix): no coset evaluation");
   if (log_size < pm.log_h)
     return fail(ctx, EON_ERR_BAD_ARG, "evaluation domain smaller than the committed polynomial length");
   EON_TRY(check_dims(ctx, log_size, pm.width));
@@ -566,14 +632,14 @@ int eon_kzg_open(eon_ctx* ctx, eon_handle h, const uint64_t* h_points, size_t np
   EON_TRY(set_device(ctx));
   ProverMatrix pm;
   EON_TRY(find_handle(ctx, h, &pm));
-  const size_t w = pm.width, rows = (size_t)1 << pm.log_h;
+  const size_t w = pm.width, rows = pm.rows;
   if (npoints == 0 || w == 0) return EON_OK;
   if (!h_points || !h_values || !h_witness_xy) return fail(ctx, EON_ERR_BAD_ARG, "null buffer");
   for (size_t p = 0; p < npoints; p++)
     if (!fr_wire_is_canonical(h_points + 4 * p)) return fail(ctx, EON_ERR_BAD_ARG, "opening point is not canonical");
   // the quotient of a length-h polynomial has h-1 coefficients: witness = MSM over srs[..h-1]
   // (commit_column(&quotient), kzg/src/pcs.rs:316); degree guard as in util.rs:38
-  if (rows - 1 > ctx->srs_n) return fail(ctx, EON_ERR_SRS_TOO_SHORT, "DegreeTooLarge: quotient longer than the SRS");
+  if (rows && rows - 1 > ctx->srs_n) return fail(ctx, EON_ERR_SRS_TOO_SHORT, "DegreeTooLarge: quotient longer than the SRS");
   const size_t ncols = npoints * w;
   void *d_quot = nullptr, *d_vals = nullptr, *d_wit = nullptr;
   EON_TRY(scratch_get(ctx, SC_QUOT, rows * ncols * sizeof(Fr) + 32, &d_quot));
@@ -583,7 +649,7 @@ int eon_kzg_open(eon_ctx* ctx, eon_handle h, const uint64_t* h_points, size_t np
     Fr z = fr_from_wire(h_points + 4 * p);
     EON_TRY(quotient_run(ctx, pm.d_coeffs, rows, w, ncols, z, (Fr*)d_quot + p * w, (Fr*)d_vals + p * w));
   }
-  EON_TRY(msm_run(ctx, ctx->d_srs, (const Fr*)d_quot, rows - 1, ncols, ncols, (G1Affine*)d_wit));
+  EON_TRY(msm_run(ctx, ctx->d_srs, (const Fr*)d_quot, rows ? rows - 1 : 0, ncols, ncols, (G1Affine*)d_wit));
   EON_CUDA(ctx, cudaMemcpyAsync(h_values, d_vals, ncols * sizeof(Fr), cudaMemcpyDeviceToHost, ctx->stream));
   EON_CUDA(ctx, cudaMemcpyAsync(h_witness_xy, d_wit, ncols * sizeof(G1Affine), cudaMemcpyDeviceToHost, ctx->stream));
   EON_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

@@ -39,11 +39,14 @@ struct TwiddleKey {
 };
 
 struct ProverMatrix {
-  Fr* d_coeffs;  // natural order, h x width
-  unsigned log_h;
+  Fr* d_coeffs;  // natural order, rows x width
+  size_t rows;   // any height for KzgMmcs matrices (kzg/src/mmcs.rs:168-190); 2^log_h for KzgPcs
+  unsigned log_h;  // log2(rows), or NOT_POW2 when rows is not a power of two (no NTT on it)
   size_t width;
   size_t cap;    // bytes allocated behind d_coeffs
 };
+
+constexpr unsigned NOT_POW2 = 0xffffffffu;
 
 // grow-only device scratch buffers, one per role, reused across calls (no allocation in steady state)
 struct Scratch {

@@ -571,7 +571,7 @@ int srs_build_tables(eon_ctx* ctx, unsigned window_bits) {
   return EON_OK;
 }
 
-// default table policy after an SRS load (n >= 2^14 points, tables within 24 GiB): the c in [10, 20]
+// default table policy after an SRS load (n >= 2^14 points, tables within 64 GiB): the c in [10, 20]
 // that minimises  n * W(c) mixed additions (10 modmul)  +  2^(c-1) bucket-reduction steps (~60 modmul
 // with the chunk offsets); 2^20 points -> c = 17 (15 windows).  Otherwise plain per-window buckets.
 int srs_build_default_tables(eon_ctx* ctx) {
@@ -587,7 +587,7 @@ int srs_build_default_tables(eon_ctx* ctx) {
     }
   }
   u32 W = msm_windows(best_c);
-  if ((size_t)W * n * sizeof(G1Affine) > ((size_t)24 << 30)) return srs_build_tables(ctx, 0);
+  if ((size_t)W * n * sizeof(G1Affine) > ((size_t)64 << 30)) return srs_build_tables(ctx, 0);
   return srs_build_tables(ctx, best_c);
 }
 

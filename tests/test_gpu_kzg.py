@@ -327,3 +327,47 @@ def test_config2_shape_commit_and_open_properties(ctx):
         assert fr.from_wire(opened[0][0][0][c])[0] == fz
         assert pt(proof[0][0][0][c]) == kG((f_alpha[c] - fz) * inv % P)
     pdata[0].free()
+
+
+# ---- KzgMmcs (kzg/src/mmcs.rs:155-237; kzg/src/tests.rs:50-70) -----------------------------------
+def test_mmcs_roundtrip_kat(ctx):
+    from plonky3_eon_b200 import GpuKzgMmcs
+    mmcs = GpuKzgMmcs.new(4, 5, ctx=ctx)
+    m = fr.to_wire([1, 2, 3, 4]).reshape(2, 2, 4)
+    com, pd = mmcs.commit([m])
+    assert pt(com[0][0]) == kG(16) and pt(com[0][1]) == kG(22)
+    opened, wits = mmcs.open_batch(0, pd)
+    assert fr.from_wire(opened[0]) == [1, 2]
+    assert pt(wits[0][0]) == kG(3) and pt(wits[0][1]) == kG(4)
+    assert np.array_equal(mmcs.get_matrices(pd)[0], m)
+    pd.free()
+
+
+def test_mmcs_mixed_heights_vs_oracle(ctx):
+    """matrices of heights 8, 6 (not a power of two), 4, 1 and widths 3, 2, 1, 2, every index."""
+    from plonky3_eon_b200 import GpuKzgMmcs
+    alpha = 999
+    mmcs = GpuKzgMmcs.new(16, alpha, ctx=ctx)
+    srs = okzg.init_srs_unsafe(16, alpha)
+    rng = np.random.default_rng(11)
+    shapes = [(8, 3), (6, 2), (4, 1), (1, 2)]
+    wire = [fr.random_wire(rng, h * w).reshape(h, w, 4) for h, w in shapes]
+    mats = [odft.mat_from_wire(a) for a in wire]
+    com, pd = mmcs.commit(wire)
+    ocom = okzg.mmcs_commit(srs, mats)
+    for a, b in zip(com, ocom):
+        assert g1.from_wire(a) == b
+    for index in range(8):
+        opened, wits = mmcs.open_batch(index, pd)
+        oopened, owits = okzg.mmcs_open_batch(srs, index, mats)
+        for i in range(len(shapes)):
+            assert fr.from_wire(opened[i]) == oopened[i], (index, i)
+            assert g1.from_wire(wits[i]) == owits[i], (index, i)
+    pd.free()
+
+
+def test_mmcs_degree_too_large(ctx):
+    from plonky3_eon_b200 import DegreeTooLarge, GpuKzgMmcs
+    mmcs = GpuKzgMmcs.new(3, 7, ctx=ctx)
+    with pytest.raises(DegreeTooLarge):
+        mmcs.commit([fr.to_wire(list(range(5))).reshape(5, 1, 4)])

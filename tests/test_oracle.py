@@ -220,3 +220,35 @@ def test_split_domains_and_evals():
     assert subs == [(5, 2), (5 * g % P, 2)]
     ev = [[i] for i in range(8)]
     assert kzg.split_evals(2, ev) == [[[0], [2], [4], [6]], [[1], [3], [5], [7]]]
+
+
+# ---- KzgMmcs: kzg/src/tests.rs:50-70 (mmcs_roundtrip) and the doc example of mmcs.rs:36-56 ------
+def test_mmcs_roundtrip_values():
+    """alpha = 5, max_degree 4, matrix [[1,2],[3,4]]: columns are the polynomials 1+3X and 2+4X.
+    commit = (1+3*5) G, (2+4*5) G; open_batch(0): values (1, 2), quotients [3], [4] -> witnesses 3G, 4G.
+    The reference checks these through the pairing (verify_batch); here the same group elements are
+    pinned directly (they are the unique elements that make e(C - vG, H) = e(W, (alpha - z) H) hold)."""
+    from oracle import g1, kzg
+    srs = kzg.init_srs_unsafe(4, 5)
+    m = [[1, 2], [3, 4]]
+    com = kzg.mmcs_commit(srs, [m])
+    assert com[0][0] == g1.mul(g1.G, 16) and com[0][1] == g1.mul(g1.G, 22)
+    opened, wits = kzg.mmcs_open_batch(srs, 0, [m])
+    assert opened == [[1, 2]]
+    assert wits[0] == [g1.mul(g1.G, 3), g1.mul(g1.G, 4)]
+    # KZG opening identity in the exponent: (f(alpha) - f(z)) = q(alpha) * (alpha - z), all rows
+    for idx in range(2):
+        opened, wits = kzg.mmcs_open_batch(srs, idx, [m])
+        for c, f_alpha in enumerate((16, 22)):
+            q_alpha = (f_alpha - opened[0][c]) * pow(5 - idx, -1, kzg.P) % kzg.P
+            assert wits[0][c] == g1.mul(g1.G, q_alpha)
+
+
+def test_mmcs_local_index_mixed_heights():
+    """mmcs.rs:203-214: index is scaled down to shorter matrices; non-power-of-two heights wrap."""
+    from oracle import kzg
+    assert kzg.mmcs_local_index(5, 8, 3) == 5
+    assert kzg.mmcs_local_index(5, 4, 3) == 2
+    assert kzg.mmcs_local_index(5, 2, 3) == 1
+    assert kzg.mmcs_local_index(7, 6, 3) == 1      # log2_ceil(6) = 3 -> 7 % 6
+    assert kzg.mmcs_local_index(3, 1, 3) == 0
