@@ -293,24 +293,41 @@ def run_eon(args):
     modmul_g = ctx.modmul_gmuls(1)
     c_bits = int(ctx.lib.eon_srs_window_bits(ctx.h)) or 16              # window tables in use (0 = plain c = 16)
     W = (255 + c_bits - 1) // c_bits                                    # msm_windows() in csrc/msm.cu
-    adds = rows * cols * W                                              # one mixed add per (point, window, column)
+    adds = rows * cols * W                                              # one bucket addition per (point, window, column)
+    rounds = int(ctx.lib.eon_msm_rounds_used(ctx.h))
     acc_ms = phases["msm_accumulate"] / args.steps
-    achieved = adds * MODMUL_PER_MIXED_ADD * IMAD_PER_MODMUL / (acc_ms * 1e-3) / 1e12
     hbm_peak, peak_src = peaks()
     ntt_ms = phases["ntt_passes"] / args.steps
     ntt_bytes = 3 * 2 * (rows * cols * 32) + 3 * 2 * (2 * rows * cols * 32) - (rows * cols * 32)
-    roofline = {
-        "kernel": "k_msm_accumulate (XYZZ mixed adds, one thread per bucket)",
-        "bound": "imad", "achieved": achieved, "peak": imad_peak, "unit": "TIMAD/s", "frac": achieved / imad_peak,
-        "traffic": None,
-        "algorithmic_ops_per_launch": adds * MODMUL_PER_MIXED_ADD * IMAD_PER_MODMUL,
-        "launch_ms": acc_ms,
+    common = {
+        "bound": "imad", "peak": imad_peak, "unit": "TIMAD/s", "traffic": None,
         "peak_source": "eon_bench_imad_peak in this run (mad.lo/mad.hi.u32, 16 independent chains/thread)",
         "note": "the dominant kernel is integer-pipe bound (SURVEY §8d), so the roofline is IMAD, not HBM/tensor; "
                 "mad.wide peak (counted as 2 ops) and measured Fq modmul rate are given beside it",
         "imad_wide_tops": imad_wide, "fq_modmul_gmul_s": modmul_g,
         "modmul_equiv_tops": modmul_g * 1e9 * IMAD_PER_MODMUL / 1e12,
     }
+    if rounds:
+        # batched-affine pairwise rounds (csrc/msm_tree.cu): k_tree_bwd does 5 Fq products per pair
+        # (2 to peel the shared inverse, lambda, lambda^2, y3); round r has adds / 2^(r+1) pairs
+        pairs = sum(adds // (1 << (r + 1)) for r in range(rounds))
+        bwd_ms = phases["msm_tree_bwd"] / args.steps
+        ops = pairs * 5 * IMAD_PER_MODMUL
+        achieved = ops / (bwd_ms * 1e-3) / 1e12
+        roofline = dict(common, kernel=f"k_tree_bwd x{rounds} (batched-affine pair additions, 5 modmul per pair)",
+                        achieved=achieved, frac=achieved / imad_peak, algorithmic_ops_per_launch=ops,
+                        launch_ms=bwd_ms,
+                        accumulate_phase={"ms": acc_ms, "tree_fwd_ms": phases["msm_tree_fwd"] / args.steps,
+                                          "tree_inv_ms": phases["msm_tree_inv"] / args.steps,
+                                          "tree_bwd_ms": bwd_ms, "finish_ms": phases["msm_finish"] / args.steps,
+                                          "bucket_additions": adds,
+                                          "xyzz_equiv_frac": adds * MODMUL_PER_MIXED_ADD * IMAD_PER_MODMUL
+                                          / (acc_ms * 1e-3) / 1e12 / imad_peak})
+    else:
+        achieved = adds * MODMUL_PER_MIXED_ADD * IMAD_PER_MODMUL / (acc_ms * 1e-3) / 1e12
+        roofline = dict(common, kernel="k_msm_accumulate (XYZZ mixed adds, one thread per bucket)",
+                        achieved=achieved, frac=achieved / imad_peak,
+                        algorithmic_ops_per_launch=adds * MODMUL_PER_MIXED_ADD * IMAD_PER_MODMUL, launch_ms=acc_ms)
     roofline_ntt = {
         "kernel": "k_ntt_pass (3 HBM passes for the 2^20 iDFT + 3 for the 2^21 LDE)",
         "bound": "hbm", "achieved": ntt_bytes / (ntt_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
@@ -338,6 +355,7 @@ def run_eon(args):
         "config": {"workload": f"KZG commit (coset iDFT + {cols} MSM) + blow-up-2 coset LDE, 2^{log_rows} rows x "
                                f"{cols} cols per GPU (BASELINE configs[1]); column-sharded {cols * n_gpus} cols total",
                    "rows": rows, "cols_per_gpu": cols, "srs_points": rows, "msm_window_bits": c_bits, "msm_windows": W,
+                   "msm_affine_rounds": rounds,
                    "l2": "inputs (512 MiB trace, 1 GiB LDE, 1 GiB sort workspace) exceed the 126 MB L2",
                    "parallelism": f"columns x{n_gpus}"},
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,

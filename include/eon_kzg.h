@@ -113,6 +113,12 @@ size_t eon_srs_size(const eon_ctx* ctx);
  * (c chosen by a cost model: 17 for 2^20 points, 20 for 2^24), as long as they fit in 64 GiB.  eon_srs_window_bits returns the c in use (0 = no tables). */
 int eon_srs_set_window_tables(eon_ctx* ctx, unsigned window_bits);
 unsigned eon_srs_window_bits(const eon_ctx* ctx);
+/* MSM bucket accumulation strategy: `rounds` batched-affine pairwise rounds (one shared Fq inversion
+ * per round, ~7.6 instead of 10 Fq products per addition) before the XYZZ finisher; 0 = XYZZ only,
+ * -1 = automatic (3 rounds once buckets average >= 64 entries).  Results are identical either way. */
+int eon_msm_set_rounds(eon_ctx* ctx, int rounds);
+/* rounds the most recent MSM on this context actually used */
+unsigned eon_msm_rounds_used(const eon_ctx* ctx);
 /* copy SRS points [first, first + n) back to the host as affine wire points */
 int eon_srs_read(eon_ctx* ctx, size_t first, size_t n, uint64_t* h_xy);
 
@@ -179,9 +185,11 @@ int eon_bench_imad_peak(eon_ctx* ctx, int kind, double* out_tops);
 /* Montgomery-product throughput (independent chains), in 1e9 modmul/s.  field: 0 Fr, 1 Fq. */
 int eon_bench_modmul(eon_ctx* ctx, int field, double* out_gmuls);
 /* per-phase device time (ms, CUDA events on the ctx stream) summed over every call since the last
- * eon_phase_reset; names via eon_phase_name (phases 0..7) */
+ * eon_phase_reset; names via eon_phase_name (phases 0 .. eon_phase_count() - 1).  The msm_tree_* and
+ * msm_finish phases are sub-intervals of msm_accumulate. */
 int eon_last_phase_ms(eon_ctx* ctx, int phase, float* out_ms);
 int eon_phase_reset(eon_ctx* ctx);
+int eon_phase_count(void);
 const char* eon_phase_name(int phase);
 
 #ifdef __cplusplus

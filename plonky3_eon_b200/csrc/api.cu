@@ -1,5 +1,7 @@
 // extern "C" entry points of libeon_kzg (see include/eon_kzg.h for the contract and the
 // reference file:line each function replaces).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 using namespace eon;
@@ -66,6 +68,13 @@ int eon_ctx_create(int device, void* stream, eon_ctx** out) {
   ctx->device = device;
   ctx->stream = (cudaStream_t)stream;
   ctx->num_sms = prop.multiProcessorCount;
+  if (const char* e = getenv("EON_L2_FETCH")) {  // experiment: L2 fetch granularity for the random base gathers
+    size_t before = 0, after = 0;
+    cudaDeviceGetLimit(&before, cudaLimitMaxL2FetchGranularity);
+    cudaError_t rc = cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(e));
+    cudaDeviceGetLimit(&after, cudaLimitMaxL2FetchGranularity);
+    fprintf(stderr, "eon: L2 fetch granularity %zu -> %zu (%s)\n", before, after, cudaGetErrorString(rc));
+  }
   *out = ctx;
   return EON_OK;
 }
@@ -297,6 +306,15 @@ int eon_srs_set_window_tables(eon_ctx* ctx, unsigned window_bits) {
   return EON_OK;
 }
 unsigned eon_srs_window_bits(const eon_ctx* ctx) { return ctx ? ctx->srs_tab_c : 0; }
+
+unsigned eon_msm_rounds_used(const eon_ctx* ctx) { return ctx ? ctx->msm_rounds_used : 0; }
+
+int eon_msm_set_rounds(eon_ctx* ctx, int rounds) {
+  if (!ctx || rounds < -1 || rounds > 6) return EON_ERR_BAD_ARG;
+  Lock lk(ctx);
+  ctx->msm_rounds = rounds;
+  return EON_OK;
+}
 
 int eon_srs_read(eon_ctx* ctx, size_t first, size_t n, uint64_t* h_xy) {
   if (!ctx) return EON_ERR_BAD_ARG;
@@ -693,9 +711,11 @@ int eon_phase_reset(eon_ctx* ctx) {
   return EON_OK;
 }
 
+int eon_phase_count(void) { return PH_COUNT; }
 const char* eon_phase_name(int phase) {
   static const char* names[PH_COUNT] = {"ntt_twiddle", "ntt_passes", "msm_digits", "msm_scan",
-                                         "msm_scatter", "msm_accumulate", "msm_reduce", "quotient"};
+                                         "msm_scatter", "msm_accumulate", "msm_reduce", "quotient",
+                                         "msm_tree_fwd", "msm_tree_inv", "msm_tree_bwd", "msm_finish"};
   return (phase >= 0 && phase < PH_COUNT) ? names[phase] : "?";
 }
 

@@ -24,6 +24,10 @@ enum Phase {
   PH_MSM_ACCUM,
   PH_MSM_REDUCE,
   PH_QUOTIENT,
+  PH_MSM_TREE_FWD,   // the three below are sub-intervals of PH_MSM_ACCUM (msm_tree.cu)
+  PH_MSM_TREE_INV,
+  PH_MSM_TREE_BWD,
+  PH_MSM_FINISH,
   PH_COUNT
 };
 
@@ -67,6 +71,10 @@ enum ScratchId {
   SC_MSM_RESULT,
   SC_MSM_MISC,
   SC_MSM_ORDER,
+  SC_MSM_TREE_A,
+  SC_MSM_TREE_B,
+  SC_MSM_TREE_T,
+  SC_MSM_TREE_P,
   SC_IO_A,
   SC_IO_B,
   SC_QUOT,
@@ -93,6 +101,9 @@ struct eon_ctx {
   // window tables tab[t][i] = 2^(c t) * srs[i] (t < ceil(256/c)), built once per SRS; null = none
   eon::G1Affine* d_srs_tab = nullptr;
   unsigned srs_tab_c = 0;
+  // batched-affine pairwise rounds before the XYZZ finisher: -1 = automatic (msm_pick_rounds)
+  int msm_rounds = -1;
+  unsigned msm_rounds_used = 0;  // rounds of the most recent MSM (reporting)
 
   std::map<eon_handle, eon::ProverMatrix> handles;
   eon_handle next_handle = 1;

@@ -16,26 +16,11 @@
 //   6 combine    per column Horner over windows (c doublings + 1 add each), to affine
 // The result is the canonical affine point, hence bit-identical to the reference whatever the
 // order of additions.
-#include "common.cuh"
+#include <stdlib.h>
+
+#include "msm.cuh"
 
 namespace eon {
-
-constexpr int MSM_THREADS = 256;
-constexpr u32 SIGN_BIT = 0x80000000u;
-
-struct MsmShape {
-  u32 c;        // window bits (2..20)
-  u32 W;        // windows = ceil(256 / c)
-  u32 NB;       // buckets per bucket set = 2^(c-1)
-  u32 nsets;    // bucket sets per column: W (plain) or 1 (merged: windows share one set because
-                // window t reads the precomputed table 2^(c t) * P_i instead of P_i)
-  u32 merged;
-  u32 chunk;    // buckets per reduction chunk
-  u32 nchunks;  // NB / chunk
-  u64 tab_stride;  // merged: points per table level
-  u64 base_first;  // merged: index of this MSM's point 0 inside a table level
-  u64 seg_cap;     // entry slots per segment: n (plain) or n * W (merged)
-};
 
 // Windows needed for a canonical scalar (< r < 2^254) in signed c-bit digits: the top window must
 // absorb the last carry without wrapping, i.e. hold at most c - 1 scalar bits: W*c >= 255.
@@ -141,8 +126,10 @@ k_msm_hist(const Fr* __restrict__ scalars, size_t n, size_t ld, u32 ncols, MsmSh
 }
 
 // ---- 2. exclusive scan per segment ----------------------------------------------------------
-// one block per segment; hist -> starts (in place), cursor = copy of starts
-__global__ void __launch_bounds__(1024) k_msm_scan(u32* __restrict__ hist, u32* __restrict__ cursor, u32 NB) {
+// one block per segment; hist -> starts (in place), cursor = copy of starts.  Every bucket's slot
+// range is rounded up to a multiple of `align` (a power of two; 2^rounds for the batched-affine
+// pairwise rounds of msm_tree.cu, else 1), so starts are multiples of `align`.
+__global__ void __launch_bounds__(1024) k_msm_scan(u32* __restrict__ hist, u32* __restrict__ cursor, u32 NB, u32 align) {
   __shared__ u32 warp_sums[32];
   __shared__ u32 s_carry;
   u32* h = hist + (size_t)blockIdx.x * NB;
@@ -152,7 +139,7 @@ __global__ void __launch_bounds__(1024) k_msm_scan(u32* __restrict__ hist, u32* 
   __syncthreads();
   for (u32 base = 0; base < NB; base += 1024) {
     u32 idx = base + tid;
-    u32 v = idx < NB ? h[idx] : 0;
+    u32 v = idx < NB ? ((h[idx] + align - 1) & ~(align - 1)) : 0;
     u32 x = v;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -212,7 +199,7 @@ k_msm_scatter(const Fr* __restrict__ scalars, size_t n, size_t ld, u32 ncols, Ms
 // gives every warp buckets of (nearly) one size.  One block per segment.
 constexpr u32 ORDER_BINS = 256;
 __global__ void __launch_bounds__(1024)
-k_msm_order(const u32* __restrict__ starts, const u32* __restrict__ ends, u32 NB, u32* __restrict__ order) {
+k_msm_order(const u32* __restrict__ starts, const u32* __restrict__ ends, u32 NB, u32 rshift, u32* __restrict__ order) {
   __shared__ u32 bin_count[ORDER_BINS];
   __shared__ u32 bin_pos[ORDER_BINS];
   const size_t seg = blockIdx.x;
@@ -221,8 +208,9 @@ k_msm_order(const u32* __restrict__ starts, const u32* __restrict__ ends, u32 NB
   u32* ord = order + seg * NB;
   for (u32 i = threadIdx.x; i < ORDER_BINS; i += blockDim.x) bin_count[i] = 0;
   __syncthreads();
+  const u32 rnd = (1u << rshift) - 1;  // after `rshift` pairwise rounds a bucket holds ceil(cnt / 2^rshift) points
   for (u32 b = threadIdx.x; b < NB; b += blockDim.x) {
-    u32 cnt = en[b] - st[b];
+    u32 cnt = (en[b] - st[b] + rnd) >> rshift;
     atomicAdd(&bin_count[min(cnt, ORDER_BINS - 1)], 1u);
   }
   __syncthreads();
@@ -235,7 +223,7 @@ k_msm_order(const u32* __restrict__ starts, const u32* __restrict__ ends, u32 NB
   }
   __syncthreads();
   for (u32 b = threadIdx.x; b < NB; b += blockDim.x) {
-    u32 cnt = en[b] - st[b];
+    u32 cnt = (en[b] - st[b] + rnd) >> rshift;
     u32 pos = atomicAdd(&bin_pos[min(cnt, ORDER_BINS - 1)], 1u);
     ord[pos] = b;
   }
@@ -248,31 +236,59 @@ struct MsmTask {
   u32 begin, end;  // entry range inside the segment
 };
 
-__device__ __forceinline__ G1Affine load_base(const G1Affine* __restrict__ bases, u32 idx) {
-  const uint4* p = reinterpret_cast<const uint4*>(bases + idx);
-  uint4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2), d = __ldg(p + 3);
+__device__ __forceinline__ G1Affine load_base(const G1Affine* __restrict__ bases, u64 idx) {
+  // two 256-bit loads (LDG.E.ENL2.256): one request per coordinate of the random 64-byte gather
+  const Fq* p = reinterpret_cast<const Fq*>(bases + idx);
   G1Affine r;
-  r.x.v[0] = a.x; r.x.v[1] = a.y; r.x.v[2] = a.z; r.x.v[3] = a.w;
-  r.x.v[4] = b.x; r.x.v[5] = b.y; r.x.v[6] = b.z; r.x.v[7] = b.w;
-  r.y.v[0] = c.x; r.y.v[1] = c.y; r.y.v[2] = c.z; r.y.v[3] = c.w;
-  r.y.v[4] = d.x; r.y.v[5] = d.y; r.y.v[6] = d.z; r.y.v[7] = d.w;
+  asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r.x.v[0]), "=r"(r.x.v[1]), "=r"(r.x.v[2]), "=r"(r.x.v[3]), "=r"(r.x.v[4]), "=r"(r.x.v[5]),
+                 "=r"(r.x.v[6]), "=r"(r.x.v[7])
+               : "l"(p));
+  asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r.y.v[0]), "=r"(r.y.v[1]), "=r"(r.y.v[2]), "=r"(r.y.v[3]), "=r"(r.y.v[4]), "=r"(r.y.v[5]),
+                 "=r"(r.y.v[6]), "=r"(r.y.v[7])
+               : "l"(p + 1));
   return r;
 }
 
-__device__ __forceinline__ G1Xyzz accumulate_range(const G1Affine* __restrict__ bases, const u32* __restrict__ ent,
-                                                   u32 begin, u32 end) {
+// Where the finisher reads its addends: the sorted entries (index | sign into `bases`), or — after
+// the batched-affine pairwise rounds of msm_tree.cu — the flat array of partial sums `pts`, in which
+// bucket [begin, end) of a segment occupies slots [(seg*seg_cap + begin) >> rshift,
+// ceil((seg*seg_cap + end) / 2^rshift)).
+struct AccSrc {
+  const G1Affine* bases;
+  const u32* entries;
+  u64 seg_cap;
+  const G1Affine* pts;
+  u32 rshift;
+};
+
+template <bool PTS>
+__device__ __forceinline__ G1Xyzz accumulate_range(const AccSrc& s, u32 seg, u32 begin, u32 end) {
   G1Xyzz acc = G1Xyzz::identity();
   if (begin >= end) return acc;
+  if (PTS) {
+    const u64 base = (u64)seg * s.seg_cap;
+    const u64 b = (base + begin) >> s.rshift, e = (base + end + ((1ull << s.rshift) - 1)) >> s.rshift;
+    G1Affine p_next = load_base(s.pts, b);
+    for (u64 i = b; i < e; i++) {
+      G1Affine p = p_next;
+      if (i + 1 < e) p_next = load_base(s.pts, i + 1);
+      g1_add_mixed(acc, p);
+    }
+    return acc;
+  }
   // software pipeline: the next base (a random 64-byte gather, HBM-resident with window tables) is
   // in flight while the current mixed addition (~11 k cycles per warp) runs
+  const u32* ent = s.entries + (u64)seg * s.seg_cap;
   u32 v_next = __ldg(ent + begin);
-  G1Affine p_next = load_base(bases, v_next & ~SIGN_BIT);
+  G1Affine p_next = load_base(s.bases, v_next & ~SIGN_BIT);
   for (u32 e = begin; e < end; e++) {
     u32 v = v_next;
     G1Affine p = p_next;
     if (e + 1 < end) {
       v_next = __ldg(ent + e + 1);
-      p_next = load_base(bases, v_next & ~SIGN_BIT);
+      p_next = load_base(s.bases, v_next & ~SIGN_BIT);
     }
     if (v & SIGN_BIT) p.y = fp_neg(p.y);
     g1_add_mixed(acc, p);
@@ -282,12 +298,13 @@ __device__ __forceinline__ G1Xyzz accumulate_range(const G1Affine* __restrict__ 
 
 __device__ __forceinline__ void store_xyzz(G1Xyzz* dst, const G1Xyzz& p) { *dst = p; }
 
-// one thread per bucket; starts[] = bucket begin, cursor[] = bucket end (after the scatter)
+// one thread per bucket; starts[] = bucket begin, cursor[] = bucket end (after the scatter).
+// chunk_min is in entry slots (a PTS chunk of chunk_min slots holds chunk_min >> rshift points).
+template <bool PTS>
 __global__ void __launch_bounds__(MSM_THREADS)
-k_msm_accumulate(const G1Affine* __restrict__ bases, const u32* __restrict__ entries, size_t seg_cap,
-                 const u32* __restrict__ starts, const u32* __restrict__ ends, const u32* __restrict__ order, u32 NB,
-                 size_t total_buckets, u32 chunk_min, G1Xyzz* __restrict__ buckets, MsmTask* __restrict__ tasks,
-                 u32* __restrict__ ntasks, u32 max_tasks) {
+k_msm_accumulate(AccSrc src, const u32* __restrict__ starts, const u32* __restrict__ ends,
+                 const u32* __restrict__ order, u32 NB, size_t total_buckets, u32 chunk_min,
+                 G1Xyzz* __restrict__ buckets, MsmTask* __restrict__ tasks, u32* __restrict__ ntasks, u32 max_tasks) {
   size_t slot = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   if (slot >= total_buckets) return;
   u32 seg = (u32)(slot / NB);
@@ -296,9 +313,10 @@ k_msm_accumulate(const G1Affine* __restrict__ bases, const u32* __restrict__ ent
   u32 cnt = end - begin;
   u32 my_end = end;
   if (cnt > chunk_min) {
-    // split: at most 512 chunks per bucket, each at least chunk_min entries
+    // split: at most 512 chunks per bucket, each at least chunk_min entries (a multiple of 2^rshift)
     u32 ch = (cnt + 511) / 512;
     if (ch < chunk_min) ch = chunk_min;
+    ch = (ch + ((1u << src.rshift) - 1)) & ~((1u << src.rshift) - 1);
     u32 extra = (cnt + ch - 1) / ch - 1;
     u32 slot = atomicAdd(ntasks, extra);
     if (slot + extra <= max_tasks) {
@@ -314,20 +332,19 @@ k_msm_accumulate(const G1Affine* __restrict__ bases, const u32* __restrict__ ent
     }
     // else: task buffer exhausted (cannot happen with the sizing in msm_run); fall back to serial
   }
-  const u32* ent = entries + (size_t)seg * seg_cap;
-  G1Xyzz acc = accumulate_range(bases, ent, begin, my_end);
+  G1Xyzz acc = accumulate_range<PTS>(src, seg, begin, my_end);
   store_xyzz(buckets + g, acc);
 }
 
 // extra chunks of oversized buckets -> partial sums
+template <bool PTS>
 __global__ void __launch_bounds__(MSM_THREADS)
-k_msm_accumulate_tasks(const G1Affine* __restrict__ bases, const u32* __restrict__ entries, size_t seg_cap,
-                       const MsmTask* __restrict__ tasks, const u32* __restrict__ ntasks, u32 max_tasks,
+k_msm_accumulate_tasks(AccSrc src, const MsmTask* __restrict__ tasks, const u32* __restrict__ ntasks, u32 max_tasks,
                        G1Xyzz* __restrict__ partial) {
   u32 nt = min(*ntasks, max_tasks);
   for (u32 t = blockIdx.x * blockDim.x + threadIdx.x; t < nt; t += gridDim.x * blockDim.x) {
     MsmTask tk = tasks[t];
-    G1Xyzz acc = accumulate_range(bases, entries + (size_t)tk.seg * seg_cap, tk.begin, tk.end);
+    G1Xyzz acc = accumulate_range<PTS>(src, tk.seg, tk.begin, tk.end);
     partial[t] = acc;
   }
 }
@@ -424,14 +441,41 @@ int g1_sum_run(eon_ctx* ctx, const G1Affine* d_points, size_t n, G1Affine* d_out
 }
 
 // ---- orchestration -----------------------------------------------------------------------------
+// Batched-affine pairwise rounds (msm_tree.cu) before the serial finisher: worth it once buckets hold
+// many entries (each round halves them at ~7.6 instead of 10 products per addition).
+// eon_msm_set_rounds / EON_MSM_ROUNDS override (0 = classic XYZZ accumulation only).
+static u32 msm_pick_rounds(const eon_ctx* ctx, size_t n, const MsmShape& sh) {
+  static int env_forced = -2;
+  if (env_forced == -2) {
+    const char* e = getenv("EON_MSM_ROUNDS");
+    env_forced = e ? atoi(e) : -1;
+  }
+  int forced = ctx->msm_rounds >= 0 ? ctx->msm_rounds : env_forced;
+  if (forced > 6) forced = 6;
+  if (forced >= 0) return (u32)forced;
+  const double per_bucket = (double)(sh.merged ? n * sh.W : n) / sh.NB;
+  if (per_bucket >= 64) return 3;
+  if (per_bucket >= 32) return 2;
+  return 0;
+}
+
+static void msm_set_rounds(MsmShape& sh, size_t n, u32 rounds) {
+  sh.rounds = rounds;
+  const u64 raw = sh.merged ? (u64)n * sh.W : (u64)n;
+  const u64 al = 1ull << rounds;
+  // every bucket may waste up to 2^rounds - 1 padding slots
+  sh.seg_cap = rounds ? ((raw + (u64)sh.NB * (al - 1) + al - 1) & ~(al - 1)) : raw;
+}
+
 static int msm_batch(eon_ctx* ctx, const G1Affine* d_bases, const Fr* d_scalars, size_t n, size_t ncols, size_t ld,
                      const MsmShape& sh, G1Affine* d_out) {
   const size_t nseg = ncols * sh.nsets;
   const size_t total_buckets = nseg * sh.NB;
-  const u32 chunk_min = 256;
+  const u32 chunk_min = 256u << sh.rounds;  // entry slots per split-off task: 256 addends in the finisher
   size_t max_tasks_sz = (nseg * sh.seg_cap) / chunk_min + 1024;
   if (max_tasks_sz > 0x7fffffffull) max_tasks_sz = 0x7fffffffull;
   const u32 max_tasks = (u32)max_tasks_sz;
+  if (sh.seg_cap >= 0xffffffffull) return fail(ctx, EON_ERR_BAD_ARG, "msm: segment too large");
 
   void *p_hist, *p_cur, *p_ent, *p_bkt, *p_tasks, *p_tpart, *p_part, *p_seg, *p_misc, *p_ord;
   EON_TRY(scratch_get(ctx, SC_MSM_ORDER, total_buckets * sizeof(u32), &p_ord));
@@ -458,33 +502,51 @@ static int msm_batch(eon_ctx* ctx, const G1Affine* d_bases, const Fr* d_scalars,
   phase_end(ctx, PH_MSM_DIGITS);
 
   phase_begin(ctx, PH_MSM_SCAN);
-  k_msm_scan<<<(unsigned)nseg, 1024, 0, st>>>((u32*)p_hist, (u32*)p_cur, sh.NB);
+  k_msm_scan<<<(unsigned)nseg, 1024, 0, st>>>((u32*)p_hist, (u32*)p_cur, sh.NB, 1u << sh.rounds);
   EON_LAUNCHED(ctx);
   phase_end(ctx, PH_MSM_SCAN);
 
   phase_begin(ctx, PH_MSM_SCATTER);
+  if (sh.rounds)  // unused slots (bucket padding, segment tails) must read as ENTRY_NONE
+    EON_CUDA(ctx, cudaMemsetAsync(p_ent, 0xff, nseg * sh.seg_cap * sizeof(u32), st));
   k_msm_scatter<<<grid_pts, MSM_THREADS, 0, st>>>(d_scalars, n, ld, (u32)ncols, sh, (u32*)p_cur, (u32*)p_ent);
   EON_LAUNCHED(ctx);
   phase_end(ctx, PH_MSM_SCATTER);
 
   phase_begin(ctx, PH_MSM_ACCUM);
   {
-    k_msm_order<<<(unsigned)nseg, 1024, 0, st>>>((const u32*)p_hist, (const u32*)p_cur, sh.NB, (u32*)p_ord);
+    AccSrc src;
+    src.bases = d_bases;
+    src.entries = (const u32*)p_ent;
+    src.seg_cap = sh.seg_cap;
+    src.pts = nullptr;
+    src.rshift = sh.rounds;
+    if (sh.rounds) EON_TRY(msm_tree_rounds(ctx, d_bases, (const u32*)p_ent, (u64)nseg * sh.seg_cap, sh.rounds, &src.pts));
+    phase_begin(ctx, PH_MSM_FINISH);
+    k_msm_order<<<(unsigned)nseg, 1024, 0, st>>>((const u32*)p_hist, (const u32*)p_cur, sh.NB, sh.rounds, (u32*)p_ord);
     EON_LAUNCHED(ctx);
     unsigned blocks = (unsigned)((total_buckets + MSM_THREADS - 1) / MSM_THREADS);
-    k_msm_accumulate<<<blocks, MSM_THREADS, 0, st>>>(d_bases, (const u32*)p_ent, sh.seg_cap, (const u32*)p_hist,
-                                                     (const u32*)p_cur, (const u32*)p_ord, sh.NB, total_buckets,
-                                                     chunk_min, (G1Xyzz*)p_bkt, (MsmTask*)p_tasks, d_ntasks,
-                                                     max_tasks);
-    EON_LAUNCHED(ctx);
     unsigned tb = (unsigned)ctx->num_sms * 8;
-    k_msm_accumulate_tasks<<<tb, MSM_THREADS, 0, st>>>(d_bases, (const u32*)p_ent, sh.seg_cap,
-                                                       (const MsmTask*)p_tasks, d_ntasks, max_tasks,
-                                                       (G1Xyzz*)p_tpart);
+    if (sh.rounds) {
+      k_msm_accumulate<true><<<blocks, MSM_THREADS, 0, st>>>(src, (const u32*)p_hist, (const u32*)p_cur,
+                                                             (const u32*)p_ord, sh.NB, total_buckets, chunk_min,
+                                                             (G1Xyzz*)p_bkt, (MsmTask*)p_tasks, d_ntasks, max_tasks);
+      EON_LAUNCHED(ctx);
+      k_msm_accumulate_tasks<true><<<tb, MSM_THREADS, 0, st>>>(src, (const MsmTask*)p_tasks, d_ntasks, max_tasks,
+                                                               (G1Xyzz*)p_tpart);
+    } else {
+      k_msm_accumulate<false><<<blocks, MSM_THREADS, 0, st>>>(src, (const u32*)p_hist, (const u32*)p_cur,
+                                                              (const u32*)p_ord, sh.NB, total_buckets, chunk_min,
+                                                              (G1Xyzz*)p_bkt, (MsmTask*)p_tasks, d_ntasks, max_tasks);
+      EON_LAUNCHED(ctx);
+      k_msm_accumulate_tasks<false><<<tb, MSM_THREADS, 0, st>>>(src, (const MsmTask*)p_tasks, d_ntasks, max_tasks,
+                                                                (G1Xyzz*)p_tpart);
+    }
     EON_LAUNCHED(ctx);
     k_msm_fold_tasks<<<tb, MSM_THREADS, 0, st>>>((const MsmTask*)p_tasks, d_ntasks, max_tasks,
                                                  (const G1Xyzz*)p_tpart, (G1Xyzz*)p_bkt);
     EON_LAUNCHED(ctx);
+    phase_end(ctx, PH_MSM_FINISH);
   }
   phase_end(ctx, PH_MSM_ACCUM);
 
@@ -522,9 +584,13 @@ int msm_run(eon_ctx* ctx, const G1Affine* d_bases, const Fr* d_scalars, size_t n
       bases = ctx->d_srs_tab;
     }
   }
-  // column batches: bound the sort workspace
-  size_t per_col = sh.seg_cap * sh.nsets * 4 + (size_t)sh.nsets * sh.NB * (sizeof(G1Xyzz) + 16);
-  size_t budget = (size_t)12 << 30;
+  msm_set_rounds(sh, n, msm_pick_rounds(ctx, n, sh));
+  ctx->msm_rounds_used = sh.rounds;
+  // column batches: bound the sort + pairwise-round workspace (entries 4 B, round outputs 32 + 16 B,
+  // level products ~5 B, prefix products 16 B per entry slot)
+  size_t per_slot = 4 + (sh.rounds ? 32 + 16 + 5 + 16 : 0);
+  size_t per_col = sh.seg_cap * sh.nsets * per_slot + (size_t)sh.nsets * sh.NB * (sizeof(G1Xyzz) + 16);
+  size_t budget = (size_t)24 << 30;
   size_t batch = budget / per_col;
   if (batch < 1) batch = 1;
   if (batch > 64) batch = 64;

@@ -48,6 +48,8 @@ _SIGS = {
     "eon_srs_read": (C.c_int, [C.c_void_p, C.c_size_t, C.c_size_t, _u64p]),
     "eon_srs_set_window_tables": (C.c_int, [C.c_void_p, C.c_uint]),
     "eon_srs_window_bits": (C.c_uint, [C.c_void_p]),
+    "eon_msm_set_rounds": (C.c_int, [C.c_void_p, C.c_int]),
+    "eon_msm_rounds_used": (C.c_uint, [C.c_void_p]),
     "eon_msm_srs_dev": (C.c_int, [C.c_void_p, _u64p, C.c_size_t, C.c_size_t, C.c_size_t, _u64p]),
     "eon_msm_srs": (C.c_int, [C.c_void_p, _u64p, C.c_size_t, C.c_size_t, C.c_size_t, _u64p]),
     "eon_msm_points": (C.c_int, [C.c_void_p, _u64p, _u64p, C.c_size_t, _u64p]),
@@ -69,6 +71,7 @@ _SIGS = {
     "eon_last_phase_ms": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_float)]),
     "eon_phase_reset": (C.c_int, [C.c_void_p]),
     "eon_phase_name": (C.c_char_p, [C.c_int]),
+    "eon_phase_count": (C.c_int, []),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGS)
@@ -188,7 +191,7 @@ class Context:
     def phase_ms(self):
         out = {}
         v = C.c_float()
-        for ph in range(8):
+        for ph in range(int(self.lib.eon_phase_count())):
             self.call("eon_last_phase_ms", ph, C.byref(v))
             out[self.lib.eon_phase_name(ph).decode()] = float(v.value)
         return out

@@ -1,0 +1,84 @@
+"""GPU parity of the batched-affine pairwise rounds (csrc/msm_tree.cu): every MSM parity case of
+tests/test_gpu_kzg.py again with the round count forced to 1, 2, 3 and 5 (the automatic policy only
+switches them on for large inputs), so that the degenerate pairs — identity operands, P + P, P + (-P),
+empty and oversized buckets, segment tails — go through k_tree_fwd / k_tree_bwd.  Results must be the
+same affine points as with the XYZZ-only accumulation (rounds = 0) and as the oracle's."""
+import numpy as np
+import pytest
+
+import test_gpu_kzg as T
+from oracle import fr, g1, kzg as okzg
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from plonky3_eon_b200 import Context
+    c = Context(0)
+    yield c
+    c.close()
+
+
+@pytest.fixture(params=[1, 2, 3, 5])
+def rctx(ctx, request):
+    ctx.call("eon_msm_set_rounds", request.param)
+    yield ctx
+    ctx.call("eon_msm_set_rounds", -1)
+
+
+def test_kats_and_edge_cases(rctx):
+    T.test_multi_exp_kats(rctx)
+    T.test_multi_exp_edge_cases(rctx)
+
+
+@pytest.mark.parametrize("n", [1, 3, 64, 257])
+def test_random_small(rctx, n):
+    T.test_multi_exp_random_small(rctx, n)
+
+
+@pytest.mark.parametrize("kind", ["zeros", "ones", "equal", "one_bit", "small64", "fib", "few_buckets"])
+def test_skewed(rctx, kind):
+    T.test_msm_skewed_scalars(rctx, kind)
+
+
+@pytest.mark.parametrize("log_n,ncols", [(10, 3), (16, 2)])
+def test_dlog_shortcut(rctx, log_n, ncols):
+    T.test_msm_srs_dlog_shortcut(rctx, log_n, ncols)
+
+
+@pytest.mark.parametrize("log_n,bits", [(15, 0), (15, 13), (16, 17)])
+def test_tables_and_ranges(rctx, log_n, bits):
+    T.test_window_tables_and_index_ranges(rctx, log_n, bits)
+
+
+def test_duplicate_bases_double_inside_rounds(rctx):
+    """all bases equal: every pair of every round is a doubling (P + P), plus sign-flipped entries
+    that cancel (P + (-P)) when digits are negative."""
+    from plonky3_eon_b200 import GpuKzgPcs
+    pcs = GpuKzgPcs(rctx)
+    n = 300
+    A = g1.mul(g1.G, 424242)
+    rng = np.random.default_rng(3)
+    sc = [int(v) for v in rng.integers(1, 1 << 62, size=n)]
+    sc[::7] = [fr.P - 5] * len(sc[::7])            # negative top digits
+    want = g1.mul(A, sum(sc) % fr.P)
+    got = T.pt(pcs.multi_exp(g1.to_wire([A] * n), fr.to_wire(sc)))
+    assert got == want
+
+
+def test_commit_matches_rounds_off(ctx):
+    """the same commit with rounds forced to 3 and to 0 gives byte-identical commitments"""
+    h, w, alpha = 1 << 12, 4, 12345
+    pcs = T.pcs_new(ctx, h - 1, alpha)
+    from plonky3_eon_b200 import TwoAdicMultiplicativeCoset
+    ev = fr.random_wire(np.random.default_rng(8), h * w).reshape(h, w, 4)
+    dom = TwoAdicMultiplicativeCoset(1, 12)
+    outs = []
+    for r in (0, 3):
+        ctx.call("eon_msm_set_rounds", r)
+        c, pd = pcs.commit([(dom, ev)])
+        outs.append(c[0].copy())
+        pd[0].free()
+    ctx.call("eon_msm_set_rounds", -1)
+    assert np.array_equal(outs[0], outs[1])
