@@ -117,6 +117,9 @@ unsigned eon_srs_window_bits(const eon_ctx* ctx);
  * per round, ~7.6 instead of 10 Fq products per addition) before the XYZZ finisher; 0 = XYZZ only,
  * -1 = automatic (3 rounds once buckets average >= 64 entries).  Results are identical either way. */
 int eon_msm_set_rounds(eon_ctx* ctx, int rounds);
+/* how entries are sorted by bucket: 0 = one pass of global atomics, 1 = coarse + fine coalesced
+ * passes (csrc/msm_sort.cu), -1 = automatic.  Results are identical either way. */
+int eon_msm_set_sort_mode(eon_ctx* ctx, int mode);
 /* rounds the most recent MSM on this context actually used */
 unsigned eon_msm_rounds_used(const eon_ctx* ctx);
 /* copy SRS points [first, first + n) back to the host as affine wire points */

@@ -307,6 +307,13 @@ int eon_srs_set_window_tables(eon_ctx* ctx, unsigned window_bits) {
 }
 unsigned eon_srs_window_bits(const eon_ctx* ctx) { return ctx ? ctx->srs_tab_c : 0; }
 
+int eon_msm_set_sort_mode(eon_ctx* ctx, int mode) {
+  if (!ctx || mode < -1 || mode > 1) return EON_ERR_BAD_ARG;
+  Lock lk(ctx);
+  ctx->msm_sort_mode = mode;
+  return EON_OK;
+}
+
 unsigned eon_msm_rounds_used(const eon_ctx* ctx) { return ctx ? ctx->msm_rounds_used : 0; }
 
 int eon_msm_set_rounds(eon_ctx* ctx, int rounds) {

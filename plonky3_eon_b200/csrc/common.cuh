@@ -75,6 +75,10 @@ enum ScratchId {
   SC_MSM_TREE_B,
   SC_MSM_TREE_T,
   SC_MSM_TREE_P,
+  SC_MSM_SORT_REGION,
+  SC_MSM_SORT_PAY,
+  SC_MSM_SORT_KEY,
+  SC_MSM_SEGTOTAL,
   SC_IO_A,
   SC_IO_B,
   SC_QUOT,
@@ -103,6 +107,7 @@ struct eon_ctx {
   unsigned srs_tab_c = 0;
   // batched-affine pairwise rounds before the XYZZ finisher: -1 = automatic (msm_pick_rounds)
   int msm_rounds = -1;
+  int msm_sort_mode = -1;        // -1 automatic, 0 one-pass atomic scatter, 1 two-pass coalesced sort
   unsigned msm_rounds_used = 0;  // rounds of the most recent MSM (reporting)
 
   std::map<eon_handle, eon::ProverMatrix> handles;

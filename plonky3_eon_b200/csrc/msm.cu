@@ -65,50 +65,6 @@ static MsmShape msm_shape_merged(size_t n, u32 c, u64 tab_stride, u64 first) {
   return s;
 }
 
-// ---- 1. scalar -> signed window digits --------------------------------------------------------
-// s * 1 * R^-1 gives the canonical integer (the reference hands halo2curves Montgomery scalars,
-// bn254/src/curve.rs:173-174).  Digits d_w in [-2^(c-1), 2^(c-1)) with sum d_w 2^(c w) = scalar;
-// The top window never wraps: W*c >= 255 leaves it at most c - 1 scalar bits, so raw + carry <=
-// 2^(c-1), which still has a bucket (index 2^(c-1) - 1).  f(w, d) for d != 0.
-template <class F>
-__device__ __forceinline__ void for_each_digit(const Fr& s, const MsmShape& sh, F f) {
-  u32 k[9];
-  fp_from_mont(k, s);
-  k[8] = 0;
-  const u32 c = sh.c;
-  const u32 mask = (1u << c) - 1;
-  const u32 half = 1u << (c - 1);
-  u32 carry = 0;
-  for (u32 w = 0; w < sh.W; w++) {
-    u32 bit = w * c;
-    u32 limb = bit >> 5, off = bit & 31;
-    u32 raw = 0;
-    if (limb < 8) {
-      u64 two = (u64)k[limb] | ((u64)k[limb + 1] << 32);
-      raw = (u32)(two >> off) & mask;
-    }
-    raw += carry;
-    int d;
-    if (raw >= half && w + 1 < sh.W) {
-      d = (int)raw - (int)(1u << c);
-      carry = 1;
-    } else {
-      d = (int)raw;
-      carry = 0;
-    }
-    if (d != 0) f(w, d);
-  }
-}
-
-__device__ __forceinline__ Fr load_scalar(const Fr* __restrict__ scalars, size_t i, size_t ld, u32 col) {
-  const uint4* sp = reinterpret_cast<const uint4*>(scalars + i * ld + col);
-  uint4 lo = __ldg(sp), hi = __ldg(sp + 1);
-  Fr s;
-  s.v[0] = lo.x; s.v[1] = lo.y; s.v[2] = lo.z; s.v[3] = lo.w;
-  s.v[4] = hi.x; s.v[5] = hi.y; s.v[6] = hi.z; s.v[7] = hi.w;
-  return s;
-}
-
 // bucket histogram.  1-D grid of ncols * ceil(n / threads) blocks, column index fastest: blocks
 // that run at the same time then update the bucket sets of ALL columns, which spreads the L2
 // atomics over ncols x more cache lines (they serialise per line: measured 3.5x on the hist pass).
@@ -129,7 +85,8 @@ k_msm_hist(const Fr* __restrict__ scalars, size_t n, size_t ld, u32 ncols, MsmSh
 // one block per segment; hist -> starts (in place), cursor = copy of starts.  Every bucket's slot
 // range is rounded up to a multiple of `align` (a power of two; 2^rounds for the batched-affine
 // pairwise rounds of msm_tree.cu, else 1), so starts are multiples of `align`.
-__global__ void __launch_bounds__(1024) k_msm_scan(u32* __restrict__ hist, u32* __restrict__ cursor, u32 NB, u32 align) {
+__global__ void __launch_bounds__(1024)
+k_msm_scan(u32* __restrict__ hist, u32* __restrict__ cursor, u32 NB, u32 align, u32* __restrict__ seg_total) {
   __shared__ u32 warp_sums[32];
   __shared__ u32 s_carry;
   u32* h = hist + (size_t)blockIdx.x * NB;
@@ -169,6 +126,7 @@ __global__ void __launch_bounds__(1024) k_msm_scan(u32* __restrict__ hist, u32* 
     if (tid == 1023) s_carry = excl + v;
     __syncthreads();
   }
+  if (tid == 0) seg_total[blockIdx.x] = s_carry;  // aligned slots in use by the segment
 }
 
 // ---- 3. scatter (counting sort by bucket) ----------------------------------------------------
@@ -488,6 +446,8 @@ static int msm_batch(eon_ctx* ctx, const G1Affine* d_bases, const Fr* d_scalars,
   EON_TRY(scratch_get(ctx, SC_MSM_PARTIALS, nseg * sh.nchunks * sizeof(G1Xyzz), &p_part));
   EON_TRY(scratch_get(ctx, SC_MSM_SEGSUM, nseg * sizeof(G1Xyzz), &p_seg));
   EON_TRY(scratch_get(ctx, SC_MSM_MISC, 256, &p_misc));
+  void* p_segtot;
+  EON_TRY(scratch_get(ctx, SC_MSM_SEGTOTAL, nseg * sizeof(u32), &p_segtot));
   u32* d_ntasks = (u32*)p_misc;
   cudaStream_t st = ctx->stream;
   const size_t grid_pts_sz = ((n + MSM_THREADS - 1) / MSM_THREADS) * ncols;
@@ -502,15 +462,30 @@ static int msm_batch(eon_ctx* ctx, const G1Affine* d_bases, const Fr* d_scalars,
   phase_end(ctx, PH_MSM_DIGITS);
 
   phase_begin(ctx, PH_MSM_SCAN);
-  k_msm_scan<<<(unsigned)nseg, 1024, 0, st>>>((u32*)p_hist, (u32*)p_cur, sh.NB, 1u << sh.rounds);
+  k_msm_scan<<<(unsigned)nseg, 1024, 0, st>>>((u32*)p_hist, (u32*)p_cur, sh.NB, 1u << sh.rounds, (u32*)p_segtot);
   EON_LAUNCHED(ctx);
   phase_end(ctx, PH_MSM_SCAN);
 
   phase_begin(ctx, PH_MSM_SCATTER);
   if (sh.rounds)  // unused slots (bucket padding, segment tails) must read as ENTRY_NONE
     EON_CUDA(ctx, cudaMemsetAsync(p_ent, 0xff, nseg * sh.seg_cap * sizeof(u32), st));
-  k_msm_scatter<<<grid_pts, MSM_THREADS, 0, st>>>(d_scalars, n, ld, (u32)ncols, sh, (u32*)p_cur, (u32*)p_ent);
-  EON_LAUNCHED(ctx);
+  {
+    static int env_mode = -2;
+    if (env_mode == -2) {
+      const char* e = getenv("EON_MSM_SORT");
+      env_mode = e ? atoi(e) : -1;
+    }
+    const int mode = ctx->msm_sort_mode >= 0 ? ctx->msm_sort_mode : env_mode;
+    int rc = 1;
+    if (mode != 0 && (mode == 1 || n >= 4096))  // two coalesced passes (msm_sort.cu); small inputs: one pass
+      rc = msm_sort_entries(ctx, d_scalars, n, ncols, ld, sh, (const u32*)p_hist, (const u32*)p_segtot, (u32*)p_cur,
+                            (u32*)p_ent);
+    if (rc < 0) return rc;
+    if (rc > 0) {
+      k_msm_scatter<<<grid_pts, MSM_THREADS, 0, st>>>(d_scalars, n, ld, (u32)ncols, sh, (u32*)p_cur, (u32*)p_ent);
+      EON_LAUNCHED(ctx);
+    }
+  }
   phase_end(ctx, PH_MSM_SCATTER);
 
   phase_begin(ctx, PH_MSM_ACCUM);

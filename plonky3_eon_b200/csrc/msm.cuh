@@ -33,5 +33,76 @@ int msm_tree_rounds(eon_ctx* ctx, const G1Affine* d_bases, const u32* d_entries,
                     const G1Affine** out_pts);
 
 
+// Counting sort of the (point, window) entries by bucket in two coalesced passes (msm_sort.cu):
+// coarse scatter by the high bucket bits into a temporary array, then a per-bin fine placement.
+// In: starts[] (aligned exclusive scan of the bucket histogram), seg_total[] (aligned slots used per
+// segment).  Out: entries[] sorted by bucket,
+// ends[g] = starts[g] + count(g).  Returns EON_OK, or a positive value if the shape is not supported
+// (caller falls back to the one-pass atomic scatter).
+int msm_sort_entries(eon_ctx* ctx, const Fr* d_scalars, size_t n, size_t ncols, size_t ld, const MsmShape& sh,
+                     const u32* d_starts, const u32* d_seg_total, u32* d_ends, u32* d_entries);
+
+#if defined(__CUDACC__)
+// ---- 1. scalar -> signed window digits --------------------------------------------------------
+// s * 1 * R^-1 gives the canonical integer (the reference hands halo2curves Montgomery scalars,
+// bn254/src/curve.rs:173-174).  Digits d_w in [-2^(c-1), 2^(c-1)) with sum d_w 2^(c w) = scalar;
+// The top window never wraps: W*c >= 255 leaves it at most c - 1 scalar bits, so raw + carry <=
+// 2^(c-1), which still has a bucket (index 2^(c-1) - 1).  f(w, d) for d != 0.
+// k: canonical scalar limbs.  The limbs are consumed through a 64-bit bit buffer in a fully unrolled
+// loop, so k[] stays in registers (indexing it by a runtime window position would spill it to local
+// memory).
+template <class F>
+__device__ __forceinline__ void for_each_digit_canonical(const u32 (&k)[8], const MsmShape& sh, F f) {
+  const u32 c = sh.c, W = sh.W;
+  const u32 mask = (1u << c) - 1;
+  const u32 half = 1u << (c - 1);
+  u64 buf = 0;
+  u32 nbits = 0, w = 0, carry = 0;
+  auto emit = [&](u32 raw) {
+    raw += carry;
+    int d;
+    if (raw >= half && w + 1 < W) {
+      d = (int)raw - (int)(1u << c);
+      carry = 1;
+    } else {
+      d = (int)raw;
+      carry = 0;
+    }
+    if (d != 0) f(w, d);
+    w++;
+  };
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    buf |= (u64)k[j] << nbits;
+    nbits += 32;
+    while (nbits >= c && w < W) {
+      emit((u32)buf & mask);
+      buf >>= c;
+      nbits -= c;
+    }
+  }
+  while (w < W) {  // top window(s): remaining bits, zero-extended
+    emit((u32)buf & mask);
+    buf >>= c;
+  }
+}
+
+template <class F>
+__device__ __forceinline__ void for_each_digit(const Fr& s, const MsmShape& sh, F f) {
+  u32 k[8];
+  fp_from_mont(k, s);
+  for_each_digit_canonical(k, sh, f);
+}
+
+__device__ __forceinline__ Fr load_scalar(const Fr* __restrict__ scalars, size_t i, size_t ld, u32 col) {
+  const uint4* sp = reinterpret_cast<const uint4*>(scalars + i * ld + col);
+  uint4 lo = __ldg(sp), hi = __ldg(sp + 1);
+  Fr s;
+  s.v[0] = lo.x; s.v[1] = lo.y; s.v[2] = lo.z; s.v[3] = lo.w;
+  s.v[4] = hi.x; s.v[5] = hi.y; s.v[6] = hi.z; s.v[7] = hi.w;
+  return s;
+}
+
+#endif  // __CUDACC__
 
 }  // namespace eon

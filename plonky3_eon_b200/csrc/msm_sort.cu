@@ -1,0 +1,247 @@
+// Two-pass counting sort of the MSM entries by bucket (sm_100a).
+//
+// The Pippenger bucket phase behind G1::multi_exp (bn254/src/curve.rs:158-180) needs, for every bucket
+// of every (column, bucket set) segment, the list of bases that fall into it.  The one-pass scatter
+// (k_msm_scatter in msm.cu) does one returning global atomic and one isolated 4-byte store per entry
+// — 2.5e8 of each at 2^20 x 16 — and is bound by L2 atomic/partial-sector traffic (6.1 ms, 8 GB of
+// DRAM traffic for a 1 GB result).  Here the same permutation is done MSD-radix style:
+//
+//   k_sort_coarse  a CTA takes a tile of 1024 scalars of one column, histograms their digits by the
+//                  HIGH bucket bits (bin = bucket >> 7) in shared memory, reserves one contiguous run
+//                  per bin with a single global atomic, groups the entries by bin in shared memory and
+//                  copies (payload, low bucket bits) out coalesced: 512 global atomics per tile and
+//                  full-sector stores instead of one atomic + one isolated store per entry.
+//   k_sort_fine    one CTA per (segment, bin): 128 bucket cursors in shared memory (from the aligned
+//                  bucket starts); the bin's entries stream in coalesced, are placed in a shared-memory
+//                  image of the bin's ~120 KB window of the final array, and the window (padding =
+//                  ENTRY_NONE) is written out coalesced.
+// (An SM retires scattered 4-byte stores at about one sector per clock whatever L2 merges afterwards;
+// that, not DRAM, bounded the one-pass scatter and a first version of this file without staging.)
+//
+// The bucket histogram / aligned scan (k_msm_hist, k_msm_scan) stay as they are: the bin regions are
+// simply [starts[bin * 128], starts[(bin + 1) * 128]), so no second scan is needed.
+#include <stdlib.h>
+
+#include "msm.cuh"
+
+namespace eon {
+
+constexpr u32 SORT_THREADS = 256;
+constexpr u32 SORT_FINE_THREADS = 1024;
+constexpr u32 SORT_MAX_TILE_BINS = 4096;   // nsets * nbins: shared histogram / offsets / run bases of a tile
+constexpr u32 SORT_WIN_CAP = 40960;        // entry slots of a bin window staged in shared memory (160 KiB)
+constexpr size_t SORT_COARSE_SMEM = 160 * 1024;
+
+// counter[key] += 1 for every active lane, returning each lane's rank.  Plain shared-memory atomics
+// (MATCH.ANY-style aggregation costs more than the few conflicts it saves on uniform scalars), except
+// when the whole warp hits ONE counter — all-equal / tiny scalars — where one atomic serves the warp.
+__device__ __forceinline__ u32 smem_rank(u32* counter, u32 key) {
+  const u32 mask = __activemask();
+  const u32 leader = __ffs(mask) - 1;
+  const u32 k0 = __shfl_sync(mask, key, leader);
+  if (__all_sync(mask, key == k0)) {
+    const u32 lane = threadIdx.x & 31;
+    u32 base = 0;
+    if (lane == leader) base = atomicAdd(counter + key, __popc(mask));
+    base = __shfl_sync(mask, base, leader);
+    return base + __popc(mask & ((1u << lane) - 1));
+  }
+  return atomicAdd(counter + key, 1u);
+}
+
+// region_cursor[seg * nbins + k] = starts[seg * NB + (k << fb)]
+__global__ void k_sort_init(const u32* __restrict__ starts, u32 NB, u32 nbins, u32 fb, size_t total_bins,
+                            u32* __restrict__ region_cursor) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= total_bins) return;
+  size_t seg = i / nbins;
+  u32 k = (u32)(i % nbins);
+  region_cursor[i] = starts[seg * NB + ((size_t)k << fb)];
+}
+
+// Coarse pass.  grid: ncols * ceil(n / tile) blocks, column index fastest (cf. k_msm_hist).
+// Shared memory: cnt[tile_bins] | off[tile_bins + 1] | gbase[tile_bins] | stage_pay[tile * W] u32 |
+// stage_key[tile * W] u16.  The tile's entries are grouped by bin in shared memory first, so the copy
+// to the temporary array is coalesced (consecutive threads -> consecutive slots of a run).
+__global__ void __launch_bounds__(SORT_THREADS)
+k_sort_coarse(const Fr* __restrict__ scalars, size_t n, size_t ld, u32 ncols, MsmShape sh, u32 nbins, u32 fb, u32 tile,
+              u32* __restrict__ region_cursor, u32* __restrict__ tmp_pay, unsigned short* __restrict__ tmp_key) {
+  extern __shared__ u32 smem[];
+  const u32 tile_bins = sh.nsets * nbins;
+  u32* s_cnt = smem;
+  u32* s_off = s_cnt + tile_bins;        // tile_bins + 1
+  u32* s_gbase = s_off + tile_bins + 1;
+  u32* s_pay = s_gbase + tile_bins;
+  unsigned short* s_key = reinterpret_cast<unsigned short*>(s_pay + (size_t)tile * sh.W);
+  __shared__ u32 s_warp[SORT_THREADS / 32];
+  const u32 tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const u32 col = blockIdx.x % ncols;
+  const size_t i0 = (size_t)(blockIdx.x / ncols) * tile;
+  const size_t seg0 = (size_t)col * sh.nsets;
+  const u32 fmask = (1u << fb) - 1;
+
+  for (u32 k = tid; k < tile_bins; k += SORT_THREADS) s_cnt[k] = 0;
+  __syncthreads();
+  // canonical scalars of this thread (tile <= 4 * SORT_THREADS), kept in registers for both sweeps
+  u32 kk[4][8];
+#pragma unroll
+  for (int q = 0; q < 4; q++) {
+    const u32 t = tid + q * SORT_THREADS;
+    const size_t i = i0 + t;
+    if (t < tile && i < n) {
+      fp_from_mont(kk[q], load_scalar(scalars, i, ld, col));
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; j++) kk[q][j] = 0;  // zero scalar: no digits
+    }
+  }
+  // histogram of the tile by bin
+#pragma unroll
+  for (int q = 0; q < 4; q++) {
+    for_each_digit_canonical(kk[q], sh, [&](u32 w, int d) {
+      u32 b = (u32)(d < 0 ? -d : d) - 1;
+      atomicAdd(&s_cnt[(sh.merged ? 0 : w) * nbins + (b >> fb)], 1u);
+    });
+  }
+  __syncthreads();
+  // exclusive scan over the bins (each thread owns a contiguous strip), one global reservation per bin
+  {
+    const u32 per = (tile_bins + SORT_THREADS - 1) / SORT_THREADS;
+    const u32 k0 = tid * per, k1 = min(tile_bins, k0 + per);
+    u32 sum = 0;
+    for (u32 k = k0; k < k1; k++) sum += s_cnt[k];
+    u32 x = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      u32 y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= (u32)o) x += y;
+    }
+    if (lane == 31) s_warp[wid] = x;
+    __syncthreads();
+    u32 wbase = 0;
+    for (u32 j = 0; j < wid; j++) wbase += s_warp[j];
+    u32 run = wbase + x - sum;
+    for (u32 k = k0; k < k1; k++) {
+      u32 c = s_cnt[k];
+      s_off[k] = run;
+      run += c;
+      s_gbase[k] = c ? atomicAdd(&region_cursor[seg0 * nbins + k], c) : 0;
+      s_cnt[k] = 0;
+    }
+    if (tid == SORT_THREADS - 1) s_off[tile_bins] = run;
+  }
+  __syncthreads();
+  // group the entries by bin in shared memory
+#pragma unroll
+  for (int q = 0; q < 4; q++) {
+    const size_t i = i0 + tid + q * SORT_THREADS;
+    for_each_digit_canonical(kk[q], sh, [&](u32 w, int d) {
+      u32 b = (u32)(d < 0 ? -d : d) - 1;
+      u32 bin = (sh.merged ? 0 : w) * nbins + (b >> fb);
+      u32 slot = s_off[bin] + smem_rank(s_cnt, bin);
+      u32 base = sh.merged ? (u32)(w * sh.tab_stride + sh.base_first + i) : (u32)i;
+      s_pay[slot] = base | (d < 0 ? SIGN_BIT : 0u);
+      s_key[slot] = (unsigned short)(b & fmask);
+    });
+  }
+  __syncthreads();
+  // coalesced copy-out, one warp per bin: lanes -> consecutive slots of the bin's run
+  for (u32 bin = wid; bin < tile_bins; bin += SORT_THREADS / 32) {
+    const u32 o0 = s_off[bin], o1 = s_off[bin + 1];
+    if (o0 == o1) continue;
+    const size_t dst = (seg0 + bin / nbins) * sh.seg_cap + s_gbase[bin];
+    for (u32 idx = o0 + lane; idx < o1; idx += 32) {
+      tmp_pay[dst + (idx - o0)] = s_pay[idx];
+      tmp_key[dst + (idx - o0)] = s_key[idx];
+    }
+  }
+}
+
+// Fine pass.  grid: nseg * nbins blocks.  Bin k of segment seg holds tmp slots [starts[k << fb],
+// region_cursor) and owns the window [starts[k << fb], starts[(k + 1) << fb]) of the final array.
+// Windows up to SORT_WIN_CAP slots are built in shared memory (padding = ENTRY_NONE) and written out
+// coalesced; larger ones (skewed scalars, very large inputs) are scattered directly.
+__global__ void __launch_bounds__(SORT_FINE_THREADS)
+k_sort_fine(const u32* __restrict__ tmp_pay, const unsigned short* __restrict__ tmp_key,
+            const u32* __restrict__ region_cursor, const u32* __restrict__ starts, const u32* __restrict__ seg_total,
+            u32 NB, u32 nbins, u32 fb, u64 seg_cap, u32* __restrict__ ends, u32* __restrict__ entries) {
+  extern __shared__ u32 smem[];
+  const u32 fine = 1u << fb;
+  u32* s_cur = smem;          // fine
+  u32* s_win = smem + fine;   // SORT_WIN_CAP
+  const size_t seg = blockIdx.x / nbins;
+  const u32 k = blockIdx.x % nbins;
+  const size_t g0 = seg * NB + ((size_t)k << fb);
+  const size_t off = seg * seg_cap;
+  const u32 tid = threadIdx.x;
+  const u32 begin = starts[g0], end = region_cursor[seg * nbins + k];
+  for (u32 f = tid; f < fine; f += SORT_FINE_THREADS) s_cur[f] = starts[g0 + f];
+  // window end: the next bin's first start, or (last bin) the aligned end of the segment
+  const u32 wend = (k + 1 < nbins) ? starts[g0 + fine] : seg_total[seg];
+  const u32 wlen = wend - begin;
+  const bool staged = wlen <= SORT_WIN_CAP;
+  if (staged)
+    for (u32 j = tid; j < wlen; j += SORT_FINE_THREADS) s_win[j] = ENTRY_NONE;
+  __syncthreads();
+  for (u32 i = begin + tid; i < end; i += SORT_FINE_THREADS) {
+    u32 key = tmp_key[off + i];
+    u32 pay = tmp_pay[off + i];
+    u32 pos = smem_rank(s_cur, key);
+    if (staged) s_win[pos - begin] = pay;
+    else entries[off + pos] = pay;
+  }
+  __syncthreads();
+  if (staged)
+    for (u32 j = tid; j < wlen; j += SORT_FINE_THREADS) entries[off + begin + j] = s_win[j];
+  for (u32 f = tid; f < fine; f += SORT_FINE_THREADS) ends[g0 + f] = s_cur[f];
+}
+
+static bool g_sort_attr_set = false;
+
+int msm_sort_entries(eon_ctx* ctx, const Fr* d_scalars, size_t n, size_t ncols, size_t ld, const MsmShape& sh,
+                     const u32* d_starts, const u32* d_seg_total, u32* d_ends, u32* d_entries) {
+  if (sh.NB < 256) return 1;  // too few buckets for a coarse level
+  u32 fb = 7;
+  while (((u64)sh.nsets * (sh.NB >> fb)) > SORT_MAX_TILE_BINS) fb++;
+  if (fb > 12 || fb >= sh.c - 1) return 1;
+  const u32 nbins = sh.NB >> fb;
+  const u32 tile_bins = sh.nsets * nbins;
+  // scalars per coarse tile: stage (6 bytes per entry, up to W entries per scalar) within the smem budget
+  u32 tile = 4 * SORT_THREADS;  // k_sort_coarse keeps 4 scalars per thread in registers
+  if (const char* e = getenv("EON_SORT_TILE")) tile = (u32)atoi(e);
+  if (tile > 4 * SORT_THREADS || tile < 64) tile = 4 * SORT_THREADS;
+  const size_t fixed = ((size_t)3 * tile_bins + 1) * sizeof(u32);
+  while (tile > 64 && fixed + (size_t)tile * sh.W * 6 > SORT_COARSE_SMEM) tile >>= 1;
+  if (fixed + (size_t)tile * sh.W * 6 > SORT_COARSE_SMEM) return 1;
+  const size_t smem_coarse = fixed + (size_t)tile * sh.W * 6 + 16;
+  const size_t smem_fine = ((size_t)(1u << fb) + SORT_WIN_CAP) * sizeof(u32);
+  const size_t nseg = ncols * sh.nsets;
+  const size_t total_bins = nseg * nbins;
+  const size_t tiles = (n + tile - 1) / tile;
+  if (tiles * ncols > 0x7fffffffull || total_bins > 0x7fffffffull) return 1;
+  if (!g_sort_attr_set) {
+    EON_CUDA(ctx, cudaFuncSetAttribute(k_sort_coarse, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)(SORT_COARSE_SMEM + 16)));
+    EON_CUDA(ctx, cudaFuncSetAttribute(k_sort_fine, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)(((size_t)(1u << 12) + SORT_WIN_CAP) * sizeof(u32))));
+    g_sort_attr_set = true;
+  }
+  void *p_reg, *p_pay, *p_key;
+  EON_TRY(scratch_get(ctx, SC_MSM_SORT_REGION, total_bins * sizeof(u32), &p_reg));
+  EON_TRY(scratch_get(ctx, SC_MSM_SORT_PAY, nseg * sh.seg_cap * sizeof(u32), &p_pay));
+  EON_TRY(scratch_get(ctx, SC_MSM_SORT_KEY, nseg * sh.seg_cap * sizeof(unsigned short), &p_key));
+  cudaStream_t st = ctx->stream;
+  k_sort_init<<<(unsigned)((total_bins + 255) / 256), 256, 0, st>>>(d_starts, sh.NB, nbins, fb, total_bins,
+                                                                    (u32*)p_reg);
+  EON_LAUNCHED(ctx);
+  k_sort_coarse<<<(unsigned)(tiles * ncols), SORT_THREADS, smem_coarse, st>>>(
+      d_scalars, n, ld, (u32)ncols, sh, nbins, fb, tile, (u32*)p_reg, (u32*)p_pay, (unsigned short*)p_key);
+  EON_LAUNCHED(ctx);
+  k_sort_fine<<<(unsigned)total_bins, SORT_FINE_THREADS, smem_fine, st>>>(
+      (const u32*)p_pay, (const unsigned short*)p_key, (const u32*)p_reg, d_starts, d_seg_total, sh.NB, nbins, fb,
+      sh.seg_cap, d_ends, d_entries);
+  EON_LAUNCHED(ctx);
+  return EON_OK;
+}
+
+}  // namespace eon
