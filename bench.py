@@ -233,6 +233,18 @@ def run_eon(args):
             dist.all_gather(gathered, t)
 
     def step_e2e():
+        # what a Pcs shim with an LDE hint calls from commit() (GpuKzgPcs.with_lde_hint): commit + the
+        # quotient-coset evaluations in one call, column groups pipelined over PCIe
+        h = C.c_uint64(0)
+        ctx.call("eon_kzg_commit_lde", host_pin_np, log_rows, cols, shift_one, commits, C.byref(h), log_rows + 1,
+                 shift_lde, lde_pin_np)
+        ctx.call("eon_handle_free", h)
+        if world > 1:
+            t = torch.from_numpy(commits.view(np.int64).reshape(-1)).cuda()
+            dist.all_gather(gathered, t)
+
+    def step_e2e_two_calls():
+        # the unhinted trait sequence: Pcs::commit, then Pcs::get_evaluations_on_domain
         h = C.c_uint64(0)
         ctx.call("eon_kzg_commit", host_pin_np, log_rows, cols, shift_one, commits, C.byref(h))
         ctx.call("eon_kzg_evals_on_coset", h, log_rows + 1, shift_lde, lde_pin_np)
@@ -277,6 +289,12 @@ def run_eon(args):
         step_e2e()
     ms_e2e = timed(step_e2e, args.steps)
     assert np.array_equal(commits, commits_device), "e2e and device-resident commitments differ"
+    lde_fused = lde_pin_np.copy() if rank == 0 and args.check_e2e else None
+    step_e2e_two_calls()
+    ms_e2e2 = timed(step_e2e_two_calls, args.steps)
+    assert np.array_equal(commits, commits_device), "two-call e2e and device-resident commitments differ"
+    if lde_fused is not None:
+        assert np.array_equal(lde_fused, lde_pin_np), "fused and two-call LDE differ"
 
     units = rows * cols * n_gpus * args.steps
     value = units / (ms_dev * 1e-3)
@@ -359,7 +377,12 @@ def run_eon(args):
                    "l2": "inputs (512 MiB trace, 1 GiB LDE, 1 GiB sort workspace) exceed the 126 MB L2",
                    "parallelism": f"columns x{n_gpus}"},
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
-                "h2d_bytes_per_step": rows * cols * 32, "d2h_bytes_per_step": 2 * rows * cols * 32 + cols * 64},
+                "h2d_bytes_per_step": rows * cols * 32, "d2h_bytes_per_step": 2 * rows * cols * 32 + cols * 64,
+                "call": "eon_kzg_commit_lde (Pcs::commit with an LDE hint; host pinned buffers in and out)",
+                "two_calls_ms_per_step": ms_e2e2 / args.steps,
+                "two_calls_value": units / (ms_e2e2 * 1e-3),
+                "two_calls": "eon_kzg_commit then eon_kzg_evals_on_coset (unhinted Pcs::commit + "
+                             "get_evaluations_on_domain)"},
         "gpu_launches": launches,
         "clocks": clocks,
         "phase_ms_per_step": {k: v / args.steps for k, v in phases.items()},
@@ -480,6 +503,7 @@ def main():
     ap.add_argument("--log-rows", type=int, default=20)
     ap.add_argument("--cols", type=int, default=16)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--check-e2e", action="store_true", help="compare the fused and two-call LDE bytes (1 GiB copy)")
     ap.add_argument("--warmup-ref", type=int, default=0)
     ap.add_argument("--window-bits", type=int, default=-1,
                     help="MSM window tables: -1 library default, 0 none (plain c=16), 8..20 explicit")

@@ -148,6 +148,15 @@ int eon_kzg_commit(eon_ctx* ctx, const uint64_t* h_evals, unsigned log_h, size_t
                    uint64_t* h_commit_xy, eon_handle* out_handle);
 int eon_kzg_commit_dev(eon_ctx* ctx, const uint64_t* d_evals, unsigned log_h, size_t width, const uint64_t shift[4],
                        uint64_t* h_commit_xy, eon_handle* out_handle);
+/* commit + the evaluations the prover asks for next, in one call: exactly eon_kzg_commit followed by
+ * eon_kzg_evals_on_coset(handle, lde_log_size, lde_shift, h_lde_out) (pcs.rs:223-265 then :267-287, as
+ * called back to back by eon-uni-stark/src/prover.rs:186-187,307-322), but the LDE of every column
+ * group crosses PCIe while that group's MSM runs, so the 2^(lde_log_size) x width download is hidden.
+ * A Pcs shim built with an "LDE hint" (quotient-domain size and shift, both known before the trace is
+ * committed) calls this from commit() and hands the matrix out from get_evaluations_on_domain(). */
+int eon_kzg_commit_lde(eon_ctx* ctx, const uint64_t* h_evals, unsigned log_h, size_t width, const uint64_t shift[4],
+                       uint64_t* h_commit_xy, eon_handle* out_handle, unsigned lde_log_size,
+                       const uint64_t lde_shift[4], uint64_t* h_lde_out);
 /* KzgMmcs::commit (kzg/src/mmcs.rs:155-190) for ONE matrix: the columns are taken as polynomials
  * in COEFFICIENT form (no iDFT); `rows` may be any height (not only powers of two).
  * commitment[c] = commit_column(matrix[:, c]) (mmcs.rs:155-165).  The matrix is kept on the device
@@ -193,6 +202,10 @@ int eon_bench_modmul(eon_ctx* ctx, int field, double* out_gmuls);
 int eon_last_phase_ms(eon_ctx* ctx, int phase, float* out_ms);
 int eon_phase_reset(eon_ctx* ctx);
 int eon_phase_count(void);
+/* strided host<->device copy rate (rows x width_bytes out of a pinned host matrix with row pitch
+ * pitch_bytes), ms per copy: sizes the column-group pipelining of the host-buffer entry points */
+int eon_bench_copy2d(eon_ctx* ctx, void* h_ptr, size_t rows, size_t width_bytes, size_t pitch_bytes, int to_device,
+                     float* out_ms);
 const char* eon_phase_name(int phase);
 
 #ifdef __cplusplus

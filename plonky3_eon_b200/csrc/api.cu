@@ -2,6 +2,8 @@
 // reference file:line each function replaces).
 #include <stdlib.h>
 
+#include <algorithm>
+
 #include "common.cuh"
 
 using namespace eon;
@@ -91,6 +93,10 @@ void eon_ctx_destroy(eon_ctx* ctx) {
   if (ctx->d_srs) cudaFree(ctx->d_srs);
   if (ctx->d_srs_tab) cudaFree(ctx->d_srs_tab);
   for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
+  for (cudaEvent_t e : ctx->ev_pipe)
+    if (e) cudaEventDestroy(e);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  if (ctx->copy_stream2) cudaStreamDestroy(ctx->copy_stream2);
   delete ctx;
 }
 
@@ -530,18 +536,144 @@ int eon_kzg_commit_dev(eon_ctx* ctx, const uint64_t* d_evals, unsigned log_h, si
   return kzg_commit_locked(ctx, d_evals, log_h, width, shift, h_commit_xy, out_handle);
 }
 
+// Column groups for the PCIe pipelining of the host-buffer entry points.  Every column's transform
+// and MSM is independent (kzg/src/pcs.rs:244-249), so group g+1 can cross PCIe while group g computes.
+// Strided copies of >= 128-byte row pieces run at >= 85 % of the contiguous rate (tools/copy2d_probe.py).
+static std::vector<std::pair<size_t, size_t>> column_groups(size_t width, size_t bytes, bool small_first) {
+  std::vector<std::pair<size_t, size_t>> g;
+  if (width < 8 || bytes < ((size_t)32 << 20) || getenv("EON_NO_PIPELINE")) {
+    g.push_back(std::make_pair((size_t)0, width));
+    return g;
+  }
+  // upload: a small first group (its copy is the only exposed one); download: two halves (256-byte rows)
+  size_t g0 = small_first ? std::max<size_t>(4, (width / 4) & ~(size_t)3) : ((width / 2 + 3) & ~(size_t)3);
+  if (g0 >= width) g0 = width / 2;
+  g.push_back(std::make_pair((size_t)0, g0));
+  g.push_back(std::make_pair(g0, width - g0));
+  return g;
+}
+
+static int pipe_init(eon_ctx* ctx) {
+  if (!ctx->copy_stream) EON_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+  if (!ctx->copy_stream2) EON_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream2, cudaStreamNonBlocking));
+  for (auto& e : ctx->ev_pipe)
+    if (!e) EON_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  return EON_OK;
+}
+
+// commit from host buffers, optionally with the evaluations on a second coset (the LDE the prover asks
+// for next, eon-uni-stark/src/prover.rs:307-322) produced in the same call: lde_log_size == 0 -> none.
+static int kzg_commit_host(eon_ctx* ctx, const uint64_t* h_evals, unsigned log_h, size_t width, const uint64_t shift[4],
+                           uint64_t* h_commit_xy, eon_handle* out_handle, unsigned lde_log_size,
+                           const uint64_t lde_shift[4], uint64_t* h_lde_out) {
+  EON_TRY(check_dims(ctx, log_h, width));
+  const bool want_lde = lde_log_size != 0;
+  Fr ls = Fr::one();
+  if (want_lde) {
+    if (lde_log_size < log_h) return fail(ctx, EON_ERR_BAD_ARG, "LDE domain smaller than the trace domain");
+    EON_TRY(check_dims(ctx, lde_log_size, width));
+    EON_TRY(check_shift(ctx, lde_shift, &ls));
+    if (width && !h_lde_out) return fail(ctx, EON_ERR_BAD_ARG, "null LDE output");
+  }
+  size_t b = mat_bytes(log_h, width);
+  if (b && !h_evals) return fail(ctx, EON_ERR_BAD_ARG, "null evals");
+  void* d_in = nullptr;
+  EON_TRY(scratch_get(ctx, SC_IO_A, b + 32, &d_in));
+  auto groups = column_groups(width, b, true);
+  if (groups.size() == 1 && !want_lde) {
+    if (b) EON_CUDA(ctx, cudaMemcpyAsync(d_in, h_evals, b, cudaMemcpyHostToDevice, ctx->stream));
+    return kzg_commit_locked(ctx, (const uint64_t*)d_in, log_h, width, shift, h_commit_xy, out_handle);
+  }
+  if (width == 0) {
+    if (!out_handle) return fail(ctx, EON_ERR_BAD_ARG, "null handle pointer");
+    return kzg_commit_locked(ctx, (const uint64_t*)d_in, log_h, width, shift, h_commit_xy, out_handle);
+  }
+  // pipelined: H2D of group g+1 (copy stream) under the iDFT + MSM of group g (compute stream)
+  if (!out_handle) return fail(ctx, EON_ERR_BAD_ARG, "null handle pointer");
+  *out_handle = 0;
+  Fr s;
+  EON_TRY(check_shift(ctx, shift, &s));
+  const size_t h = (size_t)1 << log_h;
+  if (h > ctx->srs_n) {  // ensure_supported(height - 1), kzg/src/pcs.rs:238-240 — before any copy
+    char msg[128];
+    snprintf(msg, sizeof(msg), "DegreeTooLarge: degree %zu > max %zu", h - 1, ctx->srs_n ? ctx->srs_n - 1 : 0);
+    return fail(ctx, EON_ERR_SRS_TOO_SHORT, msg);
+  }
+  if (!h_commit_xy) return fail(ctx, EON_ERR_BAD_ARG, "null buffer");
+  EON_TRY(pipe_init(ctx));
+  Fr* d_coeffs = nullptr;
+  size_t cap = 0;
+  EON_TRY(coeff_buffer_get(ctx, b + 32, &d_coeffs, &cap));
+  void* d_commit = nullptr;
+  int rc = scratch_get(ctx, SC_MSM_RESULT, width * sizeof(G1Affine) + 64, &d_commit);
+  void* d_lde = nullptr;
+  const size_t lde_rows = want_lde ? (size_t)1 << lde_log_size : 0;
+  if (rc == EON_OK && want_lde) rc = scratch_get(ctx, SC_IO_B, mat_bytes(lde_log_size, width) + 32, &d_lde);
+  const size_t pitch = width * sizeof(Fr);
+  // earlier work on the compute stream may still read d_in (same scratch): copies wait for it
+  if (rc == EON_OK && cudaEventRecord(ctx->ev_pipe[7], ctx->stream) != cudaSuccess) rc = fail(ctx, EON_ERR_CUDA, "event");
+  if (rc == EON_OK) cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_pipe[7], 0);
+  for (size_t g = 0; rc == EON_OK && g < groups.size(); g++) {
+    const size_t c0 = groups[g].first, gw = groups[g].second;
+    cudaError_t e = cudaMemcpy2DAsync((Fr*)d_in + c0, pitch, (const Fr*)h_evals + c0, pitch, gw * sizeof(Fr), h,
+                                      cudaMemcpyHostToDevice, ctx->copy_stream);
+    if (e == cudaSuccess) e = cudaEventRecord(ctx->ev_pipe[g], ctx->copy_stream);
+    if (e != cudaSuccess) rc = fail(ctx, EON_ERR_CUDA, std::string("group upload failed: ") + cudaGetErrorString(e));
+  }
+  for (size_t g = 0; rc == EON_OK && g < groups.size(); g++) {
+    const size_t c0 = groups[g].first, gw = groups[g].second;
+    cudaStreamWaitEvent(ctx->stream, ctx->ev_pipe[g], 0);
+    rc = ntt_inverse(ctx, (const Fr*)d_in + c0, d_coeffs + c0, log_h, gw, s, LAYOUT_NATURAL, width, width);
+    if (rc == EON_OK && want_lde) {
+      // the group's LDE goes out over PCIe (second copy stream: downloads run beside the uploads)
+      // while its MSM, the long part, runs
+      rc = ntt_forward(ctx, d_coeffs + c0, (Fr*)d_lde + c0, lde_log_size, lde_log_size - log_h, gw, ls, LAYOUT_NATURAL,
+                       width, width);
+      if (rc == EON_OK) {
+        cudaError_t e = cudaEventRecord(ctx->ev_pipe[8 + g], ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->copy_stream2, ctx->ev_pipe[8 + g], 0);
+        if (e == cudaSuccess)
+          e = cudaMemcpy2DAsync((Fr*)h_lde_out + c0, pitch, (const Fr*)d_lde + c0, pitch, gw * sizeof(Fr), lde_rows,
+                                cudaMemcpyDeviceToHost, ctx->copy_stream2);
+        if (e != cudaSuccess) rc = fail(ctx, EON_ERR_CUDA, std::string("LDE download failed: ") + cudaGetErrorString(e));
+      }
+    }
+    if (rc == EON_OK) rc = msm_run(ctx, ctx->d_srs, d_coeffs + c0, h, gw, width, (G1Affine*)d_commit + c0);
+  }
+  if (rc == EON_OK) {
+    cudaError_t e = cudaMemcpyAsync(h_commit_xy, d_commit, width * sizeof(G1Affine), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e == cudaSuccess && want_lde) e = cudaStreamSynchronize(ctx->copy_stream2);
+    if (e != cudaSuccess) rc = fail(ctx, EON_ERR_CUDA, std::string("commit readback failed: ") + cudaGetErrorString(e));
+  }
+  if (rc != EON_OK) {
+    cudaStreamSynchronize(ctx->copy_stream);
+    cudaStreamSynchronize(ctx->copy_stream2);
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_coeffs);
+    return rc;
+  }
+  *out_handle = handle_new(ctx, d_coeffs, h, log_h, width, cap);
+  return EON_OK;
+}
+
 int eon_kzg_commit(eon_ctx* ctx, const uint64_t* h_evals, unsigned log_h, size_t width, const uint64_t shift[4],
                    uint64_t* h_commit_xy, eon_handle* out_handle) {
   if (!ctx) return EON_ERR_BAD_ARG;
   Lock lk(ctx);
   EON_TRY(set_device(ctx));
-  EON_TRY(check_dims(ctx, log_h, width));
-  size_t b = mat_bytes(log_h, width);
-  if (b && !h_evals) return fail(ctx, EON_ERR_BAD_ARG, "null evals");
-  void* d_in = nullptr;
-  EON_TRY(scratch_get(ctx, SC_IO_A, b + 32, &d_in));
-  if (b) EON_CUDA(ctx, cudaMemcpyAsync(d_in, h_evals, b, cudaMemcpyHostToDevice, ctx->stream));
-  return kzg_commit_locked(ctx, (const uint64_t*)d_in, log_h, width, shift, h_commit_xy, out_handle);
+  return kzg_commit_host(ctx, h_evals, log_h, width, shift, h_commit_xy, out_handle, 0, nullptr, nullptr);
+}
+
+int eon_kzg_commit_lde(eon_ctx* ctx, const uint64_t* h_evals, unsigned log_h, size_t width, const uint64_t shift[4],
+                       uint64_t* h_commit_xy, eon_handle* out_handle, unsigned lde_log_size,
+                       const uint64_t lde_shift[4], uint64_t* h_lde_out) {
+  if (!ctx) return EON_ERR_BAD_ARG;
+  if (lde_log_size == 0) return EON_ERR_BAD_ARG;
+  Lock lk(ctx);
+  EON_TRY(set_device(ctx));
+  return kzg_commit_host(ctx, h_evals, log_h, width, shift, h_commit_xy, out_handle, lde_log_size, lde_shift,
+                         h_lde_out);
 }
 
 static int find_handle(eon_ctx* ctx, eon_handle h, ProverMatrix* pm) {
@@ -625,13 +757,39 @@ int eon_kzg_evals_on_coset(eon_ctx* ctx, eon_handle h, unsigned log_size, const 
   size_t b = mat_bytes(log_size, pm.width);
   void* d_out = nullptr;
   EON_TRY(scratch_get(ctx, SC_IO_B, b + 32, &d_out));
-  EON_TRY(evals_on_coset_locked(ctx, h, log_size, shift, (Fr*)d_out));
-  if (b) {
-    if (!h_out) return fail(ctx, EON_ERR_BAD_ARG, "null output");
-    EON_CUDA(ctx, cudaMemcpyAsync(h_out, d_out, b, cudaMemcpyDeviceToHost, ctx->stream));
+  auto groups = column_groups(pm.width, b, false);
+  if (groups.size() == 1 || pm.log_h == NOT_POW2 || log_size < pm.log_h) {
+    EON_TRY(evals_on_coset_locked(ctx, h, log_size, shift, (Fr*)d_out));
+    if (b) {
+      if (!h_out) return fail(ctx, EON_ERR_BAD_ARG, "null output");
+      EON_CUDA(ctx, cudaMemcpyAsync(h_out, d_out, b, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    EON_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return EON_OK;
   }
-  EON_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  return EON_OK;
+  // pipelined: D2H of group g (copy stream) under the coset NTT of group g+1 (compute stream)
+  Fr s;
+  EON_TRY(check_shift(ctx, shift, &s));
+  EON_TRY(check_dims(ctx, log_size, pm.width));
+  if (!h_out) return fail(ctx, EON_ERR_BAD_ARG, "null output");
+  EON_TRY(pipe_init(ctx));
+  const size_t w = pm.width, rows = (size_t)1 << log_size, pitch = w * sizeof(Fr);
+  int rc = EON_OK;
+  for (size_t g = 0; rc == EON_OK && g < groups.size(); g++) {
+    const size_t c0 = groups[g].first, gw = groups[g].second;
+    rc = ntt_forward(ctx, pm.d_coeffs + c0, (Fr*)d_out + c0, log_size, log_size - pm.log_h, gw, s, LAYOUT_NATURAL, w, w);
+    if (rc != EON_OK) break;
+    cudaError_t e = cudaEventRecord(ctx->ev_pipe[g], ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_pipe[g], 0);
+    if (e == cudaSuccess)
+      e = cudaMemcpy2DAsync((Fr*)h_out + c0, pitch, (const Fr*)d_out + c0, pitch, gw * sizeof(Fr), rows,
+                            cudaMemcpyDeviceToHost, ctx->copy_stream);
+    if (e != cudaSuccess) rc = fail(ctx, EON_ERR_CUDA, std::string("group download failed: ") + cudaGetErrorString(e));
+  }
+  cudaError_t e1 = cudaStreamSynchronize(ctx->copy_stream), e2 = cudaStreamSynchronize(ctx->stream);
+  if (rc == EON_OK && (e1 != cudaSuccess || e2 != cudaSuccess))
+    rc = fail(ctx, EON_ERR_CUDA, std::string("download failed: ") + cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
+  return rc;
 }
 
 int eon_quotient_and_eval_dev(eon_ctx* ctx, const uint64_t* d_coeffs, size_t h, size_t width, const uint64_t z[4],
@@ -715,6 +873,33 @@ int eon_phase_reset(eon_ctx* ctx) {
   EON_TRY(set_device(ctx));
   EON_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   phase_reset(ctx);
+  return EON_OK;
+}
+
+// measurement helper: strided (2-D) copy rate between a pinned host matrix and the device, ms per copy
+int eon_bench_copy2d(eon_ctx* ctx, void* h_ptr, size_t rows, size_t width_bytes, size_t pitch_bytes, int to_device,
+                     float* out_ms) {
+  if (!ctx || !h_ptr || !out_ms) return EON_ERR_BAD_ARG;
+  Lock lk(ctx);
+  EON_TRY(set_device(ctx));
+  void* d = nullptr;
+  EON_TRY(scratch_get(ctx, SC_IO_A, rows * width_bytes + 32, &d));
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  for (int it = 0; it < 2; it++) {
+    cudaEventRecord(e0, ctx->stream);
+    cudaError_t rc = to_device ? cudaMemcpy2DAsync(d, width_bytes, h_ptr, pitch_bytes, width_bytes, rows,
+                                                   cudaMemcpyHostToDevice, ctx->stream)
+                               : cudaMemcpy2DAsync(h_ptr, pitch_bytes, d, width_bytes, width_bytes, rows,
+                                                   cudaMemcpyDeviceToHost, ctx->stream);
+    cudaEventRecord(e1, ctx->stream);
+    if (rc != cudaSuccess) return fail(ctx, EON_ERR_CUDA, cudaGetErrorString(rc));
+    EON_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  cudaEventElapsedTime(out_ms, e0, e1);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
   return EON_OK;
 }
 

@@ -110,6 +110,13 @@ struct eon_ctx {
   int msm_sort_mode = -1;        // -1 automatic, 0 one-pass atomic scatter, 1 two-pass coalesced sort
   unsigned msm_rounds_used = 0;  // rounds of the most recent MSM (reporting)
 
+  // second stream + events: the host-buffer entry points move column groups over PCIe while the
+  // previous group computes (created on first use)
+  cudaStream_t copy_stream = nullptr;
+  cudaStream_t copy_stream2 = nullptr;  // opposite PCIe direction (downloads while uploads are in flight)
+  cudaEvent_t ev_pipe[12] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
+                             nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+
   std::map<eon_handle, eon::ProverMatrix> handles;
   eon_handle next_handle = 1;
   // freed coefficient buffers kept for the next commit of a similar size (a prover commits and
@@ -225,11 +232,12 @@ inline Fr fr_two_adic_generator(unsigned bits) {
 enum Layout { LAYOUT_NATURAL = 0, LAYOUT_BITREV = 1 };
 
 // forward coset NTT of size 2^log_n from 2^(log_n-k) coefficient rows (zero-padded).
+// ld_src / ld_dst: row pitch in elements (0 = dense, i.e. width): a column group of a wider matrix.
 int ntt_forward(eon_ctx* ctx, const Fr* d_src, Fr* d_dst, unsigned log_n, unsigned k, size_t width, const Fr& shift,
-                Layout src_layout);
+                Layout src_layout, size_t ld_src = 0, size_t ld_dst = 0);
 // inverse coset NTT of size 2^log_n: evaluations on shift*H (natural) -> coefficients.
 int ntt_inverse(eon_ctx* ctx, const Fr* d_src, Fr* d_dst, unsigned log_n, size_t width, const Fr& shift,
-                Layout dst_layout);
+                Layout dst_layout, size_t ld_src = 0, size_t ld_dst = 0);
 
 // out[c] = sum_i scalars[i*ld + c] * bases[i], c < ncols.  d_out: ncols affine points (device).
 int msm_run(eon_ctx* ctx, const G1Affine* d_bases, const Fr* d_scalars, size_t n, size_t ncols, size_t ld,

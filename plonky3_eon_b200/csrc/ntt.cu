@@ -97,6 +97,8 @@ struct PassParams {
   const uint4* src;
   uint4* dst;
   const uint4* tw;
+  u64 ld_src, ld_dst;  // physical row pitch (elements) of src / dst: w for a dense matrix, more when the
+                       // transform runs on a column group of a wider matrix
   u64 V;        // virtual width = 2^l0 * w elements between consecutive tile rows
   u64 tiles_v;  // ceil(V / cv)
   u32 log_n, w;
@@ -141,7 +143,8 @@ __global__ void __launch_bounds__(NTT_THREADS, 3) k_ntt_pass(const PassParams p)
   const u64 row_base = hi << p.r;  // tile row m is matrix "row group" row_base + m
 
   // ---- load tile (16-byte units, consecutive threads -> consecutive units) ----
-  const bool plain_in = (p.k == 0 && !p.in_rev);
+  const bool plain_in = (p.k == 0 && !p.in_rev && p.ld_src == p.w);
+  const bool plain_out = (p.ld_dst == p.w);
   for (u32 u = tid; u < tile_elems * 2; u += NTT_THREADS) {
     u32 e = u >> 1, half = u & 1;
     u32 m = e >> p.log_cv, vc = e & (cv - 1);
@@ -160,7 +163,7 @@ __global__ void __launch_bounds__(NTT_THREADS, 3) k_ntt_pass(const PassParams p)
         u32 bits = p.log_n - p.k;
         srow = bits ? (u64)(__brev((u32)srow) >> (32 - bits)) : 0;
       }
-      src_elem = srow * p.w + col;
+      src_elem = srow * p.ld_src + col;
     }
     uint4 val = p.src[src_elem * 2 + half];
     (half ? s_hi : s_lo)[e] = val;
@@ -216,9 +219,14 @@ __global__ void __launch_bounds__(NTT_THREADS, 3) k_ntt_pass(const PassParams p)
       if (p.out_rev) {
         u64 pos = row_base + m;  // l0 == 0, V == w
         u64 drow = p.log_n ? (u64)(__brev((u32)pos) >> (32 - p.log_n)) : 0;
-        dst_elem = drow * p.w + vidx;
-      } else {
+        dst_elem = drow * p.ld_dst + vidx;
+      } else if (plain_out) {
         dst_elem = (row_base + m) * p.V + vidx;
+      } else {
+        u64 lo;
+        u32 col;
+        split_vidx(p, vidx, lo, col);
+        dst_elem = (((row_base + m) << p.l0) + lo) * p.ld_dst + col;
       }
       p.dst[dst_elem * 2 + half] = (half ? s_hi : s_lo)[e];
     }
@@ -231,9 +239,14 @@ __global__ void __launch_bounds__(NTT_THREADS, 3) k_ntt_pass(const PassParams p)
       if (p.out_rev) {
         u64 pos = row_base + m;
         u64 drow = p.log_n ? (u64)(__brev((u32)pos) >> (32 - p.log_n)) : 0;
-        dst_elem = drow * p.w + vidx;
-      } else {
+        dst_elem = drow * p.ld_dst + vidx;
+      } else if (plain_out) {
         dst_elem = (row_base + m) * p.V + vidx;
+      } else {
+        u64 lo;
+        u32 col;
+        split_vidx(p, vidx, lo, col);
+        dst_elem = (((row_base + m) << p.l0) + lo) * p.ld_dst + col;
       }
       Fr x = fp_mul(fr_from_units(s_lo[e], s_hi[e]), p.scale_c);
       uint4 lo, hi4;
@@ -321,7 +334,9 @@ static int launch_pass(eon_ctx* ctx, PassParams& p, const PassPlan& pl, unsigned
 }
 
 int ntt_forward(eon_ctx* ctx, const Fr* d_src, Fr* d_dst, unsigned log_n, unsigned k, size_t width, const Fr& shift,
-                Layout src_layout) {
+                Layout src_layout, size_t ld_src, size_t ld_dst) {
+  if (ld_src == 0) ld_src = width;
+  if (ld_dst == 0) ld_dst = width;
   if (width == 0) return EON_OK;
   if (log_n > 28) return fail(ctx, EON_ERR_TWO_ADICITY, "transform size exceeds 2^28 (Fr::TWO_ADICITY)");
   if (k > log_n) return fail(ctx, EON_ERR_BAD_ARG, "ntt_forward: added bits exceed transform size");
@@ -337,12 +352,15 @@ int ntt_forward(eon_ctx* ctx, const Fr* d_src, Fr* d_dst, unsigned log_n, unsign
     p.dif = 0;
     if (i == 0) {
       p.src = (const uint4*)d_src;
+      p.ld_src = ld_src;
       p.k = k;
       p.in_rev = (src_layout == LAYOUT_NATURAL) ? 1 : 0;
     } else {
       p.src = (const uint4*)d_dst;
+      p.ld_src = ld_dst;
     }
     p.dst = (uint4*)d_dst;
+    p.ld_dst = ld_dst;
     EON_TRY(launch_pass(ctx, p, plan[i], log_n, width));
   }
   phase_end(ctx, PH_NTT_PASSES);
@@ -350,7 +368,9 @@ int ntt_forward(eon_ctx* ctx, const Fr* d_src, Fr* d_dst, unsigned log_n, unsign
 }
 
 int ntt_inverse(eon_ctx* ctx, const Fr* d_src, Fr* d_dst, unsigned log_n, size_t width, const Fr& shift,
-                Layout dst_layout) {
+                Layout dst_layout, size_t ld_src, size_t ld_dst) {
+  if (ld_src == 0) ld_src = width;
+  if (ld_dst == 0) ld_dst = width;
   if (width == 0) return EON_OK;
   if (log_n > 28) return fail(ctx, EON_ERR_TWO_ADICITY, "transform size exceeds 2^28 (Fr::TWO_ADICITY)");
   if (width > 0xffffffffull) return fail(ctx, EON_ERR_BAD_ARG, "ntt: width too large");
@@ -360,10 +380,12 @@ int ntt_inverse(eon_ctx* ctx, const Fr* d_src, Fr* d_dst, unsigned log_n, size_t
   const size_t np = plan.size();
   const bool out_rev = (dst_layout == LAYOUT_NATURAL);
   Fr* work = d_dst;
+  size_t ld_work = ld_dst;
   if (np > 1 && out_rev) {
     void* tmp = nullptr;
     EON_TRY(scratch_get(ctx, SC_NTT_TMP, ((size_t)width << log_n) * sizeof(Fr), &tmp));
     work = (Fr*)tmp;
+    ld_work = width;
   }
   Fr n_inv = Fr::one();
   if (log_n) n_inv = fp_inv(fp_from_u64<FrParams>(1ull << log_n));
@@ -376,7 +398,9 @@ int ntt_inverse(eon_ctx* ctx, const Fr* d_src, Fr* d_dst, unsigned log_n, size_t
     p.dif = 1;
     const bool last = (s == np - 1);
     p.src = (const uint4*)(s == 0 ? d_src : work);
+    p.ld_src = (s == 0) ? ld_src : ld_work;
     p.dst = (uint4*)(last ? d_dst : work);
+    p.ld_dst = last ? ld_dst : ld_work;
     if (last) {
       p.out_rev = out_rev ? 1 : 0;
       if (log_n) {

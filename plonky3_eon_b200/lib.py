@@ -57,6 +57,8 @@ _SIGS = {
     "eon_msm_srs_range_dev": (C.c_int, [C.c_void_p, _u64p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t, _u64p]),
     "eon_g1_sum": (C.c_int, [C.c_void_p, _u64p, C.c_size_t, _u64p]),
     "eon_kzg_commit": (C.c_int, [C.c_void_p, _u64p, C.c_uint, C.c_size_t, _u64p, _u64p, C.POINTER(C.c_uint64)]),
+    "eon_kzg_commit_lde": (C.c_int, [C.c_void_p, _u64p, C.c_uint, C.c_size_t, _u64p, _u64p, C.POINTER(C.c_uint64),
+                                     C.c_uint, _u64p, _u64p]),
     "eon_kzg_commit_dev": (C.c_int, [C.c_void_p, _u64p, C.c_uint, C.c_size_t, _u64p, _u64p, C.POINTER(C.c_uint64)]),
     "eon_kzg_commit_coeffs": (C.c_int, [C.c_void_p, _u64p, C.c_size_t, C.c_size_t, _u64p, C.POINTER(C.c_uint64)]),
     "eon_kzg_commit_coeffs_dev": (C.c_int, [C.c_void_p, _u64p, C.c_size_t, C.c_size_t, _u64p, C.POINTER(C.c_uint64)]),
@@ -73,6 +75,8 @@ _SIGS = {
     "eon_phase_reset": (C.c_int, [C.c_void_p]),
     "eon_phase_name": (C.c_char_p, [C.c_int]),
     "eon_phase_count": (C.c_int, []),
+    "eon_bench_copy2d": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_int,
+                                   C.POINTER(C.c_float)]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGS)

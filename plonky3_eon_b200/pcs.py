@@ -73,6 +73,8 @@ class MatrixProverData:
     evals: np.ndarray
     handle: int
     _ctx: object = dc_field(default=None, repr=False)
+    # (log_size, shift, evaluations) produced ahead of time by commit() under an LDE hint
+    lde: tuple = dc_field(default=None, repr=False)
 
     def coeffs(self):
         h, w = self.evals.shape[0], self.evals.shape[1]
@@ -91,6 +93,16 @@ class GpuKzgPcs:
 
     def __init__(self, ctx=None, device=0):
         self.ctx = ctx or default_context(device)
+        self.lde_hint = None
+
+    def with_lde_hint(self, added_bits, shift=field.GENERATOR):
+        """The prover evaluates every committed trace on the quotient coset right after committing it
+        (eon-uni-stark/src/prover.rs:186-187 then :307-322); its size (trace height << added_bits) and
+        shift (Fr::GENERATOR, commit/src/domain.rs:167) are known before the commit.  With the hint,
+        commit() produces that matrix in the same call (eon_kzg_commit_lde: the download hides under the
+        MSM) and get_evaluations_on_domain() hands it out."""
+        self.lde_hint = (int(added_bits), int(shift) % field.P)
+        return self
 
     # -- constructors (pcs.rs:170-203) -------------------------------------------------------
     @classmethod
@@ -137,10 +149,18 @@ class GpuKzgPcs:
             assert h == domain.size(), "evaluation height must match domain size"
             cols = np.zeros((w, 8), dtype=np.uint64)
             handle = C.c_uint64(0)
-            self.ctx.call("eon_kzg_commit", a, domain.log_size, w, field.to_wire(domain.shift),
-                          cols, C.byref(handle))
+            lde = None
+            if self.lde_hint is not None and w > 0:
+                added, lshift = self.lde_hint
+                out = np.empty((h << added, w, 4), dtype=np.uint64)
+                self.ctx.call("eon_kzg_commit_lde", a, domain.log_size, w, field.to_wire(domain.shift), cols,
+                              C.byref(handle), domain.log_size + added, field.to_wire(lshift), out)
+                lde = (domain.log_size + added, lshift, out)
+            else:
+                self.ctx.call("eon_kzg_commit", a, domain.log_size, w, field.to_wire(domain.shift),
+                              cols, C.byref(handle))
             commitments.append(cols)
-            prover.append(MatrixProverData(domain, a, int(handle.value), self.ctx))
+            prover.append(MatrixProverData(domain, a, int(handle.value), self.ctx, lde))
         return commitments, prover
 
     def commit_quotient(self, quotient_domain, quotient_evaluations, num_chunks):
@@ -155,6 +175,8 @@ class GpuKzgPcs:
         m = prover_data[idx]
         if m.domain.shift == domain.shift and m.domain.size() == domain.size():
             return m.evals.copy()
+        if m.lde is not None and m.lde[0] == domain.log_size and m.lde[1] == domain.shift % field.P:
+            return m.lde[2]
         w = m.evals.shape[1]
         out = np.empty((domain.size(), w, 4), dtype=np.uint64)
         self.ctx.call("eon_kzg_evals_on_coset", C.c_uint64(m.handle), domain.log_size,

@@ -371,3 +371,67 @@ def test_mmcs_degree_too_large(ctx):
     mmcs = GpuKzgMmcs.new(3, 7, ctx=ctx)
     with pytest.raises(DegreeTooLarge):
         mmcs.commit([fr.to_wire(list(range(5))).reshape(5, 1, 4)])
+
+
+def test_pipelined_host_entry_points_match_unpipelined(ctx):
+    """eon_kzg_commit / eon_kzg_evals_on_coset move column groups over PCIe under the compute of the
+    previous group for matrices >= 32 MiB.  Same bytes as the single-copy path (EON_NO_PIPELINE), from
+    pinned and from pageable host memory, and spot checks against the oracle's Horner evaluation."""
+    import torch
+    from plonky3_eon_b200 import TwoAdicMultiplicativeCoset
+    log_h, w, alpha = 17, 12, 4242
+    h = 1 << log_h
+    pcs = pcs_new(ctx, h - 1, alpha)
+    evw = fr.random_wire(np.random.default_rng(21), h * w).reshape(h, w, 4)
+    pinned = torch.from_numpy(evw.view(np.int64)).pin_memory().numpy().view(np.uint64)
+    dom = TwoAdicMultiplicativeCoset(1, log_h)
+    qdom = dom.create_disjoint_domain(2 * h)
+    res = {}
+    for name, src in (("plain", evw), ("piped", evw), ("piped_pinned", pinned)):
+        if name == "plain":
+            os.environ["EON_NO_PIPELINE"] = "1"
+        else:
+            os.environ.pop("EON_NO_PIPELINE", None)
+        commit, pd = pcs.commit([(dom, src)])
+        lde = pcs.get_evaluations_on_domain(pd, 0, qdom)
+        res[name] = (commit[0].copy(), pd[0].coeffs(), lde)
+        pd[0].free()
+    os.environ.pop("EON_NO_PIPELINE", None)
+    for name in ("piped", "piped_pinned"):
+        for a, b in zip(res["plain"], res[name]):
+            assert np.array_equal(a, b), name
+    coeffs, lde = res["piped"][1], res["piped"][2]
+    g2 = fr.two_adic_generator(log_h + 1)
+    for c in (0, 5, 11):
+        col = fr.from_wire(coeffs[:, c, :])
+        for j in (0, 3, 2 * h - 1):
+            x = fr.GENERATOR * pow(g2, j, P) % P
+            assert fr.from_wire(lde[j, c])[0] == okzg.eval_poly(col, x), (c, j)
+
+
+@pytest.mark.parametrize("log_h,w", [(3, 2), (10, 5), (17, 12)])
+def test_commit_with_lde_hint_matches_two_calls(ctx, log_h, w):
+    """GpuKzgPcs.with_lde_hint: commit() also produces the quotient-coset evaluations
+    (eon_kzg_commit_lde).  Same commitments, coefficients and LDE bytes as commit() followed by
+    get_evaluations_on_domain(); a non-matching domain still goes through eon_kzg_evals_on_coset."""
+    from plonky3_eon_b200 import GpuKzgPcs, TwoAdicMultiplicativeCoset
+    h, alpha = 1 << log_h, 777
+    pcs = pcs_new(ctx, h - 1, alpha)
+    evw = fr.random_wire(np.random.default_rng(log_h), h * w).reshape(h, w, 4)
+    dom = TwoAdicMultiplicativeCoset(1, log_h)
+    qdom = dom.create_disjoint_domain(2 * h)
+    c0, pd0 = pcs.commit([(dom, evw)])
+    lde0 = pcs.get_evaluations_on_domain(pd0, 0, qdom)
+    hinted = GpuKzgPcs(ctx).with_lde_hint(1)
+    c1, pd1 = hinted.commit([(dom, evw)])
+    assert pd1[0].lde is not None
+    lde1 = hinted.get_evaluations_on_domain(pd1, 0, qdom)
+    assert lde1 is pd1[0].lde[2]
+    assert np.array_equal(c0[0], c1[0])
+    assert np.array_equal(pd0[0].coeffs(), pd1[0].coeffs())
+    assert np.array_equal(lde0, lde1)
+    other = dom.create_disjoint_domain(4 * h)
+    assert np.array_equal(hinted.get_evaluations_on_domain(pd1, 0, other),
+                          pcs.get_evaluations_on_domain(pd0, 0, other))
+    pd0[0].free()
+    pd1[0].free()
