@@ -116,6 +116,19 @@ def synth_trace(seed, rows, cols):
     return out.reshape(rows, cols, 4)
 
 
+def bind_to_gpu_numa_node(local):
+    """Pin this process to the CPU cores next to its GPU before any pinned host buffer is allocated
+    (first touch then places the buffers on that NUMA node): with 8 ranks the host<->device copies of
+    the e2e leg otherwise cross the socket interconnect."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local))
+        return sorted(os.sched_getaffinity(0))
+    except Exception:
+        return None
+
+
 # ------------------------------------------------------------------------------------------------
 def cpu_reference_sample(log_rows, cols, sample_cols, srs=None, repeats=1):
     """The CPU port (oracle/c) on a bounded sample: full iDFT + LDE of the rows x cols trace, MSM on
@@ -198,6 +211,7 @@ def run_eon(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the eon arm has no CPU fallback")
     torch.cuda.set_device(local)
+    cpus = bind_to_gpu_numa_node(local) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     n_gpus = world
@@ -375,7 +389,8 @@ def run_eon(args):
                    "rows": rows, "cols_per_gpu": cols, "srs_points": rows, "msm_window_bits": c_bits, "msm_windows": W,
                    "msm_affine_rounds": rounds,
                    "l2": "inputs (512 MiB trace, 1 GiB LDE, 1 GiB sort workspace) exceed the 126 MB L2",
-                   "parallelism": f"columns x{n_gpus}"},
+                   "parallelism": f"columns x{n_gpus}",
+                   "host_affinity": (f"rank 0 bound to {len(cpus)} cores next to its GPU (NVML)" if cpus else "none")},
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
                 "h2d_bytes_per_step": rows * cols * 32, "d2h_bytes_per_step": 2 * rows * cols * 32 + cols * 64,
                 "call": "eon_kzg_commit_lde (Pcs::commit with an LDE hint; host pinned buffers in and out)",

@@ -166,6 +166,63 @@ EON_HD Fp<PP> fp_sub(const Fp<PP>& a, const Fp<PP>& b) {
   return r;
 }
 
+// ---- lazily reduced arithmetic (NTT butterflies) ---------------------------------------------------
+// Both moduli are < 2^254, so 4p < 2^256: values may float in [0, 2p) or [0, 4p) between butterfly
+// layers and are canonicalised once at the end, saving two of the three conditional corrections per
+// butterfly (Harvey-style).  All of these take and return raw limbs, not canonical Fp values.
+
+// r = a - 2p if a >= 2p else a      (a < 4p  ->  r < 2p)
+template <class PP>
+EON_HD void fp_reduce_2p(u32 r[8], const u32 a[8]) {
+  constexpr u32 C = 0;
+  (void)C;
+  u32 p2[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) p2[i] = (PP::mod(i) << 1) | (i ? (PP::mod(i - 1) >> 31) : 0u);
+  u32 s[8];
+  s[0] = cc::sub_cc(a[0], p2[0]);
+#pragma unroll
+  for (int i = 1; i < 8; i++) s[i] = cc::subc_cc(a[i], p2[i]);
+  u32 borrow = cc::subc(0, 0);
+#pragma unroll
+  for (int i = 0; i < 8; i++) r[i] = borrow ? a[i] : s[i];
+}
+
+// r = a + b  (no reduction; caller guarantees a + b < 2^256)
+EON_HD void fp_add_raw(u32 r[8], const u32 a[8], const u32 b[8]) {
+  r[0] = cc::add_cc(a[0], b[0]);
+#pragma unroll
+  for (int i = 1; i < 7; i++) r[i] = cc::addc_cc(a[i], b[i]);
+  r[7] = cc::addc(a[7], b[7]);
+}
+
+// r = a - b + 2p  (a, b < 2p  ->  0 < r < 4p)
+template <class PP>
+EON_HD void fp_sub_plus_2p(u32 r[8], const u32 a[8], const u32 b[8]) {
+  u32 p2[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) p2[i] = (PP::mod(i) << 1) | (i ? (PP::mod(i - 1) >> 31) : 0u);
+  u32 t[8];
+  t[0] = cc::add_cc(a[0], p2[0]);
+#pragma unroll
+  for (int i = 1; i < 7; i++) t[i] = cc::addc_cc(a[i], p2[i]);
+  t[7] = cc::addc(a[7], p2[7]);
+  r[0] = cc::sub_cc(t[0], b[0]);
+#pragma unroll
+  for (int i = 1; i < 7; i++) r[i] = cc::subc_cc(t[i], b[i]);
+  r[7] = cc::subc(t[7], b[7]);
+}
+
+// canonical value of a < 4p
+template <class PP>
+EON_HD Fp<PP> fp_canon_4p(const u32 a[8]) {
+  u32 t[8];
+  fp_reduce_2p<PP>(t, a);
+  Fp<PP> r;
+  fp_final_sub<PP>(r.v, t);
+  return r;
+}
+
 template <class PP>
 EON_HD Fp<PP> fp_neg(const Fp<PP>& a) {
   // p - a, with 0 -> 0

@@ -15,6 +15,8 @@
 // Inverse transform  = the exact inverse network, layers descending, output bit-reversed:
 //     (u, v) -> (u + v, (u - v) * TW_l[j]^-1),  then one multiply by 1/n on the final store.
 // Both are exact field arithmetic, so results equal the reference's canonical limbs.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace eon {
@@ -33,6 +35,27 @@ __device__ __forceinline__ void fr_to_units(const Fr& a, uint4& lo, uint4& hi) {
 __device__ __forceinline__ Fr fr_ldg(const uint4* p) {
   uint4 lo = __ldg(p), hi = __ldg(p + 1);
   return fr_from_units(lo, hi);
+}
+
+// ---- lazily reduced butterflies (fp.cuh): Fr used as a plain 256-bit container ---------------------
+// forward (DIT) values live in [0, 4r) between layers, inverse (DIF) values in [0, 2r); the last pass
+// of a transform canonicalises (or multiplies by 1/n, which canonicalises too).
+__device__ __forceinline__ Fr lz_red(const Fr& a) { Fr r; fp_reduce_2p<FrParams>(r.v, a.v); return r; }
+__device__ __forceinline__ Fr lz_add(const Fr& a, const Fr& b) { Fr r; fp_add_raw(r.v, a.v, b.v); return r; }
+__device__ __forceinline__ Fr lz_sub(const Fr& a, const Fr& b) { Fr r; fp_sub_plus_2p<FrParams>(r.v, a.v, b.v); return r; }
+// tw canonical (< r), x any 256-bit value -> [0, 2r)
+__device__ __forceinline__ Fr lz_mul(const Fr& tw, const Fr& x) { Fr r; fp_mul_lazy<FrParams>(r.v, tw.v, x.v); return r; }
+// forward butterfly: a in [0, 4r), b in [0, 4r) -> both outputs in [0, 4r)
+__device__ __forceinline__ void bf_dit(Fr& a, Fr& b, const Fr& tw) {
+  Fr x = lz_red(a), t = lz_mul(tw, b);
+  a = lz_add(x, t);
+  b = lz_sub(x, t);
+}
+// inverse butterfly: u, v in [0, 2r) -> both outputs in [0, 2r)
+__device__ __forceinline__ void bf_dif(Fr& u, Fr& v, const Fr& tw) {
+  Fr s = lz_red(lz_add(u, v));
+  v = lz_mul(tw, lz_sub(u, v));
+  u = s;
 }
 
 // ---- twiddle tables ---------------------------------------------------------------------
@@ -109,12 +132,21 @@ struct PassParams {
   int in_rev;   // ... bit-reversed over (log_n - k) bits
   int out_rev;  // destination row = bitrev_{log_n}(position)   (only with l0 == 0)
   int dif;      // 0: forward DIT butterflies, layers ascending; 1: inverse butterflies, descending
-  int scale;    // multiply every output by scale_c
+  int scale;    // last pass of a transform: 1 = multiply every output by scale_c, 2 = canonicalise
   Fr scale_c;
 };
 
 constexpr int NTT_THREADS = 256;
-constexpr u32 NTT_TILE_ELEMS = 2048;  // 64 KiB of shared memory per CTA -> 3 CTAs per SM
+constexpr u32 NTT_TILE_MAX = 2048;  // 64 KiB of shared memory per CTA -> 3 CTAs per SM
+static u32 g_ntt_tile = 0;            // elements per tile in use (EON_NTT_TILE = 1024 | 2048)
+static u32 ntt_tile_elems() {
+  if (!g_ntt_tile) {
+    const char* e = getenv("EON_NTT_TILE");
+    g_ntt_tile = e ? (u32)atoi(e) : NTT_TILE_MAX;
+    if (g_ntt_tile != 1024 && g_ntt_tile != 2048) g_ntt_tile = NTT_TILE_MAX;
+  }
+  return g_ntt_tile;
+}
 
 __device__ __forceinline__ void split_vidx(const PassParams& p, u64 vidx, u64& lo, u32& col) {
   if (p.w_shift >= 0) {
@@ -126,7 +158,8 @@ __device__ __forceinline__ void split_vidx(const PassParams& p, u64 vidx, u64& l
   }
 }
 
-__global__ void __launch_bounds__(NTT_THREADS, 3) k_ntt_pass(const PassParams p) {
+template <int MINB, bool R4>
+__global__ void __launch_bounds__(NTT_THREADS, MINB) k_ntt_pass(const PassParams p) {
   extern __shared__ uint4 smem[];
   const u32 R = 1u << p.r;
   const u32 cv = 1u << p.log_cv;
@@ -171,8 +204,60 @@ __global__ void __launch_bounds__(NTT_THREADS, 3) k_ntt_pass(const PassParams p)
   __syncthreads();
 
   // ---- butterfly layers ----
+  // Two layers at a time on quartets held in registers (half the shared-memory traffic and barriers
+  // of a layer-by-layer sweep), then a single radix-2 layer if r is odd.
+  u32 step = 0;
+  if (R4) {
+    const u32 nq = tile_elems >> 2;
+    for (; step + 1 < p.r; step += 2) {
+      // forward: layers (t, t+1) ascending; inverse: layers (t+1, t) descending
+      const u32 t = p.dif ? (p.r - 2 - step) : step;
+      const u32 tmask = (1u << t) - 1;
+      const u64 twA_base = (1ull << (p.l0 + t)) - 1;
+      const u64 twB_base = (1ull << (p.l0 + t + 1)) - 1;
+      for (u32 idx = tid; idx < nq; idx += NTT_THREADS) {
+        u32 vc = idx & (cv - 1);
+        if (vc >= ncv) continue;
+        u32 b = idx >> p.log_cv;
+        u32 i0 = ((b >> t) << (t + 2)) | (b & tmask);
+        u32 e0 = (i0 << p.log_cv) + vc;
+        u32 st1 = (1u << t) << p.log_cv;
+        u32 e1 = e0 + st1, e2 = e0 + 2 * st1, e3 = e0 + 3 * st1;
+        u64 j = (u64)(b & tmask) << p.l0;
+        if (p.l0) {
+          u64 lo;
+          u32 col;
+          split_vidx(p, v0 + vc, lo, col);
+          j += lo;
+        }
+        Fr twA = fr_ldg(p.tw + (twA_base + j) * 2);
+        Fr twB0 = fr_ldg(p.tw + (twB_base + j) * 2);
+        Fr twB1 = fr_ldg(p.tw + (twB_base + j + (1ull << (p.l0 + t))) * 2);
+        Fr x0 = fr_from_units(s_lo[e0], s_hi[e0]);
+        Fr x1 = fr_from_units(s_lo[e1], s_hi[e1]);
+        Fr x2 = fr_from_units(s_lo[e2], s_hi[e2]);
+        Fr x3 = fr_from_units(s_lo[e3], s_hi[e3]);
+        if (!p.dif) {
+          bf_dit(x0, x1, twA);
+          bf_dit(x2, x3, twA);
+          bf_dit(x0, x2, twB0);
+          bf_dit(x1, x3, twB1);
+        } else {
+          bf_dif(x0, x2, twB0);
+          bf_dif(x1, x3, twB1);
+          bf_dif(x0, x1, twA);
+          bf_dif(x2, x3, twA);
+        }
+        fr_to_units(x0, s_lo[e0], s_hi[e0]);
+        fr_to_units(x1, s_lo[e1], s_hi[e1]);
+        fr_to_units(x2, s_lo[e2], s_hi[e2]);
+        fr_to_units(x3, s_lo[e3], s_hi[e3]);
+      }
+      __syncthreads();
+    }
+  }
   const u32 nbf = tile_elems >> 1;
-  for (u32 step = 0; step < p.r; step++) {
+  for (; step < p.r; step++) {
     const u32 t = p.dif ? (p.r - 1 - step) : step;
     const u32 tmask = (1u << t) - 1;
     const u64 tw_base = (1ull << (p.l0 + t)) - 1;
@@ -193,15 +278,9 @@ __global__ void __launch_bounds__(NTT_THREADS, 3) k_ntt_pass(const PassParams p)
       Fr tw = fr_ldg(p.tw + (tw_base + j) * 2);
       Fr a = fr_from_units(s_lo[e0], s_hi[e0]);
       Fr bb = fr_from_units(s_lo[e1], s_hi[e1]);
-      Fr o0, o1;
-      if (!p.dif) {
-        Fr x = fp_mul(bb, tw);
-        o0 = fp_add(a, x);
-        o1 = fp_sub(a, x);
-      } else {
-        o0 = fp_add(a, bb);
-        o1 = fp_mul(fp_sub(a, bb), tw);
-      }
+      Fr o0 = a, o1 = bb;
+      if (!p.dif) bf_dit(o0, o1, tw);
+      else bf_dif(o0, o1, tw);
       fr_to_units(o0, s_lo[e0], s_hi[e0]);
       fr_to_units(o1, s_lo[e1], s_hi[e1]);
     }
@@ -248,7 +327,8 @@ __global__ void __launch_bounds__(NTT_THREADS, 3) k_ntt_pass(const PassParams p)
         split_vidx(p, vidx, lo, col);
         dst_elem = (((row_base + m) << p.l0) + lo) * p.ld_dst + col;
       }
-      Fr x = fp_mul(fr_from_units(s_lo[e], s_hi[e]), p.scale_c);
+      Fr x = fr_from_units(s_lo[e], s_hi[e]);
+      x = (p.scale == 1) ? fp_mul(p.scale_c, x) : fp_canon_4p<FrParams>(x.v);
       uint4 lo, hi4;
       fr_to_units(x, lo, hi4);
       p.dst[dst_elem * 2] = lo;
@@ -276,7 +356,7 @@ static u32 ilog2_u32(u32 x) {
 // split layers [first, last) into passes (ascending l0)
 static std::vector<PassPlan> plan_passes(u32 first, u32 last, size_t w) {
   std::vector<PassPlan> out;
-  const u32 tile_log = ilog2_u32(NTT_TILE_ELEMS);
+  const u32 tile_log = ilog2_u32(ntt_tile_elems());
   auto rmax_at = [&](u32 l0) {
     u64 V = ((u64)w) << l0;
     return tile_log - log_cv_for(V);
@@ -323,12 +403,33 @@ static int launch_pass(eon_ctx* ctx, PassParams& p, const PassPlan& pl, unsigned
   u64 grid = tiles_hi * p.tiles_v;
   if (grid == 0 || grid > 0x7fffffffull) return fail(ctx, EON_ERR_BAD_ARG, "ntt: grid too large");
   size_t smem = ((size_t)1 << (pl.r + pl.log_cv)) * 32 + 64;
+  static int radix4 = -1;
+  if (radix4 < 0) {
+    const char* e = getenv("EON_NTT_RADIX4");
+    radix4 = e ? atoi(e) : 1;
+  }
+  static int minb = -1;
+  if (minb < 0) {
+    const char* e = getenv("EON_NTT_MINB");
+    minb = e ? atoi(e) : (ntt_tile_elems() == 1024 ? 4 : 3);
+  }
   if (!g_attr_set) {
-    EON_CUDA(ctx, cudaFuncSetAttribute(k_ntt_pass, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)(NTT_TILE_ELEMS * 32 + 64)));
+    const int mx = (int)(NTT_TILE_MAX * 32 + 64);
+    EON_CUDA(ctx, cudaFuncSetAttribute(k_ntt_pass<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+    EON_CUDA(ctx, cudaFuncSetAttribute(k_ntt_pass<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+    EON_CUDA(ctx, cudaFuncSetAttribute(k_ntt_pass<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+    EON_CUDA(ctx, cudaFuncSetAttribute(k_ntt_pass<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+    EON_CUDA(ctx, cudaFuncSetAttribute(k_ntt_pass<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
     g_attr_set = true;
   }
-  k_ntt_pass<<<(unsigned)grid, NTT_THREADS, smem, ctx->stream>>>(p);
+  if (radix4) {
+    if (minb >= 4) k_ntt_pass<4, true><<<(unsigned)grid, NTT_THREADS, smem, ctx->stream>>>(p);
+    else if (minb == 3) k_ntt_pass<3, true><<<(unsigned)grid, NTT_THREADS, smem, ctx->stream>>>(p);
+    else k_ntt_pass<2, true><<<(unsigned)grid, NTT_THREADS, smem, ctx->stream>>>(p);
+  } else {
+    if (minb >= 4) k_ntt_pass<4, false><<<(unsigned)grid, NTT_THREADS, smem, ctx->stream>>>(p);
+    else k_ntt_pass<3, false><<<(unsigned)grid, NTT_THREADS, smem, ctx->stream>>>(p);
+  }
   EON_LAUNCHED(ctx);
   return EON_OK;
 }
@@ -361,6 +462,7 @@ int ntt_forward(eon_ctx* ctx, const Fr* d_src, Fr* d_dst, unsigned log_n, unsign
     }
     p.dst = (uint4*)d_dst;
     p.ld_dst = ld_dst;
+    if (i + 1 == plan.size()) p.scale = 2;  // lazily reduced values leave the transform canonical
     EON_TRY(launch_pass(ctx, p, plan[i], log_n, width));
   }
   phase_end(ctx, PH_NTT_PASSES);
@@ -406,6 +508,8 @@ int ntt_inverse(eon_ctx* ctx, const Fr* d_src, Fr* d_dst, unsigned log_n, size_t
       if (log_n) {
         p.scale = 1;
         p.scale_c = n_inv;
+      } else {
+        p.scale = 2;
       }
     }
     EON_TRY(launch_pass(ctx, p, pl, log_n, width));

@@ -41,6 +41,26 @@ void host_fp_op(int which, int op, const uint32_t* a, const uint32_t* b, uint32_
   }
 }
 
+// Lazily reduced NTT butterflies (fp.cuh): one forward (DIT) and one inverse (DIF) radix-2 butterfly on
+// raw 256-bit limbs, then canonicalised.  a, b may be anywhere in [0, 4r) (dit) / [0, 2r) (dif).
+void host_lazy_butterfly(int dif, const uint32_t* a, const uint32_t* b, const uint32_t* tw, uint32_t* o0, uint32_t* o1) {
+  uint32_t x[8], t[8], s[8], d[8];
+  if (!dif) {
+    fp_reduce_2p<FrParams>(x, a);
+    fp_mul_lazy<FrParams>(t, tw, b);
+    fp_add_raw(s, x, t);
+    fp_sub_plus_2p<FrParams>(d, x, t);
+  } else {
+    uint32_t u[8];
+    fp_add_raw(u, a, b);
+    fp_reduce_2p<FrParams>(s, u);
+    fp_sub_plus_2p<FrParams>(x, a, b);
+    fp_mul_lazy<FrParams>(d, tw, x);
+  }
+  st(o0, fp_canon_4p<FrParams>(s));
+  st(o1, fp_canon_4p<FrParams>(d));
+}
+
 static G1Affine lda(const uint32_t* p) { G1Affine a; memcpy(a.x.v, p, 32); memcpy(a.y.v, p + 8, 32); return a; }
 static void sta(uint32_t* p, const G1Affine& a) { memcpy(p, a.x.v, 32); memcpy(p + 8, a.y.v, 32); }
 

@@ -125,3 +125,31 @@ def test_curve_ops(lib):
         pw = g1.to_wire([pts[2]])
         lib.host_g1_mul_u32(_ptr(pw), k, _ptr(out))
         assert g1.from_wire(out)[0] == g1.mul(pts[2], 2 * k)
+
+
+def test_lazy_ntt_butterflies(lib):
+    """The lazily reduced butterflies of csrc/ntt.cu (inputs anywhere in [0, 4r) forward / [0, 2r)
+    inverse, one conditional correction each) agree with the canonical definitions
+    (a + t b, a - t b) and (u + v, (u - v) t) of dft/src/butterflies.rs:52-63,118-132 after the final
+    canonicalisation, including the extreme representatives."""
+    P = fr.P
+    R = 1 << 256
+    rng = np.random.default_rng(9)
+    rinv = pow(R, -1, P)
+    for dif in (0, 1):
+        top = 2 * P if dif else 4 * P
+        cases = [(0, 0), (top - 1, top - 1), (top - 1, 0), (0, top - 1), (P, P - 1), (2 * P - 1, 1)]
+        cases += [(int.from_bytes(rng.bytes(40), "little") % top, int.from_bytes(rng.bytes(40), "little") % top)
+                  for _ in range(200)]
+        for a, b in cases:
+            tw = int.from_bytes(rng.bytes(40), "little") % P        # canonical Montgomery twiddle
+            A, B, T = from_int(a), from_int(b), from_int(tw)
+            o0 = np.zeros(4, dtype=np.uint64)
+            o1 = np.zeros(4, dtype=np.uint64)
+            lib.host_lazy_butterfly(dif, _ptr(A), _ptr(B), _ptr(T), _ptr(o0), _ptr(o1))
+            if not dif:
+                t = tw * b * rinv % P                               # Montgomery product
+                want = ((a + t) % P, (a - t) % P)
+            else:
+                want = ((a + b) % P, (a - b) * tw * rinv % P)
+            assert (to_int(o0), to_int(o1)) == want, (dif, a, b)
