@@ -237,6 +237,16 @@ def run_eon(args):
     gathered = [torch.empty(cols * 8, dtype=torch.int64, device="cuda") for _ in range(world)] if world > 1 else None
 
     def step_device():
+        # commit + the hinted quotient-coset LDE in one call (the LDE transform runs beside the MSM)
+        h = C.c_uint64(0)
+        ctx.call("eon_kzg_commit_lde_dev", C.c_void_p(d_evals.data_ptr()), log_rows, cols, shift_one, commits,
+                 C.byref(h), log_rows + 1, shift_lde, C.c_void_p(d_lde.data_ptr()))
+        ctx.call("eon_handle_free", h)
+        if world > 1:
+            t = torch.from_numpy(commits.view(np.int64).reshape(-1)).cuda()
+            dist.all_gather(gathered, t)
+
+    def step_device_two_calls():
         h = C.c_uint64(0)
         ctx.call("eon_kzg_commit_dev", C.c_void_p(d_evals.data_ptr()), log_rows, cols, shift_one, commits,
                  C.byref(h))
@@ -298,6 +308,15 @@ def run_eon(args):
     clocks = sampler.stop() if rank == 0 else None
     phases = ctx.phase_ms()          # summed over the timed steps
     commits_device = commits.copy()
+    lde_dev_fused = d_lde.clone() if args.check_e2e else None
+    step_device_two_calls()
+    ctx.phase_reset()
+    ms_dev2 = timed(step_device_two_calls, args.steps)
+    phases_serial = ctx.phase_ms()   # the same kernels run back to back: per-kernel times for the rooflines
+    assert np.array_equal(commits, commits_device), "fused and two-call commitments differ"
+    if lde_dev_fused is not None:
+        assert torch.equal(lde_dev_fused, d_lde), "fused and two-call device LDE differ"
+        del lde_dev_fused
 
     for _ in range(max(1, min(args.warmup, 2))):
         step_e2e()
@@ -318,6 +337,11 @@ def run_eon(args):
         if world > 1:
             dist.destroy_process_group()
         return
+
+    # per-kernel durations for the rooflines come from the two-call timed run, where the same kernels run
+    # back to back on one stream (in the fused step the LDE passes share the GPU with the MSM kernels)
+    phases_overlapped = phases
+    phases = phases_serial
 
     # ---- roofline of the dominant kernel (MSM bucket accumulation: integer pipe) -----------------
     imad_peak = max(ctx.imad_peak_tops(0), ctx.imad_peak_tops(1))       # T IMAD/s, measured now
@@ -385,7 +409,8 @@ def run_eon(args):
         "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u256 (8x32-bit Montgomery limbs, BN254 Fr/Fq)", "data": "synthetic",
         "config": {"workload": f"KZG commit (coset iDFT + {cols} MSM) + blow-up-2 coset LDE, 2^{log_rows} rows x "
-                               f"{cols} cols per GPU (BASELINE configs[1]); column-sharded {cols * n_gpus} cols total",
+                               f"{cols} cols per GPU (BASELINE configs[1]); column-sharded {cols * n_gpus} cols total; "
+                               "one eon_kzg_commit_lde call per step (LDE on a second stream beside the MSM)",
                    "rows": rows, "cols_per_gpu": cols, "srs_points": rows, "msm_window_bits": c_bits, "msm_windows": W,
                    "msm_affine_rounds": rounds,
                    "l2": "inputs (512 MiB trace, 1 GiB LDE, 1 GiB sort workspace) exceed the 126 MB L2",
@@ -400,7 +425,10 @@ def run_eon(args):
                              "get_evaluations_on_domain)"},
         "gpu_launches": launches,
         "clocks": clocks,
+        "two_calls": {"ms_per_step": ms_dev2 / args.steps, "value": units / (ms_dev2 * 1e-3),
+                      "what": "eon_kzg_commit_dev then eon_kzg_evals_on_coset_dev (LDE after the MSM, one stream)"},
         "phase_ms_per_step": {k: v / args.steps for k, v in phases.items()},
+        "phase_ms_per_step_fused": {k: v / args.steps for k, v in phases_overlapped.items()},
         "roofline": roofline, "roofline_ntt": roofline_ntt, "cpu_baseline": cpu,
         "msm_points_per_s": rows * cols / (sum(phases[k] for k in phases if k.startswith("msm_")) / args.steps * 1e-3),
     }
@@ -506,6 +534,65 @@ def run_msm(args):
         dist.destroy_process_group()
 
 
+def run_open(args):
+    """KzgPcs::open (kzg/src/pcs.rs:289-335) of one committed 2^log_rows x cols matrix at the two points the
+    prover uses (zeta, zeta * omega; eon-uni-stark/src/prover.rs:416-431): per step 2 * cols synthetic
+    divisions (k_quot_*) and one batched MSM of 2 * cols columns over the SRS.  Single GPU."""
+    import ctypes as C
+
+    import torch
+
+    import plonky3_eon_b200 as eon
+    from plonky3_eon_b200 import field
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the eon arm has no CPU fallback")
+    torch.cuda.set_device(0)
+    rows, cols, log_rows = 1 << args.log_rows, args.cols, args.log_rows
+    stream = torch.cuda.current_stream()
+    ctx = eon.Context(0, stream=stream.cuda_stream)
+    eon.GpuKzgPcs.new(rows - 1, ALPHA, ctx=ctx)
+    host = synth_trace(1, rows, cols)
+    d_evals = torch.from_numpy(host.view(np.int64)).to("cuda")
+    commits = np.zeros((cols, 8), dtype=np.uint64)
+    h = C.c_uint64(0)
+    ctx.call("eon_kzg_commit_dev", C.c_void_p(d_evals.data_ptr()), log_rows, cols, field.to_wire(1), commits, C.byref(h))
+    zeta = 0x1234567890ABCDEF1234567890ABCDEF1234567890ABCDEF
+    omega = pow(field.two_adic_generator(log_rows), 1, field.P)
+    pts = np.stack([field.to_wire(zeta), field.to_wire(zeta * omega % field.P)])
+    vals = np.zeros((2, cols, 4), dtype=np.uint64)
+    wits = np.zeros((2, cols, 8), dtype=np.uint64)
+
+    def step():
+        ctx.call("eon_kzg_open", h, pts, 2, vals, wits)
+
+    for _ in range(args.warmup):
+        step()
+    ctx.phase_reset()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = ctx.launch_count()
+    e0.record(stream)
+    for _ in range(args.steps):
+        step()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    phases = ctx.phase_ms()
+    line = {
+        "metric": "kzg_open_cols_rows_per_s", "value": rows * cols * args.steps / (ms * 1e-3), "unit": "cols*rows/s",
+        "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u256 (8x32-bit Montgomery limbs, BN254 Fr/Fq)", "data": "synthetic",
+        "config": {"workload": f"KzgPcs::open of a committed 2^{log_rows} x {cols} trace at 2 points (zeta, zeta*omega): "
+                               f"{2 * cols} quotient scans + one MSM of {2 * cols} columns; values and witnesses to the host",
+                   "rows": rows, "cols": cols, "points": 2},
+        "gpu_launches": ctx.launch_count() - launches0,
+        "phase_ms_per_step": {k: v / args.steps for k, v in phases.items()},
+    }
+    print(json.dumps(line), flush=True)
+
+
 def main():
     # keep stdout to the one JSON line: NCCL prints its version banner there at NCCL_DEBUG=VERSION
     if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
@@ -522,8 +609,9 @@ def main():
     ap.add_argument("--warmup-ref", type=int, default=0)
     ap.add_argument("--window-bits", type=int, default=-1,
                     help="MSM window tables: -1 library default, 0 none (plain c=16), 8..20 explicit")
-    ap.add_argument("--workload", default="commit", choices=["commit", "msm"],
-                    help="commit: KZG commit + LDE (the headline metric); msm: standalone MSM (configs[2])")
+    ap.add_argument("--workload", default="commit", choices=["commit", "msm", "open"],
+                    help="commit: KZG commit + LDE (the headline metric); msm: standalone MSM (configs[2]); "
+                         "open: KzgPcs::open at 2 points")
     ap.add_argument("--log-n", type=int, default=24, help="msm workload: log2 of the point count")
     ap.add_argument("--msm-cols", type=int, default=1, help="msm workload: scalar columns sharing the bases")
     args = ap.parse_args()
@@ -531,6 +619,8 @@ def main():
         run_reference(args)
     elif args.workload == "msm":
         run_msm(args)
+    elif args.workload == "open":
+        run_open(args)
     else:
         run_eon(args)
 

@@ -151,9 +151,14 @@ int eon_kzg_commit_dev(eon_ctx* ctx, const uint64_t* d_evals, unsigned log_h, si
 /* commit + the evaluations the prover asks for next, in one call: exactly eon_kzg_commit followed by
  * eon_kzg_evals_on_coset(handle, lde_log_size, lde_shift, h_lde_out) (pcs.rs:223-265 then :267-287, as
  * called back to back by eon-uni-stark/src/prover.rs:186-187,307-322), but the LDE of every column
- * group crosses PCIe while that group's MSM runs, so the 2^(lde_log_size) x width download is hidden.
+ * group crosses PCIe while that group's MSM runs, so the 2^(lde_log_size) x width download is hidden,
+ * and the LDE transform itself runs on a second stream beside the MSM (whose sort and base-gather
+ * phases leave the integer pipe idle).  _dev: device buffers in and out.
  * A Pcs shim built with an "LDE hint" (quotient-domain size and shift, both known before the trace is
  * committed) calls this from commit() and hands the matrix out from get_evaluations_on_domain(). */
+int eon_kzg_commit_lde_dev(eon_ctx* ctx, const uint64_t* d_evals, unsigned log_h, size_t width,
+                           const uint64_t shift[4], uint64_t* h_commit_xy, eon_handle* out_handle,
+                           unsigned lde_log_size, const uint64_t lde_shift[4], uint64_t* d_lde_out);
 int eon_kzg_commit_lde(eon_ctx* ctx, const uint64_t* h_evals, unsigned log_h, size_t width, const uint64_t shift[4],
                        uint64_t* h_commit_xy, eon_handle* out_handle, unsigned lde_log_size,
                        const uint64_t lde_shift[4], uint64_t* h_lde_out);

@@ -97,6 +97,7 @@ void eon_ctx_destroy(eon_ctx* ctx) {
     if (e) cudaEventDestroy(e);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->copy_stream2) cudaStreamDestroy(ctx->copy_stream2);
+  if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
   delete ctx;
 }
 
@@ -446,13 +447,42 @@ static eon_handle handle_new(eon_ctx* ctx, Fr* d_coeffs, size_t rows, unsigned l
   return id;
 }
 
+static int pipe_init(eon_ctx* ctx);
+
+// Coset NTT of a (column group of a) coefficient matrix on the auxiliary compute stream: queued behind
+// what the main stream has done so far (the iDFT that produced the coefficients), it then runs BESIDE
+// whatever the main stream does next — the MSM, whose histogram / sort / base-gather phases leave the
+// integer pipe mostly idle.  ev_pipe[ev_slot] is recorded on the auxiliary stream when it is done.
+static int lde_on_aux(eon_ctx* ctx, const Fr* d_coeffs, Fr* d_lde, unsigned lde_log_size, unsigned added, size_t gw,
+                      const Fr& ls, size_t ld, int ev_slot) {
+  EON_TRY(pipe_init(ctx));
+  EON_CUDA(ctx, cudaEventRecord(ctx->ev_pipe[ev_slot], ctx->stream));
+  EON_CUDA(ctx, cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_pipe[ev_slot], 0));
+  cudaStream_t main_stream = ctx->stream;
+  ctx->stream = ctx->aux_stream;
+  int rc = ntt_forward(ctx, d_coeffs, d_lde, lde_log_size, added, gw, ls, LAYOUT_NATURAL, ld, ld);
+  ctx->stream = main_stream;
+  EON_TRY(rc);
+  EON_CUDA(ctx, cudaEventRecord(ctx->ev_pipe[ev_slot], ctx->aux_stream));
+  return EON_OK;
+}
+
 static int kzg_commit_locked(eon_ctx* ctx, const uint64_t* d_evals, unsigned log_h, size_t width,
-                             const uint64_t shift[4], uint64_t* h_commit_xy, eon_handle* out_handle) {
+                             const uint64_t shift[4], uint64_t* h_commit_xy, eon_handle* out_handle,
+                             unsigned lde_log_size = 0, const uint64_t* lde_shift = nullptr, Fr* d_lde = nullptr) {
   if (!out_handle) return fail(ctx, EON_ERR_BAD_ARG, "null handle pointer");
   *out_handle = 0;
   EON_TRY(check_dims(ctx, log_h, width));
   Fr s;
   EON_TRY(check_shift(ctx, shift, &s));
+  const bool want_lde = lde_log_size != 0 && width != 0;
+  Fr ls = Fr::one();
+  if (want_lde) {
+    if (lde_log_size < log_h) return fail(ctx, EON_ERR_BAD_ARG, "LDE domain smaller than the trace domain");
+    EON_TRY(check_dims(ctx, lde_log_size, width));
+    EON_TRY(check_shift(ctx, lde_shift, &ls));
+    if (!d_lde) return fail(ctx, EON_ERR_BAD_ARG, "null LDE output");
+  }
   const size_t h = (size_t)1 << log_h;
   if (h > ctx->srs_n) {  // ensure_supported(height - 1), kzg/src/pcs.rs:238-240
     char b[128];
@@ -464,8 +494,12 @@ static int kzg_commit_locked(eon_ctx* ctx, const uint64_t* d_evals, unsigned log
   size_t cap = 0;
   EON_TRY(coeff_buffer_get(ctx, mat_bytes(log_h, width) + 32, &d_coeffs, &cap));
   int rc = ntt_inverse(ctx, (const Fr*)d_evals, d_coeffs, log_h, width, s, LAYOUT_NATURAL);
+  if (rc == EON_OK && want_lde) rc = lde_on_aux(ctx, d_coeffs, d_lde, lde_log_size, lde_log_size - log_h, width, ls, width, 19);
   if (rc == EON_OK) rc = msm_to_host(ctx, ctx->d_srs, d_coeffs, h, width, width, h_commit_xy);
+  if (rc == EON_OK && want_lde)  // the call returns with the LDE complete as well
+    if (cudaStreamSynchronize(ctx->aux_stream) != cudaSuccess) rc = fail(ctx, EON_ERR_CUDA, "LDE stream failed");
   if (rc != EON_OK) {
+    if (ctx->aux_stream) cudaStreamSynchronize(ctx->aux_stream);
     cudaFree(d_coeffs);
     return rc;
   }
@@ -536,6 +570,16 @@ int eon_kzg_commit_dev(eon_ctx* ctx, const uint64_t* d_evals, unsigned log_h, si
   return kzg_commit_locked(ctx, d_evals, log_h, width, shift, h_commit_xy, out_handle);
 }
 
+int eon_kzg_commit_lde_dev(eon_ctx* ctx, const uint64_t* d_evals, unsigned log_h, size_t width, const uint64_t shift[4],
+                           uint64_t* h_commit_xy, eon_handle* out_handle, unsigned lde_log_size,
+                           const uint64_t lde_shift[4], uint64_t* d_lde_out) {
+  if (!ctx || lde_log_size == 0) return EON_ERR_BAD_ARG;
+  Lock lk(ctx);
+  EON_TRY(set_device(ctx));
+  return kzg_commit_locked(ctx, d_evals, log_h, width, shift, h_commit_xy, out_handle, lde_log_size, lde_shift,
+                           (Fr*)d_lde_out);
+}
+
 // Column groups for the PCIe pipelining of the host-buffer entry points.  Every column's transform
 // and MSM is independent (kzg/src/pcs.rs:244-249), so group g+1 can cross PCIe while group g computes.
 // Strided copies of >= 128-byte row pieces run at >= 85 % of the contiguous rate (tools/copy2d_probe.py).
@@ -554,8 +598,10 @@ static std::vector<std::pair<size_t, size_t>> column_groups(size_t width, size_t
 }
 
 static int pipe_init(eon_ctx* ctx) {
+  if (ctx->copy_stream && ctx->copy_stream2 && ctx->aux_stream && ctx->ev_pipe[19]) return EON_OK;
   if (!ctx->copy_stream) EON_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
   if (!ctx->copy_stream2) EON_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream2, cudaStreamNonBlocking));
+  if (!ctx->aux_stream) EON_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking));
   for (auto& e : ctx->ev_pipe)
     if (!e) EON_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   return EON_OK;
@@ -627,11 +673,9 @@ static int kzg_commit_host(eon_ctx* ctx, const uint64_t* h_evals, unsigned log_h
     if (rc == EON_OK && want_lde) {
       // the group's LDE goes out over PCIe (second copy stream: downloads run beside the uploads)
       // while its MSM, the long part, runs
-      rc = ntt_forward(ctx, d_coeffs + c0, (Fr*)d_lde + c0, lde_log_size, lde_log_size - log_h, gw, ls, LAYOUT_NATURAL,
-                       width, width);
+      rc = lde_on_aux(ctx, d_coeffs + c0, (Fr*)d_lde + c0, lde_log_size, lde_log_size - log_h, gw, ls, width, 8 + (int)g);
       if (rc == EON_OK) {
-        cudaError_t e = cudaEventRecord(ctx->ev_pipe[8 + g], ctx->stream);
-        if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->copy_stream2, ctx->ev_pipe[8 + g], 0);
+        cudaError_t e = cudaStreamWaitEvent(ctx->copy_stream2, ctx->ev_pipe[8 + g], 0);
         if (e == cudaSuccess)
           e = cudaMemcpy2DAsync((Fr*)h_lde_out + c0, pitch, (const Fr*)d_lde + c0, pitch, gw * sizeof(Fr), lde_rows,
                                 cudaMemcpyDeviceToHost, ctx->copy_stream2);
@@ -648,6 +692,7 @@ static int kzg_commit_host(eon_ctx* ctx, const uint64_t* h_evals, unsigned log_h
   }
   if (rc != EON_OK) {
     cudaStreamSynchronize(ctx->copy_stream);
+    if (ctx->aux_stream) cudaStreamSynchronize(ctx->aux_stream);
     cudaStreamSynchronize(ctx->copy_stream2);
     cudaStreamSynchronize(ctx->stream);
     cudaFree(d_coeffs);

@@ -113,9 +113,11 @@ struct eon_ctx {
   // second stream + events: the host-buffer entry points move column groups over PCIe while the
   // previous group computes (created on first use)
   cudaStream_t copy_stream = nullptr;
-  cudaStream_t copy_stream2 = nullptr;  // opposite PCIe direction (downloads while uploads are in flight)
-  cudaEvent_t ev_pipe[12] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
-                             nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaStream_t copy_stream2 = nullptr;
+  cudaStream_t aux_stream = nullptr;    // second compute stream: the hinted LDE runs beside the MSM, whose
+                                        // sort / gather phases leave the integer pipe idle  // opposite PCIe direction (downloads while uploads are in flight)
+  cudaEvent_t ev_pipe[20] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
+                             nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 
   std::map<eon_handle, eon::ProverMatrix> handles;
   eon_handle next_handle = 1;

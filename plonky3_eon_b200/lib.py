@@ -59,6 +59,8 @@ _SIGS = {
     "eon_kzg_commit": (C.c_int, [C.c_void_p, _u64p, C.c_uint, C.c_size_t, _u64p, _u64p, C.POINTER(C.c_uint64)]),
     "eon_kzg_commit_lde": (C.c_int, [C.c_void_p, _u64p, C.c_uint, C.c_size_t, _u64p, _u64p, C.POINTER(C.c_uint64),
                                      C.c_uint, _u64p, _u64p]),
+    "eon_kzg_commit_lde_dev": (C.c_int, [C.c_void_p, _u64p, C.c_uint, C.c_size_t, _u64p, _u64p, C.POINTER(C.c_uint64),
+                                         C.c_uint, _u64p, _u64p]),
     "eon_kzg_commit_dev": (C.c_int, [C.c_void_p, _u64p, C.c_uint, C.c_size_t, _u64p, _u64p, C.POINTER(C.c_uint64)]),
     "eon_kzg_commit_coeffs": (C.c_int, [C.c_void_p, _u64p, C.c_size_t, C.c_size_t, _u64p, C.POINTER(C.c_uint64)]),
     "eon_kzg_commit_coeffs_dev": (C.c_int, [C.c_void_p, _u64p, C.c_size_t, C.c_size_t, _u64p, C.POINTER(C.c_uint64)]),

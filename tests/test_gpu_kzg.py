@@ -435,3 +435,39 @@ def test_commit_with_lde_hint_matches_two_calls(ctx, log_h, w):
                           pcs.get_evaluations_on_domain(pd0, 0, other))
     pd0[0].free()
     pd1[0].free()
+
+
+@pytest.mark.parametrize("log_h,w", [(0, 1), (4, 3), (15, 6)])
+def test_commit_lde_dev_matches_two_calls(ctx, log_h, w):
+    """eon_kzg_commit_lde_dev (device buffers; the LDE transform runs on a second stream beside the MSM)
+    returns the same commitments, coefficients and LDE bytes as eon_kzg_commit_dev followed by
+    eon_kzg_evals_on_coset_dev."""
+    import ctypes as C
+    from plonky3_eon_b200 import field
+    h, alpha = 1 << log_h, 31
+    pcs_new(ctx, max(h - 1, 1), alpha)
+    evw = fr.random_wire(np.random.default_rng(log_h + 40), h * w).reshape(h, w, 4)
+    d_ev = ctx.dev_alloc(evw.nbytes)
+    ctx.h2d(d_ev, evw)
+    lde_bytes = 2 * evw.nbytes
+    d_l1, d_l2 = ctx.dev_alloc(lde_bytes), ctx.dev_alloc(lde_bytes)
+    one, five = field.to_wire(1), field.to_wire(5)
+    c1, c2 = np.zeros((w, 8), np.uint64), np.zeros((w, 8), np.uint64)
+    h1, h2 = C.c_uint64(0), C.c_uint64(0)
+    ctx.call("eon_kzg_commit_dev", C.c_void_p(d_ev), log_h, w, one, c1, C.byref(h1))
+    ctx.call("eon_kzg_evals_on_coset_dev", h1, log_h + 1, five, C.c_void_p(d_l1))
+    ctx.call("eon_kzg_commit_lde_dev", C.c_void_p(d_ev), log_h, w, one, c2, C.byref(h2), log_h + 1, five, C.c_void_p(d_l2))
+    l1 = np.empty((2 * h, w, 4), np.uint64)
+    l2 = np.empty((2 * h, w, 4), np.uint64)
+    ctx.d2h(l1, d_l1)
+    ctx.d2h(l2, d_l2)
+    k1 = np.empty((h, w, 4), np.uint64)
+    k2 = np.empty((h, w, 4), np.uint64)
+    ctx.call("eon_kzg_read_coeffs", h1, k1)
+    ctx.call("eon_kzg_read_coeffs", h2, k2)
+    assert np.array_equal(c1, c2) and np.array_equal(l1, l2) and np.array_equal(k1, k2)
+    assert odft.mat_from_wire(l2) == odft.coset_lde_batch(odft.mat_from_wire(evw), 1, fr.GENERATOR) if log_h <= 4 else True
+    for p in (d_ev, d_l1, d_l2):
+        ctx.dev_free(p)
+    ctx.call("eon_handle_free", h1)
+    ctx.call("eon_handle_free", h2)
