@@ -370,9 +370,22 @@ def run_eon(args):
         bwd_ms = phases["msm_tree_bwd"] / args.steps
         ops = pairs * 5 * IMAD_PER_MODMUL
         achieved = ops / (bwd_ms * 1e-3) / 1e12
+        # HBM view of the same kernel family: per pair 2 points in (128 B), prefix product in (32 B), sum out (64 B)
+        alg_bytes = pairs * 224
+        # ncu --set full, 2^20 x 16 (profiles/r01h_ncu_full_summary.txt): the round-0 launch moves 40.25 GB read +
+        # 8.28 GB written for 125.8 M pairs = 386 B per pair against 224 algorithmic (DRAM fetches 128 B per random
+        # 64-byte base gather); the dense rounds move 15.8 + 6.2 GB for 94.4 M pairs = 233 B per pair
+        traffic = None
+        if log_rows == 20 and cols == 16 and rounds == 3:
+            traffic = 40.25e9 + 8.28e9 + 15.83e9 + 6.17e9
         roofline = dict(common, kernel=f"k_tree_bwd x{rounds} (batched-affine pair additions, 5 modmul per pair)",
                         achieved=achieved, frac=achieved / imad_peak, algorithmic_ops_per_launch=ops,
-                        launch_ms=bwd_ms,
+                        launch_ms=bwd_ms, traffic=traffic,
+                        traffic_source="ncu --set full capture of these launches (profiles/r01h_ncu_full_summary.txt), "
+                                       "sum over the 3 rounds of one step" if traffic else None,
+                        hbm_view={"bound": "hbm", "algorithmic_bytes": alg_bytes,
+                                  "achieved": alg_bytes / (bwd_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                                  "frac": alg_bytes / (bwd_ms * 1e-3) / 1e9 / hbm_peak},
                         accumulate_phase={"ms": acc_ms, "tree_fwd_ms": phases["msm_tree_fwd"] / args.steps,
                                           "tree_inv_ms": phases["msm_tree_inv"] / args.steps,
                                           "tree_bwd_ms": bwd_ms, "finish_ms": phases["msm_finish"] / args.steps,
@@ -387,7 +400,9 @@ def run_eon(args):
     roofline_ntt = {
         "kernel": "k_ntt_pass (3 HBM passes for the 2^20 iDFT + 3 for the 2^21 LDE)",
         "bound": "hbm", "achieved": ntt_bytes / (ntt_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-        "frac": ntt_bytes / (ntt_ms * 1e-3) / 1e9 / hbm_peak, "traffic": None, "launch_ms_total": ntt_ms,
+        "frac": ntt_bytes / (ntt_ms * 1e-3) / 1e9 / hbm_peak,
+        # ncu --set full (profiles/r01h_ncu_full_summary.txt): 1.05-1.07 GB per 2^20 pass, 1.57-2.1 GB per 2^21 pass
+        "traffic": (3.20e9 + 5.76e9) if (log_rows == 20 and cols == 16) else None, "launch_ms_total": ntt_ms,
         "peak_source": peak_src,
         "imad_frac": ((rows // 2) * log_rows * cols + rows * log_rows * cols + rows * cols) * IMAD_PER_MODMUL
         / (ntt_ms * 1e-3) / 1e12 / imad_peak,
