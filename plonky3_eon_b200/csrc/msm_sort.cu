@@ -63,6 +63,7 @@ __global__ void k_sort_init(const u32* __restrict__ starts, u32 NB, u32 nbins, u
 // Shared memory: cnt[tile_bins] | off[tile_bins + 1] | gbase[tile_bins] | stage_pay[tile * W] u32 |
 // stage_key[tile * W] u16.  The tile's entries are grouped by bin in shared memory first, so the copy
 // to the temporary array is coalesced (consecutive threads -> consecutive slots of a run).
+template <bool MERGED>
 __global__ void __launch_bounds__(SORT_THREADS)
 k_sort_coarse(const Fr* __restrict__ scalars, size_t n, size_t ld, u32 ncols, MsmShape sh, u32 nbins, u32 fb, u32 tile,
               u32* __restrict__ region_cursor, u32* __restrict__ tmp_pay, unsigned short* __restrict__ tmp_key) {
@@ -100,7 +101,7 @@ k_sort_coarse(const Fr* __restrict__ scalars, size_t n, size_t ld, u32 ncols, Ms
   for (int q = 0; q < 4; q++) {
     for_each_digit_canonical(kk[q], sh, [&](u32 w, int d) {
       u32 b = (u32)(d < 0 ? -d : d) - 1;
-      atomicAdd(&s_cnt[(sh.merged ? 0 : w) * nbins + (b >> fb)], 1u);
+      atomicAdd(&s_cnt[(MERGED ? 0 : w * nbins) + (b >> fb)], 1u);
     });
   }
   __syncthreads();
@@ -134,13 +135,14 @@ k_sort_coarse(const Fr* __restrict__ scalars, size_t n, size_t ld, u32 ncols, Ms
   // group the entries by bin in shared memory
 #pragma unroll
   for (int q = 0; q < 4; q++) {
-    const size_t i = i0 + tid + q * SORT_THREADS;
+    const u32 i = (u32)(i0 + tid + q * SORT_THREADS);
+    const u32 base0 = MERGED ? (u32)sh.base_first + i : i;  // entry = base index: + w * tab_stride with tables
+    const u32 stride = MERGED ? (u32)sh.tab_stride : 0u;
     for_each_digit_canonical(kk[q], sh, [&](u32 w, int d) {
       u32 b = (u32)(d < 0 ? -d : d) - 1;
-      u32 bin = (sh.merged ? 0 : w) * nbins + (b >> fb);
+      u32 bin = (MERGED ? 0 : w * nbins) + (b >> fb);
       u32 slot = s_off[bin] + smem_rank(s_cnt, bin);
-      u32 base = sh.merged ? (u32)(w * sh.tab_stride + sh.base_first + i) : (u32)i;
-      s_pay[slot] = base | (d < 0 ? SIGN_BIT : 0u);
+      s_pay[slot] = (base0 + w * stride) | ((u32)d & SIGN_BIT);
       s_key[slot] = (unsigned short)(b & fmask);
     });
   }
@@ -149,7 +151,7 @@ k_sort_coarse(const Fr* __restrict__ scalars, size_t n, size_t ld, u32 ncols, Ms
   for (u32 bin = wid; bin < tile_bins; bin += SORT_THREADS / 32) {
     const u32 o0 = s_off[bin], o1 = s_off[bin + 1];
     if (o0 == o1) continue;
-    const size_t dst = (seg0 + bin / nbins) * sh.seg_cap + s_gbase[bin];
+    const size_t dst = (seg0 + (MERGED ? 0 : bin / nbins)) * sh.seg_cap + s_gbase[bin];
     for (u32 idx = o0 + lane; idx < o1; idx += 32) {
       tmp_pay[dst + (idx - o0)] = s_pay[idx];
       tmp_key[dst + (idx - o0)] = s_key[idx];
@@ -220,7 +222,9 @@ int msm_sort_entries(eon_ctx* ctx, const Fr* d_scalars, size_t n, size_t ncols, 
   const size_t tiles = (n + tile - 1) / tile;
   if (tiles * ncols > 0x7fffffffull || total_bins > 0x7fffffffull) return 1;
   if (!g_sort_attr_set) {
-    EON_CUDA(ctx, cudaFuncSetAttribute(k_sort_coarse, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    EON_CUDA(ctx, cudaFuncSetAttribute(k_sort_coarse<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)(SORT_COARSE_SMEM + 16)));
+    EON_CUDA(ctx, cudaFuncSetAttribute(k_sort_coarse<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)(SORT_COARSE_SMEM + 16)));
     EON_CUDA(ctx, cudaFuncSetAttribute(k_sort_fine, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)(((size_t)(1u << 12) + SORT_WIN_CAP) * sizeof(u32))));
@@ -234,8 +238,12 @@ int msm_sort_entries(eon_ctx* ctx, const Fr* d_scalars, size_t n, size_t ncols, 
   k_sort_init<<<(unsigned)((total_bins + 255) / 256), 256, 0, st>>>(d_starts, sh.NB, nbins, fb, total_bins,
                                                                     (u32*)p_reg);
   EON_LAUNCHED(ctx);
-  k_sort_coarse<<<(unsigned)(tiles * ncols), SORT_THREADS, smem_coarse, st>>>(
-      d_scalars, n, ld, (u32)ncols, sh, nbins, fb, tile, (u32*)p_reg, (u32*)p_pay, (unsigned short*)p_key);
+  if (sh.merged)
+    k_sort_coarse<true><<<(unsigned)(tiles * ncols), SORT_THREADS, smem_coarse, st>>>(
+        d_scalars, n, ld, (u32)ncols, sh, nbins, fb, tile, (u32*)p_reg, (u32*)p_pay, (unsigned short*)p_key);
+  else
+    k_sort_coarse<false><<<(unsigned)(tiles * ncols), SORT_THREADS, smem_coarse, st>>>(
+        d_scalars, n, ld, (u32)ncols, sh, nbins, fb, tile, (u32*)p_reg, (u32*)p_pay, (unsigned short*)p_key);
   EON_LAUNCHED(ctx);
   k_sort_fine<<<(unsigned)total_bins, SORT_FINE_THREADS, smem_fine, st>>>(
       (const u32*)p_pay, (const unsigned short*)p_key, (const u32*)p_reg, d_starts, d_seg_total, sh.NB, nbins, fb,

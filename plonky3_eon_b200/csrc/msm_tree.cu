@@ -225,8 +225,8 @@ static int tree_b() {
   static int b = 0;
   if (!b) {
     const char* e = getenv("EON_TREE_B");
-    b = e ? atoi(e) : 16;
-    if (b != 8 && b != 16 && b != 32) b = 16;
+    b = e ? atoi(e) : 32;
+    if (b != 8 && b != 16 && b != 32) b = 32;
   }
   return b;
 }
