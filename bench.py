@@ -230,9 +230,13 @@ def run_eon(args):
     host_pin = torch.from_numpy(host_np.view(np.int64)).pin_memory()
     host_pin_np = host_pin.numpy().view(np.uint64)
     d_evals = host_pin.to("cuda", non_blocking=False)
-    d_lde = torch.empty((2 * rows, cols, 4), dtype=torch.int64, device="cuda")
-    lde_pin = torch.empty((2 * rows, cols, 4), dtype=torch.int64).pin_memory()
-    lde_pin_np = lde_pin.numpy().view(np.uint64)
+    ab = args.added_bits                                         # blow-up 2^ab (1 = configs[1], 2 = configs[4])
+    d_lde = torch.empty((rows << ab, cols, 4), dtype=torch.int64, device="cuda")
+    if args.no_e2e:
+        lde_pin = lde_pin_np = None
+    else:
+        lde_pin = torch.empty((rows << ab, cols, 4), dtype=torch.int64).pin_memory()
+        lde_pin_np = lde_pin.numpy().view(np.uint64)
     commits = np.zeros((cols, 8), dtype=np.uint64)
     gathered = [torch.empty(cols * 8, dtype=torch.int64, device="cuda") for _ in range(world)] if world > 1 else None
 
@@ -240,7 +244,7 @@ def run_eon(args):
         # commit + the hinted quotient-coset LDE in one call (the LDE transform runs beside the MSM)
         h = C.c_uint64(0)
         ctx.call("eon_kzg_commit_lde_dev", C.c_void_p(d_evals.data_ptr()), log_rows, cols, shift_one, commits,
-                 C.byref(h), log_rows + 1, shift_lde, C.c_void_p(d_lde.data_ptr()))
+                 C.byref(h), log_rows + ab, shift_lde, C.c_void_p(d_lde.data_ptr()))
         ctx.call("eon_handle_free", h)
         if world > 1:
             t = torch.from_numpy(commits.view(np.int64).reshape(-1)).cuda()
@@ -250,7 +254,7 @@ def run_eon(args):
         h = C.c_uint64(0)
         ctx.call("eon_kzg_commit_dev", C.c_void_p(d_evals.data_ptr()), log_rows, cols, shift_one, commits,
                  C.byref(h))
-        ctx.call("eon_kzg_evals_on_coset_dev", h, log_rows + 1, shift_lde, C.c_void_p(d_lde.data_ptr()))
+        ctx.call("eon_kzg_evals_on_coset_dev", h, log_rows + ab, shift_lde, C.c_void_p(d_lde.data_ptr()))
         ctx.call("eon_handle_free", h)
         if world > 1:
             t = torch.from_numpy(commits.view(np.int64).reshape(-1)).cuda()
@@ -260,7 +264,7 @@ def run_eon(args):
         # what a Pcs shim with an LDE hint calls from commit() (GpuKzgPcs.with_lde_hint): commit + the
         # quotient-coset evaluations in one call, column groups pipelined over PCIe
         h = C.c_uint64(0)
-        ctx.call("eon_kzg_commit_lde", host_pin_np, log_rows, cols, shift_one, commits, C.byref(h), log_rows + 1,
+        ctx.call("eon_kzg_commit_lde", host_pin_np, log_rows, cols, shift_one, commits, C.byref(h), log_rows + ab,
                  shift_lde, lde_pin_np)
         ctx.call("eon_handle_free", h)
         if world > 1:
@@ -271,7 +275,7 @@ def run_eon(args):
         # the unhinted trait sequence: Pcs::commit, then Pcs::get_evaluations_on_domain
         h = C.c_uint64(0)
         ctx.call("eon_kzg_commit", host_pin_np, log_rows, cols, shift_one, commits, C.byref(h))
-        ctx.call("eon_kzg_evals_on_coset", h, log_rows + 1, shift_lde, lde_pin_np)
+        ctx.call("eon_kzg_evals_on_coset", h, log_rows + ab, shift_lde, lde_pin_np)
         ctx.call("eon_handle_free", h)
         if world > 1:
             t = torch.from_numpy(commits.view(np.int64).reshape(-1)).cuda()
@@ -318,20 +322,23 @@ def run_eon(args):
         assert torch.equal(lde_dev_fused, d_lde), "fused and two-call device LDE differ"
         del lde_dev_fused
 
-    for _ in range(max(1, min(args.warmup, 2))):
-        step_e2e()
-    ms_e2e = timed(step_e2e, args.steps)
-    assert np.array_equal(commits, commits_device), "e2e and device-resident commitments differ"
-    lde_fused = lde_pin_np.copy() if rank == 0 and args.check_e2e else None
-    step_e2e_two_calls()
-    ms_e2e2 = timed(step_e2e_two_calls, args.steps)
-    assert np.array_equal(commits, commits_device), "two-call e2e and device-resident commitments differ"
-    if lde_fused is not None:
-        assert np.array_equal(lde_fused, lde_pin_np), "fused and two-call LDE differ"
+    if args.no_e2e:
+        ms_e2e = ms_e2e2 = None
+    else:
+        for _ in range(max(1, min(args.warmup, 2))):
+            step_e2e()
+        ms_e2e = timed(step_e2e, args.steps)
+        assert np.array_equal(commits, commits_device), "e2e and device-resident commitments differ"
+        lde_fused = lde_pin_np.copy() if rank == 0 and args.check_e2e else None
+        step_e2e_two_calls()
+        ms_e2e2 = timed(step_e2e_two_calls, args.steps)
+        assert np.array_equal(commits, commits_device), "two-call e2e and device-resident commitments differ"
+        if lde_fused is not None:
+            assert np.array_equal(lde_fused, lde_pin_np), "fused and two-call LDE differ"
 
     units = rows * cols * n_gpus * args.steps
     value = units / (ms_dev * 1e-3)
-    e2e_value = units / (ms_e2e * 1e-3)
+    e2e_value = units / (ms_e2e * 1e-3) if ms_e2e else None
 
     if rank != 0:
         if world > 1:
@@ -354,7 +361,7 @@ def run_eon(args):
     acc_ms = phases["msm_accumulate"] / args.steps
     hbm_peak, peak_src = peaks()
     ntt_ms = phases["ntt_passes"] / args.steps
-    ntt_bytes = 3 * 2 * (rows * cols * 32) + 3 * 2 * (2 * rows * cols * 32) - (rows * cols * 32)
+    ntt_bytes = 3 * 2 * (rows * cols * 32) + 3 * 2 * ((rows << ab) * cols * 32) - ((rows << ab) - rows) * cols * 32
     common = {
         "bound": "imad", "peak": imad_peak, "unit": "TIMAD/s", "traffic": None,
         "peak_source": "eon_bench_imad_peak in this run (mad.lo/mad.hi.u32, 16 independent chains/thread)",
@@ -404,7 +411,7 @@ def run_eon(args):
         # ncu --set full (profiles/r01h_ncu_full_summary.txt): 1.05-1.07 GB per 2^20 pass, 1.57-2.1 GB per 2^21 pass
         "traffic": (3.20e9 + 5.76e9) if (log_rows == 20 and cols == 16) else None, "launch_ms_total": ntt_ms,
         "peak_source": peak_src,
-        "imad_frac": ((rows // 2) * log_rows * cols + rows * log_rows * cols + rows * cols) * IMAD_PER_MODMUL
+        "imad_frac": ((rows // 2) * log_rows * cols + ((rows << ab) // 2) * log_rows * cols + rows * cols) * IMAD_PER_MODMUL
         / (ntt_ms * 1e-3) / 1e12 / imad_peak,
     }
 
@@ -423,7 +430,7 @@ def run_eon(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u256 (8x32-bit Montgomery limbs, BN254 Fr/Fq)", "data": "synthetic",
-        "config": {"workload": f"KZG commit (coset iDFT + {cols} MSM) + blow-up-2 coset LDE, 2^{log_rows} rows x "
+        "config": {"workload": f"KZG commit (coset iDFT + {cols} MSM) + blow-up-{1 << ab} coset LDE, 2^{log_rows} rows x "
                                f"{cols} cols per GPU (BASELINE configs[1]); column-sharded {cols * n_gpus} cols total; "
                                "one eon_kzg_commit_lde call per step (LDE on a second stream beside the MSM)",
                    "rows": rows, "cols_per_gpu": cols, "srs_points": rows, "msm_window_bits": c_bits, "msm_windows": W,
@@ -431,8 +438,8 @@ def run_eon(args):
                    "l2": "inputs (512 MiB trace, 1 GiB LDE, 1 GiB sort workspace) exceed the 126 MB L2",
                    "parallelism": f"columns x{n_gpus}",
                    "host_affinity": (f"rank 0 bound to {len(cpus)} cores next to its GPU (NVML)" if cpus else "none")},
-        "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
-                "h2d_bytes_per_step": rows * cols * 32, "d2h_bytes_per_step": 2 * rows * cols * 32 + cols * 64,
+        "e2e": None if args.no_e2e else {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
+                "h2d_bytes_per_step": rows * cols * 32, "d2h_bytes_per_step": (rows << ab) * cols * 32 + cols * 64,
                 "call": "eon_kzg_commit_lde (Pcs::commit with an LDE hint; host pinned buffers in and out)",
                 "two_calls_ms_per_step": ms_e2e2 / args.steps,
                 "two_calls_value": units / (ms_e2e2 * 1e-3),
@@ -620,6 +627,8 @@ def main():
     ap.add_argument("--log-rows", type=int, default=20)
     ap.add_argument("--cols", type=int, default=16)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--added-bits", type=int, default=1, help="log2 of the LDE blow-up (1: configs[1]; 2: configs[4])")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (large shapes: pinned LDE buffer)")
     ap.add_argument("--check-e2e", action="store_true", help="compare the fused and two-call LDE bytes (1 GiB copy)")
     ap.add_argument("--warmup-ref", type=int, default=0)
     ap.add_argument("--window-bits", type=int, default=-1,
