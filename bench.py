@@ -615,6 +615,68 @@ def run_open(args):
     print(json.dumps(line), flush=True)
 
 
+def run_prove_pcs(args):
+    """BASELINE configs[3], PCS side only: the reference has no BN254 Poseidon2 AIR, so this
+    replays the PCS call sequence of eon_uni_stark::prove (eon-uni-stark/src/prover.rs:186-187, 307-322,
+    371-372, 416-442) on a random 2^log_rows x cols trace through the host mirror of the Pcs trait:
+    commit(trace) -> get_evaluations_on_domain(quotient coset) -> commit_quotient(2 chunks) ->
+    open(trace at zeta and zeta*omega, chunks at zeta).  Host buffers throughout; wall-clock per phase."""
+    import torch
+
+    import plonky3_eon_b200 as eon
+    from plonky3_eon_b200 import field
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the eon arm has no CPU fallback")
+    rows, cols, log_rows = 1 << args.log_rows, args.cols, args.log_rows
+    ctx = eon.Context(0)
+    pcs = eon.GpuKzgPcs.new(rows - 1, ALPHA, ctx=ctx).with_lde_hint(1)
+    trace = eon.pinned_empty((rows, cols, 4))        # the prover keeps its matrices in page-locked memory
+    trace[:] = synth_trace(1, rows, cols)
+    quotient = eon.pinned_empty((2 * rows, 1, 4))    # stands in for quotient_values (CPU side in the reference)
+    quotient[:] = synth_trace(2, 2 * rows, 1)
+    dom = pcs.natural_domain_for_degree(rows)
+    qdom = dom.create_disjoint_domain(2 * rows)
+    zeta = 0x1234567890ABCDEF1234567890ABCDEF1234567890ABCDEF
+
+    def once():
+        t = [time.perf_counter()]
+        tc, tpd = pcs.commit([(dom, trace)])
+        t.append(time.perf_counter())
+        lde = pcs.get_evaluations_on_domain(tpd, 0, qdom)
+        t.append(time.perf_counter())
+        qc, qpd = pcs.commit_quotient(qdom, quotient, 2)
+        t.append(time.perf_counter())
+        opened, proof = pcs.open([(tpd, [[zeta, dom.next_point(zeta)]]), (qpd, [[zeta], [zeta]])])
+        t.append(time.perf_counter())
+        for m in tpd + qpd:
+            m.free()
+        assert lde.shape[0] == 2 * rows and len(proof) == 2
+        return [b - a for a, b in zip(t, t[1:])]
+
+    for _ in range(args.warmup):
+        once()
+    launches0 = ctx.launch_count()
+    runs = [once() for _ in range(args.steps)]
+    launches = ctx.launch_count() - launches0
+    med = [float(np.median([r[i] for r in runs])) for i in range(4)]
+    total = sum(med)
+    line = {
+        "metric": "prove_pcs_cols_rows_per_s", "value": rows * cols / total, "unit": "cols*rows/s", "n_gpus": 1,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": total * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u256 (8x32-bit Montgomery limbs, BN254 Fr/Fq)",
+        "data": "synthetic",
+        "config": {"workload": f"PCS call sequence of eon_uni_stark::prove on a random 2^{log_rows} x {cols} trace, "
+                               "log_quotient_degree 1, 2 quotient chunks, page-locked host buffers, Python mirror of the "
+                               "Pcs trait (BASELINE configs[3] without the AIR)",
+                   "rows": rows, "cols": cols},
+        "phase_ms": {"commit_trace_with_lde_hint": med[0] * 1e3, "get_evaluations_on_domain": med[1] * 1e3,
+                     "commit_quotient_2_chunks": med[2] * 1e3, "open": med[3] * 1e3},
+        "gpu_launches": launches,
+    }
+    print(json.dumps(line), flush=True)
+
+
 def main():
     # keep stdout to the one JSON line: NCCL prints its version banner there at NCCL_DEBUG=VERSION
     if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
@@ -633,7 +695,7 @@ def main():
     ap.add_argument("--warmup-ref", type=int, default=0)
     ap.add_argument("--window-bits", type=int, default=-1,
                     help="MSM window tables: -1 library default, 0 none (plain c=16), 8..20 explicit")
-    ap.add_argument("--workload", default="commit", choices=["commit", "msm", "open"],
+    ap.add_argument("--workload", default="commit", choices=["commit", "msm", "open", "prove-pcs"],
                     help="commit: KZG commit + LDE (the headline metric); msm: standalone MSM (configs[2]); "
                          "open: KzgPcs::open at 2 points")
     ap.add_argument("--log-n", type=int, default=24, help="msm workload: log2 of the point count")
@@ -645,6 +707,8 @@ def main():
         run_msm(args)
     elif args.workload == "open":
         run_open(args)
+    elif args.workload == "prove-pcs":
+        run_prove_pcs(args)
     else:
         run_eon(args)
 

@@ -68,6 +68,10 @@ const char* eon_version(void);
 int eon_dev_alloc(eon_ctx* ctx, size_t bytes, void** d_out);
 int eon_dev_free(eon_ctx* ctx, void* d_ptr);
 int eon_h2d(eon_ctx* ctx, void* d_dst, const void* h_src, size_t bytes);
+/* page-locked host memory (cudaHostAlloc) for matrices handed to / returned by the host-buffer entry
+ * points: pageable buffers work too but copy at about half the rate.  A shim keeps a pool of these. */
+int eon_host_alloc(size_t bytes, void** h_out);
+int eon_host_free(void* h_ptr);
 int eon_d2h(eon_ctx* ctx, void* h_dst, const void* d_src, size_t bytes);
 
 /* ---- TwoAdicSubgroupDft<Fr> (dft/src/traits.rs) --------------------------------------------

@@ -128,6 +128,16 @@ int eon_dev_free(eon_ctx* ctx, void* d_ptr) {
   EON_CUDA(ctx, cudaFree(d_ptr));
   return EON_OK;
 }
+// page-locked host buffers for the matrices that cross PCIe (pageable memory halves the copy rate and a
+// freshly allocated pageable output pays a page fault per 4 KiB on top)
+int eon_host_alloc(size_t bytes, void** h_out) {
+  if (!h_out) return EON_ERR_BAD_ARG;
+  *h_out = nullptr;
+  cudaError_t e = cudaHostAlloc(h_out, bytes ? bytes : 1, cudaHostAllocDefault);
+  return e == cudaSuccess ? EON_OK : (e == cudaErrorMemoryAllocation ? EON_ERR_OOM : EON_ERR_CUDA);
+}
+int eon_host_free(void* h_ptr) { return cudaFreeHost(h_ptr) == cudaSuccess ? EON_OK : EON_ERR_CUDA; }
+
 int eon_h2d(eon_ctx* ctx, void* d_dst, const void* h_src, size_t bytes) {
   if (!ctx) return EON_ERR_BAD_ARG;
   Lock lk(ctx);

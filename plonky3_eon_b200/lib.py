@@ -30,6 +30,8 @@ _SIGS = {
     "eon_ctx_launch_count": (C.c_uint64, [C.c_void_p]),
     "eon_dev_alloc": (C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]),
     "eon_dev_free": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "eon_host_alloc": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p)]),
+    "eon_host_free": (C.c_int, [C.c_void_p]),
     "eon_h2d": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
     "eon_d2h": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
     "eon_dft_batch_dev": (C.c_int, [C.c_void_p, _u64p, _u64p, C.c_uint, C.c_size_t]),
@@ -112,6 +114,42 @@ def load():
         fn.argtypes = args
     _lib = lib
     return lib
+
+
+class _PinnedPool:
+    """Page-locked host matrices (eon_host_alloc), recycled by size: cudaHostAlloc costs ~0.2 s per GiB, and
+    a prover asks for the same shapes over and over."""
+
+    def __init__(self):
+        self.free = {}
+
+    def empty(self, shape, dtype=np.uint64):
+        import weakref
+        nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        lst = self.free.get(nbytes)
+        if lst:
+            addr = lst.pop()
+        else:
+            p = C.c_void_p()
+            rc = load().eon_host_alloc(nbytes, C.byref(p))
+            if rc != EON_OK:
+                raise EonError(rc, "pinned host allocation failed")
+            addr = p.value
+        buf = (C.c_char * max(nbytes, 1)).from_address(addr)
+        arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+        weakref.finalize(buf, self._recycle, nbytes, addr)   # back to the pool when the last view dies
+        return arr
+
+    def _recycle(self, nbytes, addr):
+        self.free.setdefault(nbytes, []).append(addr)
+
+
+_pinned = _PinnedPool()
+
+
+def pinned_empty(shape, dtype=np.uint64):
+    """Uninitialised page-locked numpy array (recycled through a pool when garbage-collected)."""
+    return _pinned.empty(shape, dtype)
 
 
 def ptr(x):

@@ -20,7 +20,7 @@ import numpy as np
 
 from . import field
 from .dft import _as_matrix, _shift_wire
-from .lib import default_context
+from .lib import default_context, pinned_empty
 
 
 @dataclass(frozen=True)
@@ -139,7 +139,7 @@ class GpuKzgPcs:
             npow <<= 1
         return TwoAdicMultiplicativeCoset(1, field.log2_strict(npow))
 
-    def commit(self, evaluations):
+    def commit(self, evaluations, _use_hint=True):
         """pcs.rs:223-265.  Returns (commitment, prover_data): commitment[m] is a uint64 [w, 8]
         array (MatrixCommitment.columns), prover_data[m] a MatrixProverData."""
         commitments, prover = [], []
@@ -150,9 +150,9 @@ class GpuKzgPcs:
             cols = np.zeros((w, 8), dtype=np.uint64)
             handle = C.c_uint64(0)
             lde = None
-            if self.lde_hint is not None and w > 0:
+            if _use_hint and self.lde_hint is not None and w > 0:
                 added, lshift = self.lde_hint
-                out = np.empty((h << added, w, 4), dtype=np.uint64)
+                out = pinned_empty((h << added, w, 4))
                 self.ctx.call("eon_kzg_commit_lde", a, domain.log_size, w, field.to_wire(domain.shift), cols,
                               C.byref(handle), domain.log_size + added, field.to_wire(lshift), out)
                 lde = (domain.log_size + added, lshift, out)
@@ -167,7 +167,7 @@ class GpuKzgPcs:
         """commit/src/pcs.rs:82-102 (trait default)."""
         subs = quotient_domain.split_evals(num_chunks, quotient_evaluations)
         doms = quotient_domain.split_domains(num_chunks)
-        return self.commit(zip(doms, subs))
+        return self.commit(zip(doms, subs), _use_hint=False)   # nobody evaluates quotient chunks on a larger coset
 
     def get_evaluations_on_domain(self, prover_data, idx, domain):
         """pcs.rs:267-287; the quadratic Horner loop of the reference is replaced by
@@ -178,7 +178,7 @@ class GpuKzgPcs:
         if m.lde is not None and m.lde[0] == domain.log_size and m.lde[1] == domain.shift % field.P:
             return m.lde[2]
         w = m.evals.shape[1]
-        out = np.empty((domain.size(), w, 4), dtype=np.uint64)
+        out = pinned_empty((domain.size(), w, 4))
         self.ctx.call("eon_kzg_evals_on_coset", C.c_uint64(m.handle), domain.log_size,
                       field.to_wire(domain.shift), out)
         return out
