@@ -162,6 +162,9 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    # torchrun exports OMP_NUM_THREADS=1 to every rank; the reference arm is rank 0 alone and is meant to use
+    # every host core it can get (the reference's rayon pool would), so undo that before OpenMP starts
+    os.environ["OMP_NUM_THREADS"] = str(len(os.sched_getaffinity(0)))
     from oracle import cport
     cores = cport.num_threads()
     sample_cols = 2 if args.cols >= 2 else 1
