@@ -205,6 +205,10 @@ int eon_quotient_and_eval_dev(eon_ctx* ctx, const uint64_t* d_coeffs, size_t h, 
 int eon_bench_imad_peak(eon_ctx* ctx, int kind, double* out_tops);
 /* Montgomery-product throughput (independent chains), in 1e9 modmul/s.  field: 0 Fr, 1 Fq. */
 int eon_bench_modmul(eon_ctx* ctx, int field, double* out_gmuls);
+/* The same for one formulation of the product.  variant: 0 = the product the library uses, 1 = word-serial
+ * (CIOS) Montgomery product, 2 = split form (one Karatsuba level + separate reduction), 3 = dedicated square
+ * (each square followed by one modular add).  All variants return identical limbs. */
+int eon_bench_modmul_variant(eon_ctx* ctx, int field, int variant, double* out_gmuls);
 /* per-phase device time (ms, CUDA events on the ctx stream) summed over every call since the last
  * eon_phase_reset; names via eon_phase_name (phases 0 .. eon_phase_count() - 1).  The msm_tree_* and
  * msm_finish phases are sub-intervals of msm_accumulate. */

@@ -253,6 +253,6 @@ int quotient_run(eon_ctx* ctx, const Fr* d_coeffs, size_t h, size_t width, size_
                  Fr* d_values);
 
 int bench_imad(eon_ctx* ctx, int kind, double* out_tops);
-int bench_modmul(eon_ctx* ctx, int field, double* out_gmuls);
+int bench_modmul(eon_ctx* ctx, int field, int variant, double* out_gmuls);
 
 }  // namespace eon

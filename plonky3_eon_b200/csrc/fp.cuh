@@ -308,9 +308,186 @@ EON_HD void mul_next(u32 X[8], u32 Y[8], const u32 a[8], u32 bi) {
 }
 }  // namespace detail
 
-// r = a*b*2^-256 mod p in [0, 2p)  (a < p; b any 256-bit value)
+// ---- split form: full 512-bit product (Karatsuba) or square, then a separate Montgomery reduction -------
+// The word-serial product above spends 64 limb MACs on a*b and 72 on the reduction.  One Karatsuba level
+// brings a*b down to 3 x 16 = 48 MACs (a dedicated square to 36) at the price of ~70 more IADD3/LOP3.
+// MEASURED ON B200 (tools/modmul_variants.py, profiles/r01j_modmul_variants.json): word-serial 67.4 G
+// products/s, split 65.4 G/s, square+add 71.5 G/s; whole step 51.6 ms (word-serial) vs 56.3 ms (split, whose
+// larger live set also costs 10-16 registers per kernel).  ptxas already fuses the word-serial form into 123
+// IMAD.WIDE per product and the extra ALU work is not free next to them, so the library uses the word-serial
+// form; the split form stays as a tested alternative behind -DEON_FP_SPLIT.
+namespace detail {
+// r[0..8) = a[0..4) * b[0..4).  Products at even limb positions accumulate in E, at odd positions in O
+// (O[k] has weight 2^(32(k+1))), one carry chain per (row, parity); r = E + 2^32 O.
+EON_HD void mul4(u32 r[8], const u32 a[4], const u32 b[4]) {
+  u32 E[8], O[7];
+  E[0] = cc::mul_lo(a[0], b[0]);  E[1] = cc::mul_hi(a[0], b[0]);
+  E[2] = cc::mul_lo(a[2], b[0]);  E[3] = cc::mul_hi(a[2], b[0]);
+  O[0] = cc::mul_lo(a[1], b[0]);  O[1] = cc::mul_hi(a[1], b[0]);
+  O[2] = cc::mul_lo(a[3], b[0]);  O[3] = cc::mul_hi(a[3], b[0]);
+  // row 1: a0 b1 @1, a2 b1 @3 (odd); a1 b1 @2, a3 b1 @4 (even)
+  O[0] = cc::mad_lo_cc(a[0], b[1], O[0]);   O[1] = cc::madc_hi_cc(a[0], b[1], O[1]);
+  O[2] = cc::madc_lo_cc(a[2], b[1], O[2]);  O[3] = cc::madc_hi_cc(a[2], b[1], O[3]);
+  O[4] = cc::addc(0, 0);
+  E[2] = cc::mad_lo_cc(a[1], b[1], E[2]);   E[3] = cc::madc_hi_cc(a[1], b[1], E[3]);
+  E[4] = cc::madc_lo_cc(a[3], b[1], 0);     E[5] = cc::madc_hi(a[3], b[1], 0);
+  // row 2: a0 b2 @2, a2 b2 @4 (even); a1 b2 @3, a3 b2 @5 (odd)
+  E[2] = cc::mad_lo_cc(a[0], b[2], E[2]);   E[3] = cc::madc_hi_cc(a[0], b[2], E[3]);
+  E[4] = cc::madc_lo_cc(a[2], b[2], E[4]);  E[5] = cc::madc_hi_cc(a[2], b[2], E[5]);
+  E[6] = cc::addc(0, 0);
+  O[2] = cc::mad_lo_cc(a[1], b[2], O[2]);   O[3] = cc::madc_hi_cc(a[1], b[2], O[3]);
+  O[4] = cc::madc_lo_cc(a[3], b[2], O[4]);  O[5] = cc::madc_hi(a[3], b[2], 0);
+  // row 3: a0 b3 @3, a2 b3 @5 (odd); a1 b3 @4, a3 b3 @6 (even)
+  O[2] = cc::mad_lo_cc(a[0], b[3], O[2]);   O[3] = cc::madc_hi_cc(a[0], b[3], O[3]);
+  O[4] = cc::madc_lo_cc(a[2], b[3], O[4]);  O[5] = cc::madc_hi_cc(a[2], b[3], O[5]);
+  O[6] = cc::addc(0, 0);
+  E[4] = cc::mad_lo_cc(a[1], b[3], E[4]);   E[5] = cc::madc_hi_cc(a[1], b[3], E[5]);
+  E[6] = cc::madc_lo_cc(a[3], b[3], E[6]);  E[7] = cc::madc_hi(a[3], b[3], 0);
+  r[0] = E[0];
+  r[1] = cc::add_cc(E[1], O[0]);
+#pragma unroll
+  for (int k = 2; k < 7; k++) r[k] = cc::addc_cc(E[k], O[k - 1]);
+  r[7] = cc::addc(E[7], O[6]);
+}
+
+// r[0..8) = a[0..4)^2: the six off-diagonal products once, doubled, plus the four squares.
+EON_HD void sqr4(u32 r[8], const u32 a[4]) {
+  u32 O[6], E2, E3, E4, E5, f[8];
+  O[0] = cc::mul_lo(a[0], a[1]);  O[1] = cc::mul_hi(a[0], a[1]);   // @1
+  O[2] = cc::mul_lo(a[0], a[3]);  O[3] = cc::mul_hi(a[0], a[3]);   // @3
+  O[4] = cc::mul_lo(a[2], a[3]);  O[5] = cc::mul_hi(a[2], a[3]);   // @5
+  O[2] = cc::mad_lo_cc(a[1], a[2], O[2]);  O[3] = cc::madc_hi_cc(a[1], a[2], O[3]);  // @3
+  O[4] = cc::addc_cc(O[4], 0);  O[5] = cc::addc(O[5], 0);
+  E2 = cc::mul_lo(a[0], a[2]);  E3 = cc::mul_hi(a[0], a[2]);       // @2
+  E4 = cc::mul_lo(a[1], a[3]);  E5 = cc::mul_hi(a[1], a[3]);       // @4
+  // f = off-diagonal sum (limb 0 is empty), < 2^225
+  f[1] = O[0];
+  f[2] = cc::add_cc(E2, O[1]);
+  f[3] = cc::addc_cc(E3, O[2]);
+  f[4] = cc::addc_cc(E4, O[3]);
+  f[5] = cc::addc_cc(E5, O[4]);
+  f[6] = cc::addc_cc(0, O[5]);
+  f[7] = cc::addc(0, 0);
+  // 2 f + squares: the squares sit on disjoint limb pairs, so one mad chain adds them all
+  f[7] = (f[7] << 1) | (f[6] >> 31);
+#pragma unroll
+  for (int k = 6; k >= 2; k--) f[k] = (f[k] << 1) | (f[k - 1] >> 31);
+  f[1] <<= 1;
+  r[0] = cc::mul_lo(a[0], a[0]);
+  r[1] = cc::mad_hi_cc(a[0], a[0], f[1]);
+  r[2] = cc::madc_lo_cc(a[1], a[1], f[2]);  r[3] = cc::madc_hi_cc(a[1], a[1], f[3]);
+  r[4] = cc::madc_lo_cc(a[2], a[2], f[4]);  r[5] = cc::madc_hi_cc(a[2], a[2], f[5]);
+  r[6] = cc::madc_lo_cc(a[3], a[3], f[6]);  r[7] = cc::madc_hi(a[3], a[3], f[7]);
+}
+
+// T[0..16) = a * b.  a = a0 + 2^128 a1, b = b0 + 2^128 b1:
+//   a b = a0 b0 + 2^256 a1 b1 + 2^128 (a0 b0 + a1 b1 + (a0 - a1)(b1 - b0))
+EON_HD void mul8_wide(u32 T[16], const u32 a[8], const u32 b[8]) {
+  mul4(T, a, b);
+  mul4(T + 8, a + 4, b + 4);
+  u32 da[4], db[4], m[8], z[9];
+  da[0] = cc::sub_cc(a[0], a[4]);
+#pragma unroll
+  for (int i = 1; i < 4; i++) da[i] = cc::subc_cc(a[i], a[4 + i]);
+  const u32 sa = cc::subc(0, 0);  // all-ones: a0 < a1
+  db[0] = cc::sub_cc(b[4], b[0]);
+#pragma unroll
+  for (int i = 1; i < 4; i++) db[i] = cc::subc_cc(b[4 + i], b[i]);
+  const u32 sb = cc::subc(0, 0);
+  // |x| = (x ^ s) - s
+  da[0] = cc::sub_cc(da[0] ^ sa, sa);
+  da[1] = cc::subc_cc(da[1] ^ sa, sa);
+  da[2] = cc::subc_cc(da[2] ^ sa, sa);
+  da[3] = cc::subc(da[3] ^ sa, sa);
+  db[0] = cc::sub_cc(db[0] ^ sb, sb);
+  db[1] = cc::subc_cc(db[1] ^ sb, sb);
+  db[2] = cc::subc_cc(db[2] ^ sb, sb);
+  db[3] = cc::subc(db[3] ^ sb, sb);
+  mul4(m, da, db);
+  const u32 neg = sa ^ sb;  // all-ones: the cross term enters with a minus sign
+  z[0] = cc::add_cc(T[0], T[8]);
+#pragma unroll
+  for (int i = 1; i < 8; i++) z[i] = cc::addc_cc(T[i], T[8 + i]);
+  z[8] = cc::addc(0, 0);
+  // z += neg ? -m : m   (two's complement over 9 limbs; the true value is non-negative)
+  (void)cc::add_cc(neg, neg);  // carry flag = neg & 1
+#pragma unroll
+  for (int i = 0; i < 8; i++) z[i] = cc::addc_cc(z[i], m[i] ^ neg);
+  z[8] = cc::addc(z[8], neg);
+  T[4] = cc::add_cc(T[4], z[0]);
+#pragma unroll
+  for (int i = 1; i < 9; i++) T[4 + i] = cc::addc_cc(T[4 + i], z[i]);
+  T[13] = cc::addc_cc(T[13], 0);
+  T[14] = cc::addc_cc(T[14], 0);
+  T[15] = cc::addc(T[15], 0);
+}
+
+// T[0..16) = a^2 = a0^2 + 2^256 a1^2 + 2^129 a0 a1
+EON_HD void sqr8_wide(u32 T[16], const u32 a[8]) {
+  sqr4(T, a);
+  sqr4(T + 8, a + 4);
+  u32 m[8];
+  mul4(m, a, a + 4);
+  T[4] = cc::add_cc(T[4], m[0] << 1);
+#pragma unroll
+  for (int i = 1; i < 8; i++) T[4 + i] = cc::addc_cc(T[4 + i], (m[i] << 1) | (m[i - 1] >> 31));
+  T[12] = cc::addc_cc(T[12], m[7] >> 31);
+  T[13] = cc::addc_cc(T[13], 0);
+  T[14] = cc::addc_cc(T[14], 0);
+  T[15] = cc::addc(T[15], 0);
+}
+
+// One reduction digit of the split form.  X = previous odd array (the even array after the 2^-32 shift),
+// Y = previous even array with Y[0] == 0; tin = the limb of T that enters the 9-limb window at this digit
+// (weight 2^(32*7) in the new frame).  The window never overflows: after digit i it holds
+// (T mod 2^(32(i+8)) + sum m_k p 2^(32k)) / 2^(32 i) < 2^(32*9).
 template <class PP>
-EON_HD void fp_mul_lazy(u32 r[8], const u32 a[8], const u32 b[8]) {
+EON_HD void redc_next(u32 X[8], u32 Y[8], u32 tin) {
+  X[0] = cc::add_cc(X[0], Y[1]);
+  const u32 m = X[0] * PP::INV;  // mul.lo leaves the carry flag alone
+  Y[0] = cc::madc_lo_cc(PP::mod(1), m, Y[2]);
+  Y[1] = cc::madc_hi_cc(PP::mod(1), m, Y[3]);
+  Y[2] = cc::madc_lo_cc(PP::mod(3), m, Y[4]);
+  Y[3] = cc::madc_hi_cc(PP::mod(3), m, Y[5]);
+  Y[4] = cc::madc_lo_cc(PP::mod(5), m, Y[6]);
+  Y[5] = cc::madc_hi_cc(PP::mod(5), m, Y[7]);
+  Y[6] = cc::madc_lo_cc(PP::mod(7), m, tin);
+  Y[7] = cc::madc_hi(PP::mod(7), m, 0);
+  X[0] = cc::mad_lo_cc(PP::mod(0), m, X[0]);
+  X[1] = cc::madc_hi_cc(PP::mod(0), m, X[1]);
+  X[2] = cc::madc_lo_cc(PP::mod(2), m, X[2]);
+  X[3] = cc::madc_hi_cc(PP::mod(2), m, X[3]);
+  X[4] = cc::madc_lo_cc(PP::mod(4), m, X[4]);
+  X[5] = cc::madc_hi_cc(PP::mod(4), m, X[5]);
+  X[6] = cc::madc_lo_cc(PP::mod(6), m, X[6]);
+  X[7] = cc::madc_hi_cc(PP::mod(6), m, X[7]);
+  Y[7] = cc::addc(Y[7], 0);
+}
+
+// r = T * 2^-256 mod p in [0, 2p) for T < p * 2^256
+template <class PP>
+EON_HD void redc_wide(u32 r[8], const u32 T[16]) {
+  u32 ev[8], od[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) { ev[i] = T[i]; od[i] = 0; }
+  redc_digit<PP>(ev, od);
+  redc_next<PP>(od, ev, T[8]);
+  redc_next<PP>(ev, od, T[9]);
+  redc_next<PP>(od, ev, T[10]);
+  redc_next<PP>(ev, od, T[11]);
+  redc_next<PP>(od, ev, T[12]);
+  redc_next<PP>(ev, od, T[13]);
+  redc_next<PP>(od, ev, T[14]);
+  r[0] = cc::add_cc(ev[0], od[1]);
+#pragma unroll
+  for (int i = 1; i < 7; i++) r[i] = cc::addc_cc(ev[i], od[i + 1]);
+  r[7] = cc::addc(ev[7], T[15]);
+}
+}  // namespace detail
+
+// r = a*b*2^-256 mod p in [0, 2p), word-serial form  (a < p; b any 256-bit value)
+template <class PP>
+EON_HD void fp_mul_lazy_cios(u32 r[8], const u32 a[8], const u32 b[8]) {
   u32 ev[8], od[8];
   detail::mul_first<PP>(ev, od, a, b[0]);
   detail::mul_next<PP>(od, ev, a, b[1]);
@@ -327,6 +504,42 @@ EON_HD void fp_mul_lazy(u32 r[8], const u32 a[8], const u32 b[8]) {
   r[7] = cc::addc(ev[7], 0);
 }
 
+// r = a*b*2^-256 mod p in [0, 2p), split form (same value, same range as the word-serial form)
+template <class PP>
+EON_HD void fp_mul_lazy_split(u32 r[8], const u32 a[8], const u32 b[8]) {
+  u32 T[16];
+  detail::mul8_wide(T, a, b);
+  detail::redc_wide<PP>(r, T);
+}
+
+// r = a*a*2^-256 mod p in [0, 2p), dedicated square + separate reduction
+template <class PP>
+EON_HD void fp_sqr_lazy_split(u32 r[8], const u32 a[8]) {
+  u32 T[16];
+  detail::sqr8_wide(T, a);
+  detail::redc_wide<PP>(r, T);
+}
+
+// r = a*b*2^-256 mod p in [0, 2p)  (a < p; b any 256-bit value)
+template <class PP>
+EON_HD void fp_mul_lazy(u32 r[8], const u32 a[8], const u32 b[8]) {
+#if defined(EON_FP_SPLIT)
+  fp_mul_lazy_split<PP>(r, a, b);
+#else
+  fp_mul_lazy_cios<PP>(r, a, b);
+#endif
+}
+
+// r = a*a*2^-256 mod p in [0, 2p)  (a < p)
+template <class PP>
+EON_HD void fp_sqr_lazy(u32 r[8], const u32 a[8]) {
+#if defined(EON_FP_SPLIT)
+  fp_sqr_lazy_split<PP>(r, a);
+#else
+  fp_mul_lazy_cios<PP>(r, a, a);
+#endif
+}
+
 // Canonical Montgomery product.  Reference: monty_mul, bn254/src/helpers.rs:188-205.
 template <class PP>
 EON_HD Fp<PP> fp_mul(const Fp<PP>& a, const Fp<PP>& b) {
@@ -338,7 +551,13 @@ EON_HD Fp<PP> fp_mul(const Fp<PP>& a, const Fp<PP>& b) {
 }
 
 template <class PP>
-EON_HD Fp<PP> fp_sqr(const Fp<PP>& a) { return fp_mul(a, a); }
+EON_HD Fp<PP> fp_sqr(const Fp<PP>& a) {
+  u32 t[8];
+  fp_sqr_lazy<PP>(t, a.v);
+  Fp<PP> r;
+  fp_final_sub<PP>(r.v, t);
+  return r;
+}
 
 // Montgomery -> canonical integer limbs (a * 1 * R^-1).  Reference: as_canonical_biguint, field.rs:455-461.
 template <class PP>

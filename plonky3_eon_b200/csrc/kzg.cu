@@ -198,19 +198,41 @@ int bench_imad(eon_ctx* ctx, int kind, double* out_tops) {
   return EON_OK;
 }
 
-template <class PP>
+// VARIANT: 0 = fp_mul as the library uses it, 1 = word-serial (CIOS) product, 2 = split product
+// (Karatsuba + separate reduction), 3 = dedicated square + one modular add
+template <class PP, int VARIANT>
+__device__ __forceinline__ Fp<PP> bench_product(const Fp<PP>& a, const Fp<PP>& b) {
+  if (VARIANT == 0) return fp_mul(a, b);
+  u32 t[8];
+  if (VARIANT == 1) fp_mul_lazy_cios<PP>(t, a.v, b.v);
+  else if (VARIANT == 2) fp_mul_lazy_split<PP>(t, a.v, b.v);
+  else fp_sqr_lazy_split<PP>(t, a.v);
+  Fp<PP> r;
+  fp_final_sub<PP>(r.v, t);
+  return VARIANT == 3 ? fp_add(r, b) : r;  // the add keeps the two chains dependent on each other
+}
+
+template <class PP, int VARIANT>
 __global__ void __launch_bounds__(256) k_modmul_peak(Fp<PP>* out, u32 iters, u32 seed) {
   Fp<PP> a = fp_from_u64<PP>(seed + threadIdx.x + 1);
   Fp<PP> b = fp_from_u64<PP>(seed * 3 + blockIdx.x + 7);
   Fp<PP> c = fp_from_u64<PP>(seed * 5 + threadIdx.x * 11 + 13);
   for (u32 it = 0; it < iters; it++) {
-    a = fp_mul(a, b);
-    c = fp_mul(c, a);
+    a = bench_product<PP, VARIANT>(a, b);
+    c = bench_product<PP, VARIANT>(c, a);
   }
   out[blockIdx.x * blockDim.x + threadIdx.x] = fp_add(a, c);
 }
 
-int bench_modmul(eon_ctx* ctx, int field, double* out_gmuls) {
+template <class PP>
+static void launch_modmul_peak(int variant, unsigned blocks, cudaStream_t st, Fp<PP>* out, u32 iters, u32 seed) {
+  if (variant == 1) k_modmul_peak<PP, 1><<<blocks, 256, 0, st>>>(out, iters, seed);
+  else if (variant == 2) k_modmul_peak<PP, 2><<<blocks, 256, 0, st>>>(out, iters, seed);
+  else if (variant == 3) k_modmul_peak<PP, 3><<<blocks, 256, 0, st>>>(out, iters, seed);
+  else k_modmul_peak<PP, 0><<<blocks, 256, 0, st>>>(out, iters, seed);
+}
+
+int bench_modmul(eon_ctx* ctx, int field, int variant, double* out_gmuls) {
   const unsigned blocks = (unsigned)ctx->num_sms * 8;
   const u32 iters = 512;
   void* buf = nullptr;
@@ -221,8 +243,8 @@ int bench_modmul(eon_ctx* ctx, int field, double* out_gmuls) {
   float best = 1e30f;
   for (int rep = 0; rep < 4; rep++) {
     EON_CUDA(ctx, cudaEventRecord(e0, ctx->stream));
-    if (field == 0) k_modmul_peak<FrParams><<<blocks, 256, 0, ctx->stream>>>((Fr*)buf, iters, 99u + rep);
-    else k_modmul_peak<FqParams><<<blocks, 256, 0, ctx->stream>>>((Fq*)buf, iters, 99u + rep);
+    if (field == 0) launch_modmul_peak<FrParams>(variant, blocks, ctx->stream, (Fr*)buf, iters, 99u + rep);
+    else launch_modmul_peak<FqParams>(variant, blocks, ctx->stream, (Fq*)buf, iters, 99u + rep);
     EON_LAUNCHED(ctx);
     EON_CUDA(ctx, cudaEventRecord(e1, ctx->stream));
     EON_CUDA(ctx, cudaEventSynchronize(e1));

@@ -75,6 +75,7 @@ _SIGS = {
     "eon_quotient_and_eval_dev": (C.c_int, [C.c_void_p, _u64p, C.c_size_t, C.c_size_t, _u64p, _u64p, _u64p]),
     "eon_bench_imad_peak": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_double)]),
     "eon_bench_modmul": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_double)]),
+    "eon_bench_modmul_variant": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_double)]),
     "eon_last_phase_ms": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_float)]),
     "eon_phase_reset": (C.c_int, [C.c_void_p]),
     "eon_phase_name": (C.c_char_p, [C.c_int]),
@@ -246,9 +247,10 @@ class Context:
         self.call("eon_bench_imad_peak", kind, C.byref(v))
         return float(v.value)
 
-    def modmul_gmuls(self, field=1):
+    def modmul_gmuls(self, field=1, variant=0):
+        """1e9 Montgomery products/s; variant 0 = the library's product, 1 = word-serial, 2 = split, 3 = square."""
         v = C.c_double()
-        self.call("eon_bench_modmul", field, C.byref(v))
+        self.call("eon_bench_modmul_variant", field, variant, C.byref(v))
         return float(v.value)
 
 

@@ -41,6 +41,30 @@ void host_fp_op(int which, int op, const uint32_t* a, const uint32_t* b, uint32_
   }
 }
 
+// Raw lazy products (result in [0, 2p), not canonicalised).  variant: 0 = word-serial (CIOS),
+// 1 = split (Karatsuba product + separate reduction), 2 = split square of a (b ignored).
+// a < p; b is any 256-bit value.
+void host_fp_mul_lazy(int which, int variant, const uint32_t* a, const uint32_t* b, uint32_t* r, int n) {
+  for (int i = 0; i < n; i++, a += 8, b += 8, r += 8) {
+    if (which == 0) {
+      if (variant == 0) fp_mul_lazy_cios<FrParams>(r, a, b);
+      else if (variant == 1) fp_mul_lazy_split<FrParams>(r, a, b);
+      else fp_sqr_lazy_split<FrParams>(r, a);
+    } else {
+      if (variant == 0) fp_mul_lazy_cios<FqParams>(r, a, b);
+      else if (variant == 1) fp_mul_lazy_split<FqParams>(r, a, b);
+      else fp_sqr_lazy_split<FqParams>(r, a);
+    }
+  }
+}
+// T[0..16) = a * b (variant 0) or a^2 (variant 1) over full 256-bit operands
+void host_wide_product(int variant, const uint32_t* a, const uint32_t* b, uint32_t* T, int n) {
+  for (int i = 0; i < n; i++, a += 8, b += 8, T += 16) {
+    if (variant == 0) detail::mul8_wide(T, a, b);
+    else detail::sqr8_wide(T, a);
+  }
+}
+
 // Lazily reduced NTT butterflies (fp.cuh): one forward (DIT) and one inverse (DIF) radix-2 butterfly on
 // raw 256-bit limbs, then canonicalised.  a, b may be anywhere in [0, 4r) (dit) / [0, 2r) (dif).
 void host_lazy_butterfly(int dif, const uint32_t* a, const uint32_t* b, const uint32_t* tw, uint32_t* o0, uint32_t* o1) {

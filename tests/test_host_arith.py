@@ -153,3 +153,72 @@ def test_lazy_ntt_butterflies(lib):
             else:
                 want = ((a + b) % P, (a - b) * tw * rinv % P)
             assert (to_int(o0), to_int(o1)) == want, (dif, a, b)
+
+
+def _wide_cases(rng, n_rand):
+    """256-bit operands that stress the Karatsuba glue: equal / ordered halves, all-ones limbs, sparse limbs."""
+    M = (1 << 256) - 1
+    lo = (1 << 128) - 1
+    specials = [0, 1, M, lo, lo << 128, 1 << 128, (1 << 128) - 1 + (1 << 255), 0x80000000 << 96,
+                (0xFFFFFFFF << 224) | 1, sum(0xFFFFFFFF << (64 * k) for k in range(4)),
+                sum(1 << (32 * k + 31) for k in range(8)), (5 << 128) | 7, (7 << 128) | 5, (9 << 128) | 9]
+    vals = list(specials)
+    for _ in range(n_rand):
+        v = int.from_bytes(rng.bytes(32), "little")
+        kind = rng.integers(0, 6)
+        if kind == 1:      # halves equal
+            v = (v & lo) | ((v & lo) << 128)
+        elif kind == 2:    # halves differ only in the lowest limb
+            v = (v & lo) | (((v & lo) ^ 1) << 128)
+        elif kind == 3:    # runs of all-ones limbs (long carry chains)
+            v |= 0xFFFFFFFFFFFFFFFF << (64 * int(rng.integers(0, 4)))
+        elif kind == 4:    # sparse
+            v &= sum(0xFFFFFFFF << (32 * int(k)) for k in rng.integers(0, 8, size=3))
+        vals.append(v)
+    return vals
+
+
+def _from_int16(v):
+    return np.array([(v >> (32 * k)) & 0xFFFFFFFF for k in range(16)], dtype=np.uint32)
+
+
+def test_wide_product_and_square(lib):
+    """detail::mul8_wide / sqr8_wide (Karatsuba level + dedicated square) against big-int products on
+    full 256-bit operands, including every pair of the special patterns."""
+    rng = np.random.default_rng(5)
+    vals = _wide_cases(rng, 400)
+    sp = vals[:14]
+    pairs = [(x, y) for x in sp for y in sp] + list(zip(vals, reversed(vals)))
+    a = np.array([from_int(x) for x, _ in pairs])
+    b = np.array([from_int(y) for _, y in pairs])
+    T = np.zeros((len(pairs), 16), dtype=np.uint32)
+    lib.host_wide_product(0, _ptr(a), _ptr(b), _ptr(T), len(pairs))
+    for i, (x, y) in enumerate(pairs):
+        assert (T[i] == _from_int16(x * y)).all(), ("mul", hex(x), hex(y))
+    lib.host_wide_product(1, _ptr(a), _ptr(b), _ptr(T), len(pairs))
+    for i, (x, _) in enumerate(pairs):
+        assert (T[i] == _from_int16(x * x)).all(), ("sqr", hex(x))
+
+
+@pytest.mark.parametrize("which,mod", [(0, fr.P), (1, g1.Q)])
+def test_split_product_equals_word_serial(lib, which, mod):
+    """The split Montgomery product (Karatsuba + separate reduction) and the dedicated square return the
+    same limbs as the word-serial CIOS form, for a < p and b anywhere in [0, 2^256) (the lazily reduced
+    NTT butterflies feed values up to 4p), and the value is a*b/R mod p in [0, 2p)."""
+    rng = np.random.default_rng(21 + which)
+    bs = _wide_cases(rng, 600)
+    as_ = [v % mod for v in _wide_cases(rng, len(bs) - 14)]
+    as_ = (as_ + EDGE(mod) * 2)[:len(bs)]
+    a = np.array([from_int(x) for x in as_])
+    b = np.array([from_int(y) for y in bs])
+    n = len(bs)
+    r0, r1, r2 = np.zeros_like(a), np.zeros_like(a), np.zeros_like(a)
+    lib.host_fp_mul_lazy(which, 0, _ptr(a), _ptr(b), _ptr(r0), n)
+    lib.host_fp_mul_lazy(which, 1, _ptr(a), _ptr(b), _ptr(r1), n)
+    lib.host_fp_mul_lazy(which, 2, _ptr(a), _ptr(b), _ptr(r2), n)
+    Rinv = pow(1 << 256, -1, mod)
+    for i in range(n):
+        x, y = as_[i], bs[i]
+        assert to_int(r1[i]) == to_int(r0[i]), (which, i, hex(x), hex(y))
+        assert to_int(r1[i]) < 2 * mod and to_int(r1[i]) % mod == x * y * Rinv % mod
+        assert to_int(r2[i]) < 2 * mod and to_int(r2[i]) % mod == x * x * Rinv % mod
