@@ -46,7 +46,9 @@ enum {
   EON_ERR_CUDA = -3,         /* CUDA runtime failure / no device */
   EON_ERR_OOM = -4,          /* device allocation failed */
   EON_ERR_BAD_HANDLE = -5,
-  EON_ERR_TWO_ADICITY = -6   /* transform size exceeds 2^28 (Fr::TWO_ADICITY, field.rs:564) */
+  EON_ERR_TWO_ADICITY = -6,  /* transform size exceeds 2^28 (Fr::TWO_ADICITY, field.rs:564) */
+  EON_ERR_BAD_POINT = -7     /* a compressed G1 encoding is not a curve point: serde's
+                                "Invalid G1 point", bn254/src/curve.rs:94-96 */
 };
 
 /* ---- context ------------------------------------------------------------------------- */
@@ -106,6 +108,25 @@ int eon_coset_lde_batch(eon_ctx* ctx, const uint64_t* h_in, uint64_t* h_out, uns
 /* Upload g1_powers as n affine points (8 x u64 each).  Replaces the per-call `to_affine` of
  * bn254/src/curve.rs:170: points are normalised once by the caller and stay resident. */
 int eon_srs_load_affine(eon_ctx* ctx, const uint64_t* h_xy, size_t n);
+/* ---- compressed G1 points (G1::to_bytes bn254/src/curve.rs:136-139; Serialize / Deserialize for G1
+ * :84-98, i.e. how StructuredReferenceString, KzgCommitment and KzgProof are (de)serialised and how
+ * CanObserve<KzgCommitment> feeds commitments to the challenger, kzg/src/pcs.rs:409-438) ------------
+ * 32 bytes per point = halo2curves' GroupEncoding of bn256::G1Affine.  halo2curves is not vendored in
+ * the reference; the layout is restated from its published definition (csrc/codec.cu):
+ *   EON_G1_ENC_HALO2   x little-endian canonical; byte 31 bit 6 = lowest bit of canonical y; byte 31
+ *                      bit 7 = identity (every other bit zero).  halo2curves 0.4 and later, incl. "0.9".
+ *   EON_G1_ENC_LEGACY  sign in byte 31 bit 7; identity = 32 zero bytes (halo2curves 0.3 and earlier). */
+enum { EON_G1_ENC_HALO2 = 0, EON_G1_ENC_LEGACY = 1 };
+/* n affine wire points (host) -> 32 n bytes (host), compressed on the device. */
+int eon_g1_compress(eon_ctx* ctx, const uint64_t* h_xy, size_t n, uint8_t* h_out, int enc);
+/* 32 n bytes (host) -> n affine wire points (host): batched square roots on the device.  Fails with
+ * EON_ERR_BAD_POINT if an encoding is not a curve point; *bad_index (may be NULL) = index of the first
+ * such encoding, or SIZE_MAX. */
+int eon_g1_decompress(eon_ctx* ctx, const uint8_t* h_in, size_t n, uint64_t* h_xy, int enc, size_t* bad_index);
+/* Deserialised-SRS ingest: g1_powers as n compressed points, decompressed straight into the resident
+ * affine SRS (and its window tables); on EON_ERR_BAD_POINT the previous SRS is gone and none is loaded. */
+int eon_srs_load_compressed(eon_ctx* ctx, const uint8_t* h_in, size_t n, int enc, size_t* bad_index);
+
 /* init_srs_unsafe (params.rs:123-139), G1 part: g1_powers[i] = alpha^i * G for i < n, generated
  * on the device.  alpha: Montgomery Fr. */
 int eon_srs_generate_unsafe(eon_ctx* ctx, const uint64_t alpha[4], size_t n);

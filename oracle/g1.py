@@ -177,3 +177,52 @@ def from_wire(arr):
             assert is_on_curve(p), "point not on curve"
             out.append(p)
     return out
+
+
+# compressed form -------------------------------------------------------------------
+# G1::to_bytes (bn254/src/curve.rs:136-139) = halo2curves G1Affine::to_bytes, Serialize / Deserialize for G1
+# (:84-98).  halo2curves is not in /root/reference; its GroupEncoding for bn256 (two spare bits in the top byte
+# of x) is restated from its published definition.  PARITY UNPINNED at the byte level: the reference holds no
+# byte vector for any point, so the two layouts halo2curves has used are both provided.
+ENC_HALO2 = 0   # 0.4 and later ("0.9" in bn254/Cargo.toml:22): sign = byte 31 bit 6, identity = byte 31 bit 7
+ENC_LEGACY = 1  # 0.3 and earlier: sign = byte 31 bit 7, identity = 32 zero bytes
+
+
+def to_bytes(p, enc=ENC_HALO2):
+    if p is None:
+        b = bytearray(32)
+        if enc == ENC_HALO2:
+            b[31] |= 0x80
+        return bytes(b)
+    x, y = p
+    b = bytearray(x.to_bytes(32, "little"))
+    b[31] |= (y & 1) << (6 if enc == ENC_HALO2 else 7)
+    return bytes(b)
+
+
+def from_bytes(data, enc=ENC_HALO2):
+    """Returns the point, or raises ValueError("Invalid G1 point") (bn254/src/curve.rs:95)."""
+    b = bytearray(data)
+    assert len(b) == 32
+    if enc == ENC_HALO2:
+        inf, sign = b[31] >> 7, (b[31] >> 6) & 1
+        b[31] &= 0x3F
+    else:
+        inf, sign = 0, b[31] >> 7
+        b[31] &= 0x7F
+    x = int.from_bytes(b, "little")
+    if inf:
+        if x or sign:
+            raise ValueError("Invalid G1 point")
+        return None
+    if enc == ENC_LEGACY and x == 0 and sign == 0:
+        return None
+    if x >= Q:
+        raise ValueError("Invalid G1 point")
+    rhs = (x * x * x + B) % Q
+    y = pow(rhs, (Q + 1) // 4, Q)
+    if y * y % Q != rhs:
+        raise ValueError("Invalid G1 point")
+    if (y & 1) != sign:
+        y = (-y) % Q
+    return (x, y)

@@ -281,11 +281,7 @@ int eon_coset_lde_batch(eon_ctx* ctx, const uint64_t* h_in, uint64_t* h_out, uns
 }
 
 // ---- SRS ---------------------------------------------------------------------------------------
-int eon_srs_load_affine(eon_ctx* ctx, const uint64_t* h_xy, size_t n) {
-  if (!ctx) return EON_ERR_BAD_ARG;
-  Lock lk(ctx);
-  EON_TRY(set_device(ctx));
-  if (n && !h_xy) return fail(ctx, EON_ERR_BAD_ARG, "null SRS pointer");
+static int srs_drop(eon_ctx* ctx) {
   if (ctx->d_srs) {
     EON_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     EON_CUDA(ctx, cudaFree(ctx->d_srs));
@@ -293,11 +289,68 @@ int eon_srs_load_affine(eon_ctx* ctx, const uint64_t* h_xy, size_t n) {
     ctx->srs_n = 0;
     EON_TRY(srs_build_tables(ctx, 0));
   }
+  return EON_OK;
+}
+
+int eon_srs_load_affine(eon_ctx* ctx, const uint64_t* h_xy, size_t n) {
+  if (!ctx) return EON_ERR_BAD_ARG;
+  Lock lk(ctx);
+  EON_TRY(set_device(ctx));
+  if (n && !h_xy) return fail(ctx, EON_ERR_BAD_ARG, "null SRS pointer");
+  EON_TRY(srs_drop(ctx));
   if (n == 0) return EON_OK;
   EON_CUDA(ctx, cudaMalloc(&ctx->d_srs, n * sizeof(G1Affine)));
   EON_CUDA(ctx, cudaMemcpyAsync(ctx->d_srs, h_xy, n * sizeof(G1Affine), cudaMemcpyHostToDevice, ctx->stream));
   ctx->srs_n = n;
   EON_TRY(srs_build_default_tables(ctx));
+  EON_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return EON_OK;
+}
+
+int eon_srs_load_compressed(eon_ctx* ctx, const uint8_t* h_in, size_t n, int enc, size_t* bad_index) {
+  if (!ctx) return EON_ERR_BAD_ARG;
+  Lock lk(ctx);
+  EON_TRY(set_device(ctx));
+  if (n && !h_in) return fail(ctx, EON_ERR_BAD_ARG, "null SRS pointer");
+  if (bad_index) *bad_index = (size_t)-1;
+  EON_TRY(srs_drop(ctx));
+  if (n == 0) return EON_OK;
+  EON_CUDA(ctx, cudaMalloc(&ctx->d_srs, n * sizeof(G1Affine)));
+  int rc = g1_decompress_run(ctx, h_in, n, ctx->d_srs, enc, bad_index);
+  if (rc != EON_OK) {
+    cudaFree(ctx->d_srs);
+    ctx->d_srs = nullptr;
+    return rc;
+  }
+  ctx->srs_n = n;
+  EON_TRY(srs_build_default_tables(ctx));
+  EON_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return EON_OK;
+}
+
+int eon_g1_compress(eon_ctx* ctx, const uint64_t* h_xy, size_t n, uint8_t* h_out, int enc) {
+  if (!ctx) return EON_ERR_BAD_ARG;
+  Lock lk(ctx);
+  EON_TRY(set_device(ctx));
+  if (n && (!h_xy || !h_out)) return fail(ctx, EON_ERR_BAD_ARG, "null pointer");
+  if (n == 0) return EON_OK;
+  void* d_pts;
+  EON_TRY(scratch_get(ctx, SC_IO_A, n * sizeof(G1Affine), &d_pts));
+  EON_CUDA(ctx, cudaMemcpyAsync(d_pts, h_xy, n * sizeof(G1Affine), cudaMemcpyHostToDevice, ctx->stream));
+  return g1_compress_run(ctx, (const G1Affine*)d_pts, n, h_out, enc);
+}
+
+int eon_g1_decompress(eon_ctx* ctx, const uint8_t* h_in, size_t n, uint64_t* h_xy, int enc, size_t* bad_index) {
+  if (!ctx) return EON_ERR_BAD_ARG;
+  Lock lk(ctx);
+  EON_TRY(set_device(ctx));
+  if (n && (!h_in || !h_xy)) return fail(ctx, EON_ERR_BAD_ARG, "null pointer");
+  if (bad_index) *bad_index = (size_t)-1;
+  if (n == 0) return EON_OK;
+  void* d_pts;
+  EON_TRY(scratch_get(ctx, SC_IO_A, n * sizeof(G1Affine), &d_pts));
+  EON_TRY(g1_decompress_run(ctx, h_in, n, (G1Affine*)d_pts, enc, bad_index));
+  EON_CUDA(ctx, cudaMemcpyAsync(h_xy, d_pts, n * sizeof(G1Affine), cudaMemcpyDeviceToHost, ctx->stream));
   EON_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return EON_OK;
 }

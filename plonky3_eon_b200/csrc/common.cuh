@@ -249,6 +249,9 @@ int srs_generate(eon_ctx* ctx, const Fr& alpha, size_t n);
 int srs_build_tables(eon_ctx* ctx, unsigned window_bits);
 int srs_build_default_tables(eon_ctx* ctx);
 
+int g1_compress_run(eon_ctx* ctx, const G1Affine* d_pts, size_t n, uint8_t* h_out, int enc);
+int g1_decompress_run(eon_ctx* ctx, const uint8_t* h_in, size_t n, G1Affine* d_out, int enc, size_t* bad_index);
+
 int quotient_run(eon_ctx* ctx, const Fr* d_coeffs, size_t h, size_t width, size_t ld_out, const Fr& z, Fr* d_quot,
                  Fr* d_values);
 

@@ -19,6 +19,9 @@ EON_ERR_CUDA = -3
 EON_ERR_OOM = -4
 EON_ERR_BAD_HANDLE = -5
 EON_ERR_TWO_ADICITY = -6
+EON_ERR_BAD_POINT = -7
+G1_ENC_HALO2 = 0   # halo2curves >= 0.4 GroupEncoding: sign = byte 31 bit 6, identity = byte 31 bit 7
+G1_ENC_LEGACY = 1  # halo2curves <= 0.3: sign = byte 31 bit 7, identity = 32 zero bytes
 
 _u64p = C.c_void_p  # all buffers are passed as raw addresses
 _SIGS = {
@@ -45,6 +48,9 @@ _SIGS = {
     "eon_coset_idft_batch": (C.c_int, [C.c_void_p, _u64p, _u64p, C.c_uint, C.c_size_t, _u64p]),
     "eon_coset_lde_batch": (C.c_int, [C.c_void_p, _u64p, _u64p, C.c_uint, C.c_size_t, C.c_uint, _u64p]),
     "eon_srs_load_affine": (C.c_int, [C.c_void_p, _u64p, C.c_size_t]),
+    "eon_srs_load_compressed": (C.c_int, [C.c_void_p, _u64p, C.c_size_t, C.c_int, C.POINTER(C.c_size_t)]),
+    "eon_g1_compress": (C.c_int, [C.c_void_p, _u64p, C.c_size_t, _u64p, C.c_int]),
+    "eon_g1_decompress": (C.c_int, [C.c_void_p, _u64p, C.c_size_t, _u64p, C.c_int, C.POINTER(C.c_size_t)]),
     "eon_srs_generate_unsafe": (C.c_int, [C.c_void_p, _u64p, C.c_size_t]),
     "eon_srs_size": (C.c_size_t, [C.c_void_p]),
     "eon_srs_read": (C.c_int, [C.c_void_p, C.c_size_t, C.c_size_t, _u64p]),
@@ -115,6 +121,15 @@ def load():
         fn.argtypes = args
     _lib = lib
     return lib
+
+
+class InvalidG1Point(EonError):
+    """serde's "Invalid G1 point" (bn254/src/curve.rs:94-96): a compressed encoding that is not a curve point.
+    `index` = position of the first such encoding in the batch."""
+
+    def __init__(self, code, msg, index=None):
+        super().__init__(code, msg)
+        self.index = index
 
 
 class _PinnedPool:
@@ -193,6 +208,8 @@ class Context:
         msg = self.lib.eon_last_error(self.h).decode()
         if rc == EON_ERR_SRS_TOO_SHORT:
             raise DegreeTooLarge(rc, msg)
+        if rc == EON_ERR_BAD_POINT:
+            raise InvalidG1Point(rc, msg)
         raise EonError(rc, msg)
 
     def call(self, name, *args):
@@ -216,6 +233,37 @@ class Context:
 
     def srs_size(self):
         return int(self.lib.eon_srs_size(self.h))
+
+    # -- compressed G1 points (bn254/src/curve.rs:84-98,136-139) ---------------------------------
+    def g1_to_bytes(self, points_wire, enc=G1_ENC_HALO2):
+        """G1::to_bytes for a batch: uint64 [n, 8] affine wire points -> uint8 [n, 32]."""
+        p = np.ascontiguousarray(points_wire, dtype=np.uint64).reshape(-1, 8)
+        out = np.zeros((p.shape[0], 32), dtype=np.uint8)
+        self.call("eon_g1_compress", p, p.shape[0], out, int(enc))
+        return out
+
+    def g1_from_bytes(self, data, enc=G1_ENC_HALO2):
+        """Deserialize for G1 for a batch: uint8 [n, 32] -> uint64 [n, 8]; raises InvalidG1Point."""
+        b = np.ascontiguousarray(data, dtype=np.uint8).reshape(-1, 32)
+        out = np.zeros((b.shape[0], 8), dtype=np.uint64)
+        bad = C.c_size_t(0)
+        try:
+            self.call("eon_g1_decompress", b, b.shape[0], out, int(enc), C.byref(bad))
+        except InvalidG1Point as e:
+            e.index = int(bad.value)
+            raise
+        return out
+
+    def srs_load_compressed(self, data, enc=G1_ENC_HALO2):
+        """g1_powers of a deserialised StructuredReferenceString (kzg/src/params.rs:56-77) as 32-byte
+        compressed points, decompressed on the device into the resident SRS."""
+        b = np.ascontiguousarray(data, dtype=np.uint8).reshape(-1, 32)
+        bad = C.c_size_t(0)
+        try:
+            self.call("eon_srs_load_compressed", b, b.shape[0], int(enc), C.byref(bad))
+        except InvalidG1Point as e:
+            e.index = int(bad.value)
+            raise
 
     def dev_alloc(self, nbytes):
         p = C.c_void_p()

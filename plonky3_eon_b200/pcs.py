@@ -88,6 +88,20 @@ class MatrixProverData:
             self.handle = 0
 
 
+def observe_commitment(commitment, ctx=None, enc=0):
+    """What `CanObserve<KzgCommitment> for DuplexChallenger` feeds the sponge (kzg/src/pcs.rs:409-438): every
+    column commitment of every matrix -> its 32 compressed bytes (G1::to_bytes) -> four little-endian u64 ->
+    `Fr::from_u64`.  Returns the canonical integers in observation order (a Fr challenger absorbs them
+    as-is; the permutation itself is out of scope).  `commitment` = list of uint64 [w, 8]
+    arrays as returned by GpuKzgPcs.commit."""
+    ctx = ctx or default_context()
+    out = []
+    for cols in commitment:
+        b = ctx.g1_to_bytes(cols, enc)
+        out.extend(int(v) for v in b.view("<u8").reshape(-1))
+    return out
+
+
 class GpuKzgPcs:
     ZK = False  # pcs.rs:216
 
@@ -113,6 +127,19 @@ class GpuKzgPcs:
         a = np.ascontiguousarray(g1_powers_wire, dtype=np.uint64).reshape(-1, 8)
         self.ctx.call("eon_srs_load_affine", a, a.shape[0])
         return self
+
+    @classmethod
+    def from_srs_bytes(cls, g1_powers_bytes, ctx=None, device=0, enc=0):
+        """A deserialised StructuredReferenceString (serde, kzg/src/params.rs:56): g1_powers as uint8 [n, 32]
+        compressed points (Serialize for G1, bn254/src/curve.rs:84-88).  Decompression (one Fq square root per
+        point) runs on the device; raises InvalidG1Point like serde's "Invalid G1 point"."""
+        self = cls(ctx, device)
+        self.ctx.srs_load_compressed(g1_powers_bytes, enc)
+        return self
+
+    def g1_powers_bytes(self, first=0, n=None, enc=0):
+        """Serialize for G1 over g1_powers[first : first + n]."""
+        return self.ctx.g1_to_bytes(self.g1_powers(first, n), enc)
 
     @classmethod
     def new(cls, max_degree, alpha, ctx=None, device=0):

@@ -57,6 +57,11 @@ def main():
     commits2, pdata2 = kzg.commit(srs, [((sh, 3), ev)], fast=False)
     out["kzg_shift"] = fr.to_wire([sh])
     out["kzg_commit_shifted"] = g1.to_wire(commits2[0])
+    # compressed encodings (G1::to_bytes): the first SRS powers, the commitments, the identity and -G
+    pts = list(srs[:6]) + list(commits[0]) + [None, g1.neg(g1.G)]
+    out["g1_points"] = g1.to_wire(pts)
+    out["g1_bytes_halo2"] = np.frombuffer(b"".join(g1.to_bytes(p, g1.ENC_HALO2) for p in pts), dtype=np.uint8).reshape(-1, 32)
+    out["g1_bytes_legacy"] = np.frombuffer(b"".join(g1.to_bytes(p, g1.ENC_LEGACY) for p in pts), dtype=np.uint8).reshape(-1, 32)
     np.savez_compressed(os.path.join(os.path.dirname(os.path.abspath(__file__)), "kzg_small.npz"), **out)
     print("wrote kzg_small.npz:", {k: v.shape for k, v in out.items()})
 

@@ -2,9 +2,12 @@
 import numpy as np
 import pytest
 
+import os
+
 from oracle import dft, fr, g1, kzg
 
 P = fr.P
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "kzg_small.npz")
 
 
 def L(x):
@@ -252,3 +255,51 @@ def test_mmcs_local_index_mixed_heights():
     assert kzg.mmcs_local_index(5, 2, 3) == 1
     assert kzg.mmcs_local_index(7, 6, 3) == 1      # log2_ceil(6) = 3 -> 7 % 6
     assert kzg.mmcs_local_index(3, 1, 3) == 0
+
+
+# ---- compressed G1 encoding (bn254/src/curve.rs:84-98,136-139 -> halo2curves GroupEncoding) ------------
+@pytest.mark.parametrize("enc", [g1.ENC_HALO2, g1.ENC_LEGACY])
+def test_g1_compressed_known_points(enc):
+    sign_bit = 0x40 if enc == g1.ENC_HALO2 else 0x80
+    # generator (1, 2): x = 1, y even
+    assert g1.to_bytes(g1.G, enc) == bytes([1] + [0] * 31)
+    # -G = (1, q - 2): q is odd, so y is odd -> sign bit set
+    b = g1.to_bytes(g1.neg(g1.G), enc)
+    assert b[0] == 1 and b[31] == sign_bit and not any(b[1:31])
+    ident = g1.to_bytes(None, enc)
+    assert ident == (bytes(31) + b"\x80" if enc == g1.ENC_HALO2 else bytes(32))
+    for p in (g1.G, g1.neg(g1.G), None, g1.mul(g1.G, 5377), g1.mul(g1.G, fr.P - 1)):
+        assert g1.from_bytes(g1.to_bytes(p, enc), enc) == p
+
+
+@pytest.mark.parametrize("enc", [g1.ENC_HALO2, g1.ENC_LEGACY])
+def test_g1_compressed_roundtrip_and_rejects(enc):
+    rng = np.random.default_rng(77)
+    for _ in range(40):
+        p = g1.mul(g1.G, int.from_bytes(rng.bytes(32), "little"))
+        b = g1.to_bytes(p, enc)
+        assert len(b) == 32 and g1.from_bytes(b, enc) == p
+        # the other sign bit gives the negated point
+        flip = bytearray(b)
+        flip[31] ^= 0x40 if enc == g1.ENC_HALO2 else 0x80
+        assert g1.from_bytes(bytes(flip), enc) == g1.neg(p)
+    # x = 4: 4^3 + 3 = 67 is not a square mod q -> rejected; x >= q -> rejected
+    assert pow(67, (g1.Q - 1) // 2, g1.Q) == g1.Q - 1
+    with pytest.raises(ValueError):
+        g1.from_bytes(bytes([4] + [0] * 31), enc)
+    with pytest.raises(ValueError):
+        g1.from_bytes(g1.Q.to_bytes(32, "little"), enc)
+    if enc == g1.ENC_HALO2:
+        with pytest.raises(ValueError):   # identity flag with other bits set
+            g1.from_bytes(bytes([1] + [0] * 30 + [0x80]), enc)
+        with pytest.raises(ValueError):
+            g1.from_bytes(bytes(31) + b"\xc0", enc)
+
+
+def test_g1_compressed_golden():
+    g = np.load(GOLD)
+    pts = g1.from_wire(g["g1_points"])
+    for enc, key in ((g1.ENC_HALO2, "g1_bytes_halo2"), (g1.ENC_LEGACY, "g1_bytes_legacy")):
+        for p, row in zip(pts, g[key]):
+            assert g1.to_bytes(p, enc) == row.tobytes()
+            assert g1.from_bytes(row.tobytes(), enc) == p
