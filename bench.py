@@ -225,6 +225,8 @@ def run_eon(args):
     pcs = eon.GpuKzgPcs.new(rows - 1, ALPHA, ctx=ctx)           # synthetic SRS alpha^i * G on the device
     if args.window_bits >= 0:                                    # default: the library's own table policy
         ctx.call("eon_srs_set_window_tables", args.window_bits)
+    if args.slice_schedule >= 0:                                 # default: the library's own policy
+        ctx.call("eon_msm_set_slice_schedule", args.slice_schedule)
     shift_one = field.to_wire(1)
     shift_lde = field.to_wire(SHIFT_LDE)
 
@@ -698,6 +700,8 @@ def main():
     ap.add_argument("--warmup-ref", type=int, default=0)
     ap.add_argument("--window-bits", type=int, default=-1,
                     help="MSM window tables: -1 library default, 0 none (plain c=16), 8..20 explicit")
+    ap.add_argument("--slice-schedule", type=int, default=-1,
+                    help="MSM round 0 walked by 64 MiB table slice: 1 on, 0 off, -1 the library's policy")
     ap.add_argument("--workload", default="commit", choices=["commit", "msm", "open", "prove-pcs"],
                     help="commit: KZG commit + LDE (the headline metric); msm: standalone MSM (configs[2]); "
                          "open: KzgPcs::open at 2 points")

@@ -145,6 +145,11 @@ int eon_msm_set_rounds(eon_ctx* ctx, int rounds);
 /* how entries are sorted by bucket: 0 = one pass of global atomics, 1 = coarse + fine coalesced
  * passes (csrc/msm_sort.cu), -1 = automatic.  Results are identical either way. */
 int eon_msm_set_sort_mode(eon_ctx* ctx, int mode);
+/* order in which round 0 of the pairwise rounds walks its pairs: 1 = by 64 MiB slice of the base table
+ * (the gathers of a multi-column commit then hit the L2 instead of DRAM; csrc/msm_tree.cu), 0 = in slot
+ * order, -1 = automatic (slices when the table exceeds the L2 and every base is used by several columns).
+ * Results are identical either way. */
+int eon_msm_set_slice_schedule(eon_ctx* ctx, int mode);
 /* rounds the most recent MSM on this context actually used */
 unsigned eon_msm_rounds_used(const eon_ctx* ctx);
 /* copy SRS points [first, first + n) back to the host as affine wire points */

@@ -384,6 +384,13 @@ int eon_msm_set_sort_mode(eon_ctx* ctx, int mode) {
   return EON_OK;
 }
 
+int eon_msm_set_slice_schedule(eon_ctx* ctx, int mode) {
+  if (!ctx || mode < -1 || mode > 1) return EON_ERR_BAD_ARG;
+  Lock lk(ctx);
+  ctx->msm_slice_mode = mode;
+  return EON_OK;
+}
+
 unsigned eon_msm_rounds_used(const eon_ctx* ctx) { return ctx ? ctx->msm_rounds_used : 0; }
 
 int eon_msm_set_rounds(eon_ctx* ctx, int rounds) {

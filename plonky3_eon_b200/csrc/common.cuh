@@ -79,6 +79,7 @@ enum ScratchId {
   SC_MSM_SORT_PAY,
   SC_MSM_SORT_KEY,
   SC_MSM_SEGTOTAL,
+  SC_MSM_SLICE,
   SC_IO_A,
   SC_IO_B,
   SC_QUOT,
@@ -108,6 +109,7 @@ struct eon_ctx {
   // batched-affine pairwise rounds before the XYZZ finisher: -1 = automatic (msm_pick_rounds)
   int msm_rounds = -1;
   int msm_sort_mode = -1;        // -1 automatic, 0 one-pass atomic scatter, 1 two-pass coalesced sort
+  int msm_slice_mode = -1;       // round 0 of the pairwise rounds by table slice: -1 automatic, 0 off, 1 on
   unsigned msm_rounds_used = 0;  // rounds of the most recent MSM (reporting)
 
   // second stream + events: the host-buffer entry points move column groups over PCIe while the

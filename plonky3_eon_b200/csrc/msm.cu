@@ -454,6 +454,9 @@ static int msm_batch(eon_ctx* ctx, const G1Affine* d_bases, const Fr* d_scalars,
   if (grid_pts_sz > 0x7fffffffull) return fail(ctx, EON_ERR_BAD_ARG, "msm: grid too large");
   const unsigned grid_pts = (unsigned)grid_pts_sz;
 
+  const SlicePlan plan = msm_slice_plan(ctx, sh.merged ? (u64)sh.W * sh.tab_stride : (u64)n, (u64)nseg * sh.seg_cap,
+                                        sh.rounds);
+
   phase_begin(ctx, PH_MSM_DIGITS);
   EON_CUDA(ctx, cudaMemsetAsync(p_hist, 0, total_buckets * sizeof(u32), st));
   EON_CUDA(ctx, cudaMemsetAsync(d_ntasks, 0, sizeof(u32), st));
@@ -478,8 +481,8 @@ static int msm_batch(eon_ctx* ctx, const G1Affine* d_bases, const Fr* d_scalars,
     const int mode = ctx->msm_sort_mode >= 0 ? ctx->msm_sort_mode : env_mode;
     int rc = 1;
     if (mode != 0 && (mode == 1 || n >= 4096))  // two coalesced passes (msm_sort.cu); small inputs: one pass
-      rc = msm_sort_entries(ctx, d_scalars, n, ncols, ld, sh, (const u32*)p_hist, (const u32*)p_segtot, (u32*)p_cur,
-                            (u32*)p_ent);
+      rc = msm_sort_entries(ctx, d_scalars, n, ncols, ld, sh, plan, (const u32*)p_hist, (const u32*)p_segtot,
+                            (u32*)p_cur, (u32*)p_ent);
     if (rc < 0) return rc;
     if (rc > 0) {
       k_msm_scatter<<<grid_pts, MSM_THREADS, 0, st>>>(d_scalars, n, ld, (u32)ncols, sh, (u32*)p_cur, (u32*)p_ent);
@@ -496,7 +499,8 @@ static int msm_batch(eon_ctx* ctx, const G1Affine* d_bases, const Fr* d_scalars,
     src.seg_cap = sh.seg_cap;
     src.pts = nullptr;
     src.rshift = sh.rounds;
-    if (sh.rounds) EON_TRY(msm_tree_rounds(ctx, d_bases, (const u32*)p_ent, (u64)nseg * sh.seg_cap, sh.rounds, &src.pts));
+    if (sh.rounds)
+      EON_TRY(msm_tree_rounds(ctx, d_bases, plan, (const u32*)p_ent, (u64)nseg * sh.seg_cap, sh.rounds, &src.pts));
     phase_begin(ctx, PH_MSM_FINISH);
     k_msm_order<<<(unsigned)nseg, 1024, 0, st>>>((const u32*)p_hist, (const u32*)p_cur, sh.NB, sh.rounds, (u32*)p_ord);
     EON_LAUNCHED(ctx);

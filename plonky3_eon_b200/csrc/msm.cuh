@@ -29,8 +29,17 @@ constexpr u32 ENTRY_NONE = 0xffffffffu;  // unused entry slot (reads as the iden
 // R rounds of out[j] = in[2j] + in[2j+1] over the flat slot array (all segments), affine with one
 // shared inversion per round.  Round 0 reads entries/bases, later rounds read points.  On return
 // *out_pts points to the final array of (total_slots >> rounds) affine points.
-int msm_tree_rounds(eon_ctx* ctx, const G1Affine* d_bases, const u32* d_entries, u64 total_slots, u32 rounds,
-                    const G1Affine** out_pts);
+// Slice schedule of round 0 (msm_tree.cu): the base table is cut into slices of 2^shift points and the pairs
+// are processed slice by slice, so their gathers hit the L2.  on = false: slot order.
+struct SlicePlan {
+  bool on;
+  u32 shift;
+  u32 nbins;
+};
+// nbases = number of points addressable through d_bases (all window-table levels).
+SlicePlan msm_slice_plan(const eon_ctx* ctx, u64 nbases, u64 total_slots, u32 rounds);
+int msm_tree_rounds(eon_ctx* ctx, const G1Affine* d_bases, const SlicePlan& plan, const u32* d_entries,
+                    u64 total_slots, u32 rounds, const G1Affine** out_pts);
 
 
 // Counting sort of the (point, window) entries by bucket in two coalesced passes (msm_sort.cu):
@@ -39,8 +48,10 @@ int msm_tree_rounds(eon_ctx* ctx, const G1Affine* d_bases, const u32* d_entries,
 // segment).  Out: entries[] sorted by bucket,
 // ends[g] = starts[g] + count(g).  Returns EON_OK, or a positive value if the shape is not supported
 // (caller falls back to the one-pass atomic scatter).
+// plan.on: the entries of every bucket are additionally ordered by table slice (so that round 0 pairs operands
+// of the same slice); any order inside a bucket gives the same sums.
 int msm_sort_entries(eon_ctx* ctx, const Fr* d_scalars, size_t n, size_t ncols, size_t ld, const MsmShape& sh,
-                     const u32* d_starts, const u32* d_seg_total, u32* d_ends, u32* d_entries);
+                     const SlicePlan& plan, const u32* d_starts, const u32* d_seg_total, u32* d_ends, u32* d_entries);
 
 #if defined(__CUDACC__)
 // ---- 1. scalar -> signed window digits --------------------------------------------------------

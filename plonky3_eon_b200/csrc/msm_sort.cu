@@ -163,14 +163,20 @@ k_sort_coarse(const Fr* __restrict__ scalars, size_t n, size_t ld, u32 ncols, Ms
 // region_cursor) and owns the window [starts[k << fb], starts[(k + 1) << fb]) of the final array.
 // Windows up to SORT_WIN_CAP slots are built in shared memory (padding = ENTRY_NONE) and written out
 // coalesced; larger ones (skewed scalars, very large inputs) are scattered directly.
+// ORDERED: inside every bucket the entries are additionally ordered by table slice (base index >> slice_shift,
+// ns slices), so that round 0 of the pairwise rounds pairs operands of the same slice (msm_tree.cu): a first
+// sweep counts per (bucket, slice), the second places.  Any order inside a bucket gives the same bucket sum.
+template <bool ORDERED>
 __global__ void __launch_bounds__(SORT_FINE_THREADS)
 k_sort_fine(const u32* __restrict__ tmp_pay, const unsigned short* __restrict__ tmp_key,
             const u32* __restrict__ region_cursor, const u32* __restrict__ starts, const u32* __restrict__ seg_total,
-            u32 NB, u32 nbins, u32 fb, u64 seg_cap, u32* __restrict__ ends, u32* __restrict__ entries) {
+            u32 NB, u32 nbins, u32 fb, u64 seg_cap, u32 slice_shift, u32 ns, u32* __restrict__ ends,
+            u32* __restrict__ entries) {
   extern __shared__ u32 smem[];
   const u32 fine = 1u << fb;
   u32* s_cur = smem;          // fine
   u32* s_win = smem + fine;   // SORT_WIN_CAP
+  u32* s_cnt2 = s_win + SORT_WIN_CAP;  // ORDERED: fine * ns (bucket, slice) counters, then cursors
   const size_t seg = blockIdx.x / nbins;
   const u32 k = blockIdx.x % nbins;
   const size_t g0 = seg * NB + ((size_t)k << fb);
@@ -184,13 +190,40 @@ k_sort_fine(const u32* __restrict__ tmp_pay, const unsigned short* __restrict__ 
   const bool staged = wlen <= SORT_WIN_CAP;
   if (staged)
     for (u32 j = tid; j < wlen; j += SORT_FINE_THREADS) s_win[j] = ENTRY_NONE;
-  __syncthreads();
-  for (u32 i = begin + tid; i < end; i += SORT_FINE_THREADS) {
-    u32 key = tmp_key[off + i];
-    u32 pay = tmp_pay[off + i];
-    u32 pos = smem_rank(s_cur, key);
-    if (staged) s_win[pos - begin] = pay;
-    else entries[off + pos] = pay;
+  if (ORDERED && staged) {
+    for (u32 j = tid; j < fine * ns; j += SORT_FINE_THREADS) s_cnt2[j] = 0;
+    __syncthreads();
+    for (u32 i = begin + tid; i < end; i += SORT_FINE_THREADS) {
+      const u32 key = tmp_key[off + i];
+      const u32 sl = min((tmp_pay[off + i] & ~SIGN_BIT) >> slice_shift, ns - 1);
+      atomicAdd(&s_cnt2[key * ns + sl], 1u);
+    }
+    __syncthreads();
+    for (u32 f = tid; f < fine; f += SORT_FINE_THREADS) {
+      u32 run = s_cur[f];
+      for (u32 q = 0; q < ns; q++) {
+        const u32 c = s_cnt2[f * ns + q];
+        s_cnt2[f * ns + q] = run;
+        run += c;
+      }
+      s_cur[f] = run;  // the bucket's end
+    }
+    __syncthreads();
+    for (u32 i = begin + tid; i < end; i += SORT_FINE_THREADS) {
+      const u32 key = tmp_key[off + i];
+      const u32 pay = tmp_pay[off + i];
+      const u32 sl = min((pay & ~SIGN_BIT) >> slice_shift, ns - 1);
+      s_win[smem_rank(s_cnt2, key * ns + sl) - begin] = pay;
+    }
+  } else {
+    __syncthreads();
+    for (u32 i = begin + tid; i < end; i += SORT_FINE_THREADS) {
+      u32 key = tmp_key[off + i];
+      u32 pay = tmp_pay[off + i];
+      u32 pos = smem_rank(s_cur, key);
+      if (staged) s_win[pos - begin] = pay;
+      else entries[off + pos] = pay;
+    }
   }
   __syncthreads();
   if (staged)
@@ -200,8 +233,10 @@ k_sort_fine(const u32* __restrict__ tmp_pay, const unsigned short* __restrict__ 
 
 static bool g_sort_attr_set = false;
 
+constexpr u32 SORT_MAX_SLICES = 32;  // ordered fine pass: (bucket, slice) counters of a bin in shared memory
+
 int msm_sort_entries(eon_ctx* ctx, const Fr* d_scalars, size_t n, size_t ncols, size_t ld, const MsmShape& sh,
-                     const u32* d_starts, const u32* d_seg_total, u32* d_ends, u32* d_entries) {
+                     const SlicePlan& plan, const u32* d_starts, const u32* d_seg_total, u32* d_ends, u32* d_entries) {
   // Worth it only while a tile still fills runs of tens of entries per bin (<= 1024 bins per tile) and a
   // bin's window fits the shared-memory image; otherwise (2^22+ points per column at c = 20, or many
   // bucket sets per column) the one-pass scatter is faster (measured: 2^24 x 1, 4.2 vs 14.6 ms).
@@ -229,8 +264,10 @@ int msm_sort_entries(eon_ctx* ctx, const Fr* d_scalars, size_t n, size_t ncols, 
                                        (int)(SORT_COARSE_SMEM + 16)));
     EON_CUDA(ctx, cudaFuncSetAttribute(k_sort_coarse<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)(SORT_COARSE_SMEM + 16)));
-    EON_CUDA(ctx, cudaFuncSetAttribute(k_sort_fine, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    EON_CUDA(ctx, cudaFuncSetAttribute(k_sort_fine<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)(((size_t)(1u << 12) + SORT_WIN_CAP) * sizeof(u32))));
+    EON_CUDA(ctx, cudaFuncSetAttribute(k_sort_fine<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)(((size_t)(1u << 7) * (1 + SORT_MAX_SLICES) + SORT_WIN_CAP) * sizeof(u32))));
     g_sort_attr_set = true;
   }
   void *p_reg, *p_pay, *p_key;
@@ -248,9 +285,15 @@ int msm_sort_entries(eon_ctx* ctx, const Fr* d_scalars, size_t n, size_t ncols, 
     k_sort_coarse<false><<<(unsigned)(tiles * ncols), SORT_THREADS, smem_coarse, st>>>(
         d_scalars, n, ld, (u32)ncols, sh, nbins, fb, tile, (u32*)p_reg, (u32*)p_pay, (unsigned short*)p_key);
   EON_LAUNCHED(ctx);
-  k_sort_fine<<<(unsigned)total_bins, SORT_FINE_THREADS, smem_fine, st>>>(
-      (const u32*)p_pay, (const unsigned short*)p_key, (const u32*)p_reg, d_starts, d_seg_total, sh.NB, nbins, fb,
-      sh.seg_cap, d_ends, d_entries);
+  static const int order_env = getenv("EON_SORT_ORDERED") ? atoi(getenv("EON_SORT_ORDERED")) : 1;
+  if (plan.on && plan.nbins > 1 && plan.nbins <= SORT_MAX_SLICES && order_env)
+    k_sort_fine<true><<<(unsigned)total_bins, SORT_FINE_THREADS, smem_fine + ((size_t)plan.nbins << fb) * sizeof(u32), st>>>(
+        (const u32*)p_pay, (const unsigned short*)p_key, (const u32*)p_reg, d_starts, d_seg_total, sh.NB, nbins, fb,
+        sh.seg_cap, plan.shift, plan.nbins, d_ends, d_entries);
+  else
+    k_sort_fine<false><<<(unsigned)total_bins, SORT_FINE_THREADS, smem_fine, st>>>(
+        (const u32*)p_pay, (const unsigned short*)p_key, (const u32*)p_reg, d_starts, d_seg_total, sh.NB, nbins, fb,
+        sh.seg_cap, 0u, 1u, d_ends, d_entries);
   EON_LAUNCHED(ctx);
   return EON_OK;
 }

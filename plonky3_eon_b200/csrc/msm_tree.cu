@@ -24,6 +24,8 @@
 // so the group law stays complete and the final affine sums are the same unique group elements.
 #include <stdlib.h>
 
+#include <algorithm>
+
 #include "msm.cuh"
 
 namespace eon {
@@ -61,6 +63,11 @@ struct Operand {
   const G1Affine* p;  // null: ENTRY_NONE
   bool neg;
   Fq x;
+  __device__ __forceinline__ void open_entry(const G1Affine* bases, u32 v) {
+    neg = (v & SIGN_BIT) != 0;
+    p = (v == ENTRY_NONE) ? nullptr : bases + (v & ~SIGN_BIT);
+    x = p ? ldg_fq(&p->x) : Fq::zero();
+  }
   __device__ __forceinline__ void open(const TreeSrc& s, u64 slot) {
     if (R0) {
       u32 v = __ldg(s.entries + slot);
@@ -160,6 +167,38 @@ __global__ void __launch_bounds__(TREE_THREADS) k_tree_down(Fq* __restrict__ T, 
   st_fq(T + i0, inv);
 }
 
+// Sum of one pair given the shared inverse chain: inv = 1 / (d_0 ... d_i) on entry, 1 / (d_0 ... d_(i-1)) on
+// exit (unchanged for a trivial pair); pre = d_0 ... d_(i-1) (read only for a non-trivial pair).
+template <bool R0>
+__device__ __forceinline__ G1Affine pair_sum(const Operand<R0>& P, const Operand<R0>& Q, int kind, const Fq& d,
+                                             Fq& inv, const Fq* pre_ptr) {
+  G1Affine r;
+  if (kind == PAIR_TRIVIAL) {
+    const bool pid = P.is_identity(), qid = Q.is_identity();
+    if (pid && !qid) { r.x = Q.x; r.y = Q.y(); }
+    else if (qid && !pid) { r.x = P.x; r.y = P.y(); }
+    else r = G1Affine::identity();  // both identity, or P == -Q
+  } else {
+    const Fq pre = ldg_fq(pre_ptr);
+    const Fq dinv = fp_mul(inv, pre);  // pre == 1 (Montgomery one) for the first non-trivial pair
+    inv = fp_mul(inv, d);
+    const Fq py = P.y();
+    Fq lam;
+    Fq xsum;
+    if (kind == PAIR_ADD) {
+      lam = fp_mul(fp_sub(Q.y(), py), dinv);
+      xsum = fp_add(P.x, Q.x);
+    } else {
+      Fq xx = fp_sqr(P.x);
+      lam = fp_mul(fp_add(fp_dbl(xx), xx), dinv);
+      xsum = fp_dbl(P.x);
+    }
+    r.x = fp_sub(fp_sqr(lam), xsum);
+    r.y = fp_sub(fp_mul(lam, fp_sub(P.x, r.x)), py);
+  }
+  return r;
+}
+
 template <bool R0, int TREE_B>
 __global__ void __launch_bounds__(TREE_THREADS, 4)
 k_tree_bwd(TreeSrc src, u64 npairs, const Fq* __restrict__ T0inv, const Fq* __restrict__ pre_all,
@@ -177,32 +216,188 @@ k_tree_bwd(TreeSrc src, u64 npairs, const Fq* __restrict__ T0inv, const Fq* __re
     Q.open(src, 2 * (j0 + i) + 1);
     Fq d;
     const int kind = pair_denominator<R0>(P, Q, d);
-    G1Affine r;
-    if (kind == PAIR_TRIVIAL) {
-      const bool pid = P.is_identity(), qid = Q.is_identity();
-      if (pid && !qid) { r.x = Q.x; r.y = Q.y(); }
-      else if (qid && !pid) { r.x = P.x; r.y = P.y(); }
-      else r = G1Affine::identity();  // both identity, or P == -Q
-    } else {
-      const Fq pre = ldg_fq(pre_all + j0 + i);
-      const Fq dinv = fp_mul(inv, pre);  // pre == 1 (Montgomery one) for the first non-trivial pair
-      inv = fp_mul(inv, d);
-      const Fq py = P.y();
-      Fq lam;
-      Fq xsum;
-      if (kind == PAIR_ADD) {
-        lam = fp_mul(fp_sub(Q.y(), py), dinv);
-        xsum = fp_add(P.x, Q.x);
-      } else {
-        Fq xx = fp_sqr(P.x);
-        lam = fp_mul(fp_add(fp_dbl(xx), xx), dinv);
-        xsum = fp_dbl(P.x);
-      }
-      r.x = fp_sub(fp_sqr(lam), xsum);
-      r.y = fp_sub(fp_mul(lam, fp_sub(P.x, r.x)), py);
-    }
+    const G1Affine r = pair_sum<R0>(P, Q, kind, d, inv, pre_all + j0 + i);
     st_fq(&out[j0 + i].x, r.x);
     st_fq(&out[j0 + i].y, r.y);
+  }
+}
+
+
+// ---- round 0 scheduled by table slice ("slice schedule") ------------------------------------------------
+// With window tables every base is used once per column, but the entries are sorted by bucket, so the round-0
+// gathers of a commit walk the whole table (15 x 64 MiB at 2^20 points) at random: 47-50 G accesses/s from
+// DRAM against 227 G/s (x only; 127 G/s for x and y) when the working set fits the L2, which holds up to
+// ~80 MiB at full rate (tools/probes/l2_gather_probe.cu, profiles/r01j_l2_gather_probe.log).  The bucket sums
+// do not depend on which entries of a bucket are paired nor on the order in which pairs are processed, so:
+//   1. the sort orders the entries of every bucket by table slice (2^19 points = 32 MiB; k_sort_fine<true>),
+//      so that most pairs take both operands from the same slice;
+//   2. a pair record (entry0, entry1, destination slot) is appended to the list of the slice of its first
+//      operand (tile-local counting sort, k_pair_hist / k_pair_scatter);
+//   3. k_tree_fwd_sliced / k_tree_bwd_sliced walk the records in that order with coalesced record reads: at
+//      any time the in-flight pairs gather from one or two slices, which stay L2-resident.
+// Each result is written to the slot the slot-order schedule would have used, so rounds >= 1 and the finisher
+// are unchanged.  Measured at 2^20 x 16 (B200): tree fwd 9.9 -> 6.4 ms, tree bwd 18.9 -> 18.2 ms, step
+// 51.6 -> 47.2 ms; without step 1 only 51.6 -> 50.8 ms (the second operand's random gathers evict the slice).
+constexpr u32 SLICE_MAX_BINS = 1024;
+constexpr int PAIR_TILE = 2048;         // pairs per CTA of the record sort (256 threads x 8)
+
+__device__ __forceinline__ u32 pair_bin(u32 e0, u32 e1, u32 shift) {
+  const u32 v = (e0 != ENTRY_NONE) ? e0 : e1;
+  return (v == ENTRY_NONE) ? 0u : ((v & ~SIGN_BIT) >> shift);
+}
+
+__global__ void __launch_bounds__(256) k_pair_hist(const uint2* __restrict__ pairs, u64 npairs, u32 nbins, u32 shift,
+                                                   unsigned long long* __restrict__ counts) {
+  __shared__ u32 h[SLICE_MAX_BINS];
+  for (u32 b = threadIdx.x; b < nbins; b += blockDim.x) h[b] = 0;
+  __syncthreads();
+  const u64 base = (u64)blockIdx.x * PAIR_TILE;
+#pragma unroll
+  for (int i = 0; i < PAIR_TILE / 256; i++) {
+    const u64 j = base + i * 256 + threadIdx.x;
+    if (j < npairs) {
+      const uint2 e = __ldg(pairs + j);
+      atomicAdd(&h[pair_bin(e.x, e.y, shift)], 1u);
+    }
+  }
+  __syncthreads();
+  for (u32 b = threadIdx.x; b < nbins; b += blockDim.x)
+    if (h[b]) atomicAdd(&counts[b], (unsigned long long)h[b]);
+}
+
+// counts[b] -> cursor[b] = exclusive prefix (one warp; nbins <= 1024)
+__global__ void k_pair_scan(const unsigned long long* __restrict__ counts, u32 nbins,
+                            unsigned long long* __restrict__ cursor) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    unsigned long long acc = 0;
+    for (u32 b = 0; b < nbins; b++) {
+      cursor[b] = acc;
+      acc += counts[b];
+    }
+  }
+}
+
+// Tile-local counting sort of the pair records by slice: the tile's records are grouped by bin in shared
+// memory, one global reservation per (tile, bin), then copied out so that consecutive threads write
+// consecutive records of a run.
+__global__ void __launch_bounds__(256) k_pair_scatter(const uint2* __restrict__ pairs, u64 npairs, u32 nbins, u32 shift,
+                                                      unsigned long long* __restrict__ cursor,
+                                                      uint2* __restrict__ rec_e, u32* __restrict__ rec_dest) {
+  __shared__ u32 h[SLICE_MAX_BINS];          // count, then the bin's first slot in the tile
+  __shared__ unsigned long long start[SLICE_MAX_BINS];
+  __shared__ uint2 s_e[PAIR_TILE];
+  __shared__ unsigned short s_bin[PAIR_TILE];
+  __shared__ unsigned short s_src[PAIR_TILE];  // index of the pair inside the tile
+  __shared__ u32 s_warp[8];
+  const u32 tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  for (u32 b = tid; b < nbins; b += 256) h[b] = 0;
+  __syncthreads();
+  const u64 base = (u64)blockIdx.x * PAIR_TILE;
+  uint2 e[PAIR_TILE / 256];
+  u32 rank[PAIR_TILE / 256], bin[PAIR_TILE / 256];
+#pragma unroll
+  for (int i = 0; i < PAIR_TILE / 256; i++) {
+    const u64 j = base + i * 256 + tid;
+    if (j < npairs) {
+      e[i] = __ldg(pairs + j);
+      bin[i] = pair_bin(e[i].x, e[i].y, shift);
+      rank[i] = atomicAdd(&h[bin[i]], 1u);
+    }
+  }
+  __syncthreads();
+  // exclusive scan of the bin counts (each thread owns a contiguous strip) + one global reservation per bin
+  {
+    const u32 per = (nbins + 255) / 256;
+    const u32 b0 = tid * per, b1 = min(nbins, b0 + per);
+    u32 sum = 0;
+    for (u32 b = b0; b < b1; b++) sum += h[b];
+    u32 x = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      u32 y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= (u32)o) x += y;
+    }
+    if (lane == 31) s_warp[wid] = x;
+    __syncthreads();
+    u32 run = x - sum;
+    for (u32 w = 0; w < wid; w++) run += s_warp[w];
+    for (u32 b = b0; b < b1; b++) {
+      const u32 c = h[b];
+      if (c) start[b] = atomicAdd(&cursor[b], (unsigned long long)c) - run;  // global slot of tile slot 0 of this bin
+      h[b] = run;
+      run += c;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < PAIR_TILE / 256; i++) {
+    const u64 j = base + i * 256 + tid;
+    if (j < npairs) {
+      const u32 slot = h[bin[i]] + rank[i];
+      // the operand that selected the slice goes first (identity + P = P + identity)
+      s_e[slot] = (e[i].x != ENTRY_NONE) ? e[i] : make_uint2(e[i].y, e[i].x);
+      s_bin[slot] = (unsigned short)bin[i];
+      s_src[slot] = (unsigned short)(i * 256 + tid);
+    }
+  }
+  __syncthreads();
+  const u32 cnt = (u32)min((u64)PAIR_TILE, npairs - base);
+  for (u32 slot = tid; slot < cnt; slot += 256) {
+    const u64 k = start[s_bin[slot]] + slot;
+    rec_e[k] = s_e[slot];
+    rec_dest[k] = (u32)(base + s_src[slot]);
+  }
+}
+
+// Thread `tid` of CTA `b` owns the records b * 128 * B + i * 128 + tid, i < B (coalesced record reads);
+// its denominators are chained in that order by both kernels.
+template <int TREE_B>
+__global__ void __launch_bounds__(TREE_THREADS)
+k_tree_fwd_sliced(const uint2* __restrict__ rec_e, u64 npairs, const G1Affine* __restrict__ bases,
+                  Fq* __restrict__ T0, Fq* __restrict__ pre) {
+  const u64 k0 = (u64)blockIdx.x * (TREE_THREADS * TREE_B) + threadIdx.x;
+  Fq run = Fq::one();
+  bool any = false;
+#pragma unroll 1
+  for (int i = 0; i < TREE_B; i++) {
+    const u64 k = k0 + (u64)i * TREE_THREADS;
+    if (k >= npairs) break;
+    st_fq(pre + k, run);
+    const uint2 e = __ldg(rec_e + k);
+    Operand<true> P, Q;
+    P.open_entry(bases, e.x);
+    Q.open_entry(bases, e.y);
+    Fq d;
+    if (pair_denominator<true>(P, Q, d) != PAIR_TRIVIAL) {
+      run = any ? fp_mul(run, d) : d;
+      any = true;
+    }
+  }
+  st_fq(T0 + (u64)blockIdx.x * TREE_THREADS + threadIdx.x, run);
+}
+
+template <int TREE_B>
+__global__ void __launch_bounds__(TREE_THREADS, 4)
+k_tree_bwd_sliced(const uint2* __restrict__ rec_e, const u32* __restrict__ rec_dest, u64 npairs,
+                  const G1Affine* __restrict__ bases, const Fq* __restrict__ T0inv, const Fq* __restrict__ pre_all,
+                  G1Affine* __restrict__ out) {
+  const u64 k0 = (u64)blockIdx.x * (TREE_THREADS * TREE_B) + threadIdx.x;
+  if (k0 >= npairs) return;
+  const int cnt = (int)min((u64)TREE_B, (npairs - k0 + TREE_THREADS - 1) / TREE_THREADS);
+  Fq inv = ldg_fq(T0inv + (u64)blockIdx.x * TREE_THREADS + threadIdx.x);
+#pragma unroll 1
+  for (int i = cnt - 1; i >= 0; i--) {
+    const u64 k = k0 + (u64)i * TREE_THREADS;
+    const uint2 e = __ldg(rec_e + k);
+    const u32 dest = __ldg(rec_dest + k);
+    Operand<true> P, Q;
+    P.open_entry(bases, e.x);
+    Q.open_entry(bases, e.y);
+    Fq d;
+    const int kind = pair_denominator<true>(P, Q, d);
+    const G1Affine r = pair_sum<true>(P, Q, kind, d, inv, pre_all + k);
+    st_fq(&out[dest].x, r.x);
+    st_fq(&out[dest].y, r.y);
   }
 }
 
@@ -231,8 +426,37 @@ static int tree_b() {
   return b;
 }
 
-int msm_tree_rounds(eon_ctx* ctx, const G1Affine* d_bases, const u32* d_entries, u64 total_slots, u32 rounds,
-                    const G1Affine** out_pts) {
+static int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+
+// Slice schedule (see k_tree_fwd_sliced): worth it when the bases do not fit the L2 and every base is gathered
+// several times per launch (one use per column with window tables).  eon_msm_set_slice_schedule /
+// EON_TREE_SLICED = 0 / 1 force it off / on; EON_SLICE_SHIFT = log2 of the points per slice.
+SlicePlan msm_slice_plan(const eon_ctx* ctx, u64 nbases, u64 total_slots, u32 rounds) {
+  static const int sliced_env = env_int("EON_TREE_SLICED", -1);
+  static const int shift_env = env_int("EON_SLICE_SHIFT", 19);
+  SlicePlan p;
+  p.shift = (shift_env >= 12 && shift_env <= 24) ? (u32)shift_env : 19u;
+  const u64 nbins = ((nbases ? nbases - 1 : 0) >> p.shift) + 1;
+  p.nbins = (u32)std::min<u64>(nbins, 0xffffffffull);
+  const int mode = ctx->msm_slice_mode >= 0 ? ctx->msm_slice_mode : sliced_env;
+  p.on = rounds > 0 && nbins <= SLICE_MAX_BINS && total_slots / 2 < 0xffffffffull;
+  if (mode == 0) p.on = false;
+  else if (mode != 1) p.on = p.on && nbases * sizeof(G1Affine) > (96ull << 20) && total_slots >= 4 * nbases;
+  return p;
+}
+
+template <int B>
+static void launch_sliced(bool fwd, unsigned grid, cudaStream_t st, const uint2* rec_e, const u32* rec_dest, u64 npairs,
+                          const G1Affine* bases, Fq* T0, Fq* pre, G1Affine* out) {
+  if (fwd) k_tree_fwd_sliced<B><<<grid, TREE_THREADS, 0, st>>>(rec_e, npairs, bases, T0, pre);
+  else k_tree_bwd_sliced<B><<<grid, TREE_THREADS, 0, st>>>(rec_e, rec_dest, npairs, bases, T0, pre, out);
+}
+
+int msm_tree_rounds(eon_ctx* ctx, const G1Affine* d_bases, const SlicePlan& plan, const u32* d_entries,
+                    u64 total_slots, u32 rounds, const G1Affine** out_pts) {
   const u64 TREE_B = (u64)tree_b();
   if (rounds == 0 || (total_slots & ((1ull << rounds) - 1)))
     return fail(ctx, EON_ERR_BAD_ARG, "msm_tree_rounds: slot count not aligned to 2^rounds");
@@ -242,8 +466,13 @@ int msm_tree_rounds(eon_ctx* ctx, const G1Affine* d_bases, const u32* d_entries,
   EON_TRY(scratch_get(ctx, SC_MSM_TREE_A, m0 * sizeof(G1Affine), &bufA));
   EON_TRY(scratch_get(ctx, SC_MSM_TREE_B, (m0 / 2 + 1) * sizeof(G1Affine), &bufB));
   // level sizes of round 0 (the largest round): n0 = ceil(m0 / B), n(l+1) = ceil(n(l) / 8)
+  static const int sliced_b_env = env_int("EON_TREE_SLICED_B", 32);
+  const u64 SLICED_B = (sliced_b_env == 8 || sliced_b_env == 16) ? (u64)sliced_b_env : 32;
+  const bool sliced = plan.on;
+  const u64 nbins = plan.nbins;
+  const u64 n0_sliced = ((m0 + TREE_THREADS * SLICED_B - 1) / (TREE_THREADS * SLICED_B)) * TREE_THREADS;
   u64 tcap = 0;
-  for (u64 n = (m0 + TREE_B - 1) / TREE_B;; n = (n + 7) / 8) {
+  for (u64 n = std::max((m0 + TREE_B - 1) / TREE_B, sliced ? n0_sliced : (u64)0);; n = (n + 7) / 8) {
     tcap += n;
     if (n <= TREE_TOP) break;
   }
@@ -257,18 +486,40 @@ int msm_tree_rounds(eon_ctx* ctx, const G1Affine* d_bases, const u32* d_entries,
   src.bases = d_bases;
   u64 npairs = m0;
   G1Affine* outs[2] = {(G1Affine*)bufA, (G1Affine*)bufB};
+  // pair records of the slice schedule live in round 1's output buffer, which is idle during round 0
+  // (12 bytes per pair against the 32 bytes per pair of that buffer)
+  uint2* rec_e = (uint2*)bufB;
+  u32* rec_dest = (u32*)(rec_e + m0);
   for (u32 r = 0; r < rounds; r++) {
     G1Affine* out = outs[r & 1];
+    const bool sl = sliced && r == 0;
     std::vector<std::pair<Fq*, u64>> lv;  // (array, size) per level
     Fq* T = (Fq*)bufT;
-    for (u64 n = (npairs + TREE_B - 1) / TREE_B;; n = (n + 7) / 8) {
+    for (u64 n = sl ? n0_sliced : (npairs + TREE_B - 1) / TREE_B;; n = (n + 7) / 8) {
       lv.push_back(std::make_pair(T, n));
       T += n;
       if (n <= TREE_TOP) break;
     }
     const unsigned g0 = grid_for(lv[0].second);
     phase_begin(ctx, PH_MSM_TREE_FWD);
-    if (TREE_B == 8) launch_fwd<8>(r == 0, g0, st, src, npairs, lv[0].first, (Fq*)bufP);
+    if (sl) {
+      void* bufC;
+      EON_TRY(scratch_get(ctx, SC_MSM_SLICE, 2 * SLICE_MAX_BINS * sizeof(unsigned long long), &bufC));
+      unsigned long long* counts = (unsigned long long*)bufC;
+      unsigned long long* cursor = counts + SLICE_MAX_BINS;
+      const unsigned gp = (unsigned)((npairs + PAIR_TILE - 1) / PAIR_TILE);
+      const uint2* pairs = reinterpret_cast<const uint2*>(d_entries);
+      EON_CUDA(ctx, cudaMemsetAsync(counts, 0, SLICE_MAX_BINS * sizeof(unsigned long long), st));
+      k_pair_hist<<<gp, 256, 0, st>>>(pairs, npairs, (u32)nbins, plan.shift, counts);
+      EON_LAUNCHED(ctx);
+      k_pair_scan<<<1, 32, 0, st>>>(counts, (u32)nbins, cursor);
+      EON_LAUNCHED(ctx);
+      k_pair_scatter<<<gp, 256, 0, st>>>(pairs, npairs, (u32)nbins, plan.shift, cursor, rec_e, rec_dest);
+      EON_LAUNCHED(ctx);
+      if (SLICED_B == 8) launch_sliced<8>(true, g0, st, rec_e, rec_dest, npairs, d_bases, lv[0].first, (Fq*)bufP, out);
+      else if (SLICED_B == 16) launch_sliced<16>(true, g0, st, rec_e, rec_dest, npairs, d_bases, lv[0].first, (Fq*)bufP, out);
+      else launch_sliced<32>(true, g0, st, rec_e, rec_dest, npairs, d_bases, lv[0].first, (Fq*)bufP, out);
+    } else if (TREE_B == 8) launch_fwd<8>(r == 0, g0, st, src, npairs, lv[0].first, (Fq*)bufP);
     else if (TREE_B == 16) launch_fwd<16>(r == 0, g0, st, src, npairs, lv[0].first, (Fq*)bufP);
     else launch_fwd<32>(r == 0, g0, st, src, npairs, lv[0].first, (Fq*)bufP);
     EON_LAUNCHED(ctx);
@@ -286,7 +537,11 @@ int msm_tree_rounds(eon_ctx* ctx, const G1Affine* d_bases, const u32* d_entries,
     }
     phase_end(ctx, PH_MSM_TREE_INV);
     phase_begin(ctx, PH_MSM_TREE_BWD);
-    if (TREE_B == 8) launch_bwd<8>(r == 0, g0, st, src, npairs, lv[0].first, (const Fq*)bufP, out);
+    if (sl) {
+      if (SLICED_B == 8) launch_sliced<8>(false, g0, st, rec_e, rec_dest, npairs, d_bases, lv[0].first, (Fq*)bufP, out);
+      else if (SLICED_B == 16) launch_sliced<16>(false, g0, st, rec_e, rec_dest, npairs, d_bases, lv[0].first, (Fq*)bufP, out);
+      else launch_sliced<32>(false, g0, st, rec_e, rec_dest, npairs, d_bases, lv[0].first, (Fq*)bufP, out);
+    } else if (TREE_B == 8) launch_bwd<8>(r == 0, g0, st, src, npairs, lv[0].first, (const Fq*)bufP, out);
     else if (TREE_B == 16) launch_bwd<16>(r == 0, g0, st, src, npairs, lv[0].first, (const Fq*)bufP, out);
     else launch_bwd<32>(r == 0, g0, st, src, npairs, lv[0].first, (const Fq*)bufP, out);
     EON_LAUNCHED(ctx);

@@ -20,11 +20,15 @@ def ctx():
     c.close()
 
 
-@pytest.fixture(params=[1, 2, 3, 5])
+# (rounds, slice schedule): the slice schedule (round 0 walked by 64 MiB table slice, msm_tree.cu) only
+# switches itself on for tables beyond the L2, so it is forced here to put every degenerate case through it
+@pytest.fixture(params=[(1, 0), (2, 0), (3, 0), (5, 0), (1, 1), (3, 1)], ids=lambda p: f"r{p[0]}{'s' if p[1] else ''}")
 def rctx(ctx, request):
-    ctx.call("eon_msm_set_rounds", request.param)
+    ctx.call("eon_msm_set_rounds", request.param[0])
+    ctx.call("eon_msm_set_slice_schedule", request.param[1])
     yield ctx
     ctx.call("eon_msm_set_rounds", -1)
+    ctx.call("eon_msm_set_slice_schedule", -1)
 
 
 def test_kats_and_edge_cases(rctx):
@@ -75,10 +79,37 @@ def test_commit_matches_rounds_off(ctx):
     ev = fr.random_wire(np.random.default_rng(8), h * w).reshape(h, w, 4)
     dom = TwoAdicMultiplicativeCoset(1, 12)
     outs = []
-    for r in (0, 3):
+    for r, sl in ((0, 0), (3, 0), (3, 1)):
         ctx.call("eon_msm_set_rounds", r)
+        ctx.call("eon_msm_set_slice_schedule", sl)
         c, pd = pcs.commit([(dom, ev)])
         outs.append(c[0].copy())
         pd[0].free()
     ctx.call("eon_msm_set_rounds", -1)
+    ctx.call("eon_msm_set_slice_schedule", -1)
+    assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[0], outs[2])
+
+
+def test_slice_schedule_multi_slice_table(ctx):
+    """2^18 points x 6 columns with a 16-bit window: the table has 16 levels = 4 slices of 2^20 points, so
+    the pair records really are binned; commitments equal the slot-order schedule's and the dlog shortcut."""
+    n, ncols, alpha = 1 << 18, 6, 12345
+    pcs = T.pcs_new(ctx, n - 1, alpha)
+    ctx.call("eon_srs_set_window_tables", 16)
+    rng = np.random.default_rng(12)
+    sc = fr.random_wire(rng, n * ncols).reshape(n, ncols, 4)
+    outs = []
+    for sl in (0, 1):
+        ctx.call("eon_msm_set_slice_schedule", sl)
+        out = np.zeros((ncols, 8), dtype=np.uint64)
+        ctx.call("eon_msm_srs", sc, n, ncols, ncols, out)
+        outs.append(out)
+    ctx.call("eon_msm_set_slice_schedule", -1)
     assert np.array_equal(outs[0], outs[1])
+    assert ctx.lib.eon_msm_rounds_used(ctx.h) >= 1
+    col0 = fr.from_wire(np.ascontiguousarray(sc[:, 0, :]))
+    dl, a = [], 1
+    for _ in range(n):
+        dl.append(a)
+        a = a * alpha % fr.P
+    assert T.pt(outs[1][0]) == g1.msm_via_dlog(dl, col0)
