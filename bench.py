@@ -384,17 +384,20 @@ def run_eon(args):
         achieved = ops / (bwd_ms * 1e-3) / 1e12
         # HBM view of the same kernel family: per pair 2 points in (128 B), prefix product in (32 B), sum out (64 B)
         alg_bytes = pairs * 224
-        # ncu --set full, 2^20 x 16 (profiles/r01h_ncu_full_summary.txt): the round-0 launch moves 40.25 GB read +
-        # 8.28 GB written for 125.8 M pairs = 386 B per pair against 224 algorithmic (DRAM fetches 128 B per random
-        # 64-byte base gather); the dense rounds move 15.8 + 6.2 GB for 94.4 M pairs = 233 B per pair
+        # ncu dram__bytes_read/write per launch at 2^20 x 16 (profiles/r01k_ncu_launches.csv).  With round 0 walked
+        # by table slice (csrc/msm_tree.cu) its launch moves 10.89 GB read + 8.25 GB written for 125.8 M pairs =
+        # 152 B per pair (the base gathers hit the L2; before: 40.25 + 8.28 GB = 386 B per pair, DRAM fetching 128 B
+        # per random 64-byte gather); the dense rounds move 14.64 + 7.32 GB for 94.4 M pairs = 233 B per pair.
         traffic = None
         if log_rows == 20 and cols == 16 and rounds == 3:
-            traffic = 40.25e9 + 8.28e9 + 15.83e9 + 6.17e9
+            r0 = (40.25e9 + 8.28e9) if args.slice_schedule == 0 else (10.89e9 + 8.25e9)
+            traffic = r0 + 10.52e9 + 4.12e9 + 5.27e9 + 2.05e9
         roofline = dict(common, kernel=f"k_tree_bwd x{rounds} (batched-affine pair additions, 5 modmul per pair)",
                         achieved=achieved, frac=achieved / imad_peak, algorithmic_ops_per_launch=ops,
                         launch_ms=bwd_ms, traffic=traffic,
-                        traffic_source="ncu --set full capture of these launches (profiles/r01h_ncu_full_summary.txt), "
-                                       "sum over the 3 rounds of one step" if traffic else None,
+                        traffic_source="ncu dram__bytes_read.sum + dram__bytes_write.sum of these launches "
+                                       "(profiles/r01k_ncu_launches.csv), sum over the 3 rounds of one step"
+                        if traffic else None,
                         hbm_view={"bound": "hbm", "algorithmic_bytes": alg_bytes,
                                   "achieved": alg_bytes / (bwd_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                                   "frac": alg_bytes / (bwd_ms * 1e-3) / 1e9 / hbm_peak},
@@ -492,6 +495,8 @@ def run_msm(args):
     pcs = eon.GpuKzgPcs.new(n - 1, ALPHA, ctx=ctx)              # replicated SRS (every rank reads its slice)
     if args.window_bits >= 0:
         ctx.call("eon_srs_set_window_tables", args.window_bits)
+    if args.slice_schedule >= 0:
+        ctx.call("eon_msm_set_slice_schedule", args.slice_schedule)
     first, cnt = edist.index_shard(n, world, rank)
     host = synth_trace(42, cnt, cols)                            # seed 42: bn254/benches/bench_curve.rs:40
     d_sc = torch.from_numpy(host.view(np.int64)).to(dev)

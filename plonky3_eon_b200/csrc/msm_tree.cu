@@ -57,18 +57,69 @@ __device__ __forceinline__ void st_fq(Fq* p, const Fq& a) {
                : "memory");
 }
 
+// L2 residency hints for the slice schedule: base points are kept (evict-last), the streams that pass through
+// once -- pair records in, prefix products and sums out -- are marked evict-first so they do not push the
+// slice out of the L2.  -DEON_NO_L2_HINTS drops them (plain accesses).
+__device__ __forceinline__ Fq ldg_fq_keep(const Fq* p) {
+#if defined(EON_NO_L2_HINTS)
+  return ldg_fq(p);
+#else
+  Fq r;
+  asm volatile("ld.global.nc.L1::evict_last.L2::evict_last.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]),
+                 "=r"(r.v[7])
+               : "l"(p));
+  return r;
+#endif
+}
+__device__ __forceinline__ void st_fq_stream(Fq* p, const Fq& a) {
+#if defined(EON_NO_L2_HINTS)
+  st_fq(p, a);
+#else
+  asm volatile("st.global.L1::no_allocate.L2::evict_first.v8.u32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p),
+               "r"(a.v[0]), "r"(a.v[1]), "r"(a.v[2]), "r"(a.v[3]), "r"(a.v[4]), "r"(a.v[5]), "r"(a.v[6]), "r"(a.v[7])
+               : "memory");
+#endif
+}
+__device__ __forceinline__ Fq ldg_fq_stream(const Fq* p) {
+#if defined(EON_NO_L2_HINTS)
+  return ldg_fq(p);
+#else
+  Fq r;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]),
+                 "=r"(r.v[7])
+               : "l"(p));
+  return r;
+#endif
+}
+__device__ __forceinline__ uint2 ldg_rec(const uint2* p) {
+#if defined(EON_NO_L2_HINTS)
+  return __ldg(p);
+#else
+  uint2 r;
+  // (the L2 eviction modifiers exist for 256-bit accesses only)
+  asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+  return r;
+#endif
+}
+
 // One operand of a pair, loaded lazily: x first (the common path needs nothing else).
 template <bool R0>
 struct Operand {
   const G1Affine* p;  // null: ENTRY_NONE
   bool neg;
+  bool keep;          // slice schedule: the point comes from an L2-resident table slice
   Fq x;
+  __device__ __forceinline__ Fq load(const Fq* q) const { return keep ? ldg_fq_keep(q) : ldg_fq(q); }
   __device__ __forceinline__ void open_entry(const G1Affine* bases, u32 v) {
+    keep = true;
     neg = (v & SIGN_BIT) != 0;
     p = (v == ENTRY_NONE) ? nullptr : bases + (v & ~SIGN_BIT);
-    x = p ? ldg_fq(&p->x) : Fq::zero();
+    x = p ? load(&p->x) : Fq::zero();
   }
   __device__ __forceinline__ void open(const TreeSrc& s, u64 slot) {
+    keep = false;
     if (R0) {
       u32 v = __ldg(s.entries + slot);
       neg = (v & SIGN_BIT) != 0;
@@ -81,10 +132,10 @@ struct Operand {
   }
   __device__ __forceinline__ Fq y() const {
     if (!p) return Fq::zero();
-    Fq v = ldg_fq(&p->y);
+    Fq v = load(&p->y);
     return neg ? fp_neg(v) : v;
   }
-  __device__ __forceinline__ bool is_identity() const { return !p || (x.is_zero() && ldg_fq(&p->y).is_zero()); }
+  __device__ __forceinline__ bool is_identity() const { return !p || (x.is_zero() && load(&p->y).is_zero()); }
 };
 
 // Denominator of pair j and what kind of pair it is.  Used identically by k_tree_fwd and by both
@@ -179,7 +230,7 @@ __device__ __forceinline__ G1Affine pair_sum(const Operand<R0>& P, const Operand
     else if (qid && !pid) { r.x = P.x; r.y = P.y(); }
     else r = G1Affine::identity();  // both identity, or P == -Q
   } else {
-    const Fq pre = ldg_fq(pre_ptr);
+    const Fq pre = P.keep ? ldg_fq_stream(pre_ptr) : ldg_fq(pre_ptr);
     const Fq dinv = fp_mul(inv, pre);  // pre == 1 (Montgomery one) for the first non-trivial pair
     inv = fp_mul(inv, d);
     const Fq py = P.y();
@@ -362,8 +413,8 @@ k_tree_fwd_sliced(const uint2* __restrict__ rec_e, u64 npairs, const G1Affine* _
   for (int i = 0; i < TREE_B; i++) {
     const u64 k = k0 + (u64)i * TREE_THREADS;
     if (k >= npairs) break;
-    st_fq(pre + k, run);
-    const uint2 e = __ldg(rec_e + k);
+    st_fq_stream(pre + k, run);
+    const uint2 e = ldg_rec(rec_e + k);
     Operand<true> P, Q;
     P.open_entry(bases, e.x);
     Q.open_entry(bases, e.y);
@@ -388,7 +439,7 @@ k_tree_bwd_sliced(const uint2* __restrict__ rec_e, const u32* __restrict__ rec_d
 #pragma unroll 1
   for (int i = cnt - 1; i >= 0; i--) {
     const u64 k = k0 + (u64)i * TREE_THREADS;
-    const uint2 e = __ldg(rec_e + k);
+    const uint2 e = ldg_rec(rec_e + k);
     const u32 dest = __ldg(rec_dest + k);
     Operand<true> P, Q;
     P.open_entry(bases, e.x);
@@ -396,8 +447,8 @@ k_tree_bwd_sliced(const uint2* __restrict__ rec_e, const u32* __restrict__ rec_d
     Fq d;
     const int kind = pair_denominator<true>(P, Q, d);
     const G1Affine r = pair_sum<true>(P, Q, kind, d, inv, pre_all + k);
-    st_fq(&out[dest].x, r.x);
-    st_fq(&out[dest].y, r.y);
+    st_fq_stream(&out[dest].x, r.x);
+    st_fq_stream(&out[dest].y, r.y);
   }
 }
 
