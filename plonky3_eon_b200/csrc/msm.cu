@@ -50,6 +50,12 @@ static MsmShape msm_shape_plain(size_t n) {
 }
 
 static MsmShape msm_shape_merged(size_t n, u32 c, u64 tab_stride, u64 first) {
+  static int chunk_env = 0;
+  if (!chunk_env) {
+    const char* e = getenv("EON_MSM_CHUNK");
+    chunk_env = e ? atoi(e) : 32;
+    if (chunk_env != 8 && chunk_env != 16 && chunk_env != 64 && chunk_env != 128) chunk_env = 32;
+  }
   MsmShape s;
   memset(&s, 0, sizeof(s));
   s.c = c;
@@ -57,7 +63,7 @@ static MsmShape msm_shape_merged(size_t n, u32 c, u64 tab_stride, u64 first) {
   s.NB = 1u << (c - 1);
   s.nsets = 1;
   s.merged = 1;
-  s.chunk = 32;
+  s.chunk = (u32)chunk_env;
   s.nchunks = s.NB / s.chunk;
   s.tab_stride = tab_stride;
   s.base_first = first;

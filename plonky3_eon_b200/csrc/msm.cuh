@@ -36,6 +36,10 @@ struct SlicePlan {
   u32 shift;
   u32 nbins;
 };
+// the sort can order the entries of a bucket by slice only up to this many slices ((bucket, slice) counters of
+// a bin in shared memory); without that order the schedule gains next to nothing (one operand of every pair
+// still comes from a random slice and evicts the resident one), so the automatic policy stops here
+constexpr u32 SLICE_ORDER_MAX = 32;
 // nbases = number of points addressable through d_bases (all window-table levels).
 SlicePlan msm_slice_plan(const eon_ctx* ctx, u64 nbases, u64 total_slots, u32 rounds);
 int msm_tree_rounds(eon_ctx* ctx, const G1Affine* d_bases, const SlicePlan& plan, const u32* d_entries,

@@ -233,8 +233,6 @@ k_sort_fine(const u32* __restrict__ tmp_pay, const unsigned short* __restrict__ 
 
 static bool g_sort_attr_set = false;
 
-constexpr u32 SORT_MAX_SLICES = 32;  // ordered fine pass: (bucket, slice) counters of a bin in shared memory
-
 int msm_sort_entries(eon_ctx* ctx, const Fr* d_scalars, size_t n, size_t ncols, size_t ld, const MsmShape& sh,
                      const SlicePlan& plan, const u32* d_starts, const u32* d_seg_total, u32* d_ends, u32* d_entries) {
   // Worth it only while a tile still fills runs of tens of entries per bin (<= 1024 bins per tile) and a
@@ -267,7 +265,7 @@ int msm_sort_entries(eon_ctx* ctx, const Fr* d_scalars, size_t n, size_t ncols, 
     EON_CUDA(ctx, cudaFuncSetAttribute(k_sort_fine<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)(((size_t)(1u << 12) + SORT_WIN_CAP) * sizeof(u32))));
     EON_CUDA(ctx, cudaFuncSetAttribute(k_sort_fine<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)(((size_t)(1u << 7) * (1 + SORT_MAX_SLICES) + SORT_WIN_CAP) * sizeof(u32))));
+                                       (int)(((size_t)(1u << 7) * (1 + SLICE_ORDER_MAX) + SORT_WIN_CAP) * sizeof(u32))));
     g_sort_attr_set = true;
   }
   void *p_reg, *p_pay, *p_key;
@@ -286,7 +284,7 @@ int msm_sort_entries(eon_ctx* ctx, const Fr* d_scalars, size_t n, size_t ncols, 
         d_scalars, n, ld, (u32)ncols, sh, nbins, fb, tile, (u32*)p_reg, (u32*)p_pay, (unsigned short*)p_key);
   EON_LAUNCHED(ctx);
   static const int order_env = getenv("EON_SORT_ORDERED") ? atoi(getenv("EON_SORT_ORDERED")) : 1;
-  if (plan.on && plan.nbins > 1 && plan.nbins <= SORT_MAX_SLICES && order_env)
+  if (plan.on && plan.nbins > 1 && plan.nbins <= SLICE_ORDER_MAX && order_env)
     k_sort_fine<true><<<(unsigned)total_bins, SORT_FINE_THREADS, smem_fine + ((size_t)plan.nbins << fb) * sizeof(u32), st>>>(
         (const u32*)p_pay, (const unsigned short*)p_key, (const u32*)p_reg, d_starts, d_seg_total, sh.NB, nbins, fb,
         sh.seg_cap, plan.shift, plan.nbins, d_ends, d_entries);

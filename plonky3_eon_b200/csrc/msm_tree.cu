@@ -495,7 +495,8 @@ SlicePlan msm_slice_plan(const eon_ctx* ctx, u64 nbases, u64 total_slots, u32 ro
   const int mode = ctx->msm_slice_mode >= 0 ? ctx->msm_slice_mode : sliced_env;
   p.on = rounds > 0 && nbins <= SLICE_MAX_BINS && total_slots / 2 < 0xffffffffull;
   if (mode == 0) p.on = false;
-  else if (mode != 1) p.on = p.on && nbases * sizeof(G1Affine) > (96ull << 20) && total_slots >= 4 * nbases;
+  else if (mode != 1)
+    p.on = p.on && nbins <= SLICE_ORDER_MAX && nbases * sizeof(G1Affine) > (96ull << 20) && total_slots >= 4 * nbases;
   return p;
 }
 
