@@ -195,7 +195,7 @@ def run_reference(args):
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    print(json.dumps(line), file=OUT, flush=True)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -462,7 +462,7 @@ def run_eon(args):
         "roofline": roofline, "roofline_ntt": roofline_ntt, "cpu_baseline": cpu,
         "msm_points_per_s": rows * cols / (sum(phases[k] for k in phases if k.startswith("msm_")) / args.steps * 1e-3),
     }
-    print(json.dumps(line))
+    print(json.dumps(line), file=OUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
@@ -561,7 +561,7 @@ def run_msm(args):
                          "peak": imad_peak, "unit": "TIMAD/s", "frac": ops / (acc_ms * 1e-3) / 1e12 / imad_peak,
                          "traffic": None, "algorithmic_ops_per_launch": ops, "launch_ms": acc_ms},
         }
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=OUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
@@ -622,7 +622,7 @@ def run_open(args):
         "gpu_launches": ctx.launch_count() - launches0,
         "phase_ms_per_step": {k: v / args.steps for k, v in phases.items()},
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=OUT, flush=True)
 
 
 def run_prove_pcs(args):
@@ -684,13 +684,24 @@ def run_prove_pcs(args):
                      "commit_quotient_2_chunks": med[2] * 1e3, "open": med[3] * 1e3},
         "gpu_launches": launches,
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=OUT, flush=True)
+
+
+OUT = sys.stdout
+
+
+def claim_stdout():
+    """Keep stdout to the one JSON line: fd 1 is pointed at stderr for the life of the process (native libraries
+    print there -- NCCL's version banner did) and the line is written to a duplicate of the real stdout."""
+    global OUT
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+    OUT = os.fdopen(real, "w")
 
 
 def main():
-    # keep stdout to the one JSON line: NCCL prints its version banner there at NCCL_DEBUG=VERSION
-    if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
-        os.environ["NCCL_DEBUG"] = "WARN"
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)

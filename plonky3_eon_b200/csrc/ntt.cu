@@ -178,28 +178,41 @@ __global__ void __launch_bounds__(NTT_THREADS, MINB) k_ntt_pass(const PassParams
   // ---- load tile (16-byte units, consecutive threads -> consecutive units) ----
   const bool plain_in = (p.k == 0 && !p.in_rev && p.ld_src == p.w);
   const bool plain_out = (p.ld_dst == p.w);
-  for (u32 u = tid; u < tile_elems * 2; u += NTT_THREADS) {
-    u32 e = u >> 1, half = u & 1;
-    u32 m = e >> p.log_cv, vc = e & (cv - 1);
-    if (vc >= ncv) continue;
-    u64 vidx = v0 + vc;
-    u64 src_elem;
-    if (plain_in) {
-      src_elem = (row_base + m) * p.V + vidx;
-    } else {
-      u64 lo;
-      u32 col;
-      split_vidx(p, vidx, lo, col);
-      u64 pos = ((row_base + m) << p.l0) + lo;
-      u64 srow = pos >> p.k;
-      if (p.in_rev) {
-        u32 bits = p.log_n - p.k;
-        srow = bits ? (u64)(__brev((u32)srow) >> (32 - bits)) : 0;
+  // LD_BATCH independent 16-byte loads are issued before the first of them is stored to shared memory (a load
+  // immediately followed by its store serialises the global round trips: 16 per thread and tile)
+  constexpr int LD_BATCH = 8;
+  for (u32 ub = tid; ub < tile_elems * 2; ub += NTT_THREADS * LD_BATCH) {
+    uint4 val[LD_BATCH];
+    u32 se[LD_BATCH];  // shared-memory slot: element | half << 31, or ~0u for nothing
+#pragma unroll
+    for (int q = 0; q < LD_BATCH; q++) {
+      const u32 u = ub + q * NTT_THREADS;
+      const u32 e = u >> 1, half = u & 1;
+      const u32 m = e >> p.log_cv, vc = e & (cv - 1);
+      se[q] = ~0u;
+      if (u >= tile_elems * 2 || vc >= ncv) continue;
+      const u64 vidx = v0 + vc;
+      u64 src_elem;
+      if (plain_in) {
+        src_elem = (row_base + m) * p.V + vidx;
+      } else {
+        u64 lo;
+        u32 col;
+        split_vidx(p, vidx, lo, col);
+        u64 pos = ((row_base + m) << p.l0) + lo;
+        u64 srow = pos >> p.k;
+        if (p.in_rev) {
+          u32 bits = p.log_n - p.k;
+          srow = bits ? (u64)(__brev((u32)srow) >> (32 - bits)) : 0;
+        }
+        src_elem = srow * p.ld_src + col;
       }
-      src_elem = srow * p.ld_src + col;
+      val[q] = p.src[src_elem * 2 + half];
+      se[q] = e | (half << 31);
     }
-    uint4 val = p.src[src_elem * 2 + half];
-    (half ? s_hi : s_lo)[e] = val;
+#pragma unroll
+    for (int q = 0; q < LD_BATCH; q++)
+      if (se[q] != ~0u) ((se[q] >> 31) ? s_hi : s_lo)[se[q] & 0x7fffffffu] = val[q];
   }
   __syncthreads();
 
