@@ -471,3 +471,45 @@ def test_commit_lde_dev_matches_two_calls(ctx, log_h, w):
         ctx.dev_free(p)
     ctx.call("eon_handle_free", h1)
     ctx.call("eon_handle_free", h2)
+
+
+def test_context_shared_by_threads(ctx):
+    """callers may run several proofs from different threads against one Pcs.  Four host threads
+    commit + open different traces through ONE context at the same time (ctypes drops the GIL inside the
+    call; the context serialises them); every result equals the single-threaded one."""
+    import threading
+    from plonky3_eon_b200 import TwoAdicMultiplicativeCoset
+    h, w, alpha = 1 << 10, 3, 12345
+    pcs = pcs_new(ctx, h - 1, alpha)
+    dom = TwoAdicMultiplicativeCoset(1, 10)
+    rng = np.random.default_rng(99)
+    traces = [fr.random_wire(rng, h * w).reshape(h, w, 4) for _ in range(4)]
+    zeta = 0x1234567
+
+    def job(ev):
+        c, pd = pcs.commit([(dom, ev)])
+        o, p = pcs.open([(pd, [[zeta]])])
+        lde = pcs.get_evaluations_on_domain(pd, 0, dom.create_disjoint_domain(2 * h))
+        pd[0].free()
+        return c[0].copy(), o[0][0][0].copy(), p[0][0][0].copy(), lde.copy()
+
+    want = [job(ev) for ev in traces]
+    got = [None] * 4
+    errs = []
+
+    def run(i):
+        try:
+            for _ in range(3):
+                got[i] = job(traces[i])
+        except Exception as e:  # pragma: no cover
+            errs.append(e)
+
+    th = [threading.Thread(target=run, args=(i,)) for i in range(4)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    assert not errs, errs
+    for a, b in zip(want, got):
+        for x, y in zip(a, b):
+            assert np.array_equal(x, y)
