@@ -135,6 +135,12 @@ k_msm_scan(u32* __restrict__ hist, u32* __restrict__ cursor, u32 NB, u32 align, 
   if (tid == 0) seg_total[blockIdx.x] = s_carry;  // aligned slots in use by the segment
 }
 
+int msm_scan_run(eon_ctx* ctx, u32* d_hist, u32* d_cur, u32 NB, u32 align, u32* d_seg_total, size_t nseg) {
+  k_msm_scan<<<(unsigned)nseg, 1024, 0, ctx->stream>>>(d_hist, d_cur, NB, align, d_seg_total);
+  EON_LAUNCHED(ctx);
+  return EON_OK;
+}
+
 // ---- 3. scatter (counting sort by bucket) ----------------------------------------------------
 // The digits are recomputed from the scalar (one modmul) instead of being stored by pass 1: that is
 // cheaper than writing and re-reading 2-4 bytes per (point, window).
@@ -463,21 +469,7 @@ static int msm_batch(eon_ctx* ctx, const G1Affine* d_bases, const Fr* d_scalars,
   const SlicePlan plan = msm_slice_plan(ctx, sh.merged ? (u64)sh.W * sh.tab_stride : (u64)n, (u64)nseg * sh.seg_cap,
                                         sh.rounds);
 
-  phase_begin(ctx, PH_MSM_DIGITS);
-  EON_CUDA(ctx, cudaMemsetAsync(p_hist, 0, total_buckets * sizeof(u32), st));
   EON_CUDA(ctx, cudaMemsetAsync(d_ntasks, 0, sizeof(u32), st));
-  k_msm_hist<<<grid_pts, MSM_THREADS, 0, st>>>(d_scalars, n, ld, (u32)ncols, sh, (u32*)p_hist);
-  EON_LAUNCHED(ctx);
-  phase_end(ctx, PH_MSM_DIGITS);
-
-  phase_begin(ctx, PH_MSM_SCAN);
-  k_msm_scan<<<(unsigned)nseg, 1024, 0, st>>>((u32*)p_hist, (u32*)p_cur, sh.NB, 1u << sh.rounds, (u32*)p_segtot);
-  EON_LAUNCHED(ctx);
-  phase_end(ctx, PH_MSM_SCAN);
-
-  phase_begin(ctx, PH_MSM_SCATTER);
-  if (sh.rounds)  // unused slots (bucket padding, segment tails) must read as ENTRY_NONE
-    EON_CUDA(ctx, cudaMemsetAsync(p_ent, 0xff, nseg * sh.seg_cap * sizeof(u32), st));
   {
     static int env_mode = -2;
     if (env_mode == -2) {
@@ -486,16 +478,29 @@ static int msm_batch(eon_ctx* ctx, const G1Affine* d_bases, const Fr* d_scalars,
     }
     const int mode = ctx->msm_sort_mode >= 0 ? ctx->msm_sort_mode : env_mode;
     int rc = 1;
-    if (mode != 0 && (mode == 1 || n >= 4096))  // two coalesced passes (msm_sort.cu); small inputs: one pass
-      rc = msm_sort_entries(ctx, d_scalars, n, ncols, ld, sh, plan, (const u32*)p_hist, (const u32*)p_segtot,
-                            (u32*)p_cur, (u32*)p_ent);
+    // coalesced multi-pass sort (msm_sort.cu), which also produces the bucket histogram; small inputs and
+    // unsupported shapes: global histogram + one-pass atomic scatter
+    if (mode != 0 && (mode == 1 || n >= 4096))
+      rc = msm_sort_entries(ctx, d_scalars, n, ncols, ld, sh, plan, (u32*)p_hist, (u32*)p_segtot, (u32*)p_cur,
+                            (u32*)p_ent);
     if (rc < 0) return rc;
     if (rc > 0) {
+      phase_begin(ctx, PH_MSM_DIGITS);
+      EON_CUDA(ctx, cudaMemsetAsync(p_hist, 0, total_buckets * sizeof(u32), st));
+      k_msm_hist<<<grid_pts, MSM_THREADS, 0, st>>>(d_scalars, n, ld, (u32)ncols, sh, (u32*)p_hist);
+      EON_LAUNCHED(ctx);
+      phase_end(ctx, PH_MSM_DIGITS);
+      phase_begin(ctx, PH_MSM_SCAN);
+      EON_TRY(msm_scan_run(ctx, (u32*)p_hist, (u32*)p_cur, sh.NB, 1u << sh.rounds, (u32*)p_segtot, nseg));
+      phase_end(ctx, PH_MSM_SCAN);
+      phase_begin(ctx, PH_MSM_SCATTER);
+      if (sh.rounds)  // unused slots (bucket padding, segment tails) must read as ENTRY_NONE
+        EON_CUDA(ctx, cudaMemsetAsync(p_ent, 0xff, nseg * sh.seg_cap * sizeof(u32), st));
       k_msm_scatter<<<grid_pts, MSM_THREADS, 0, st>>>(d_scalars, n, ld, (u32)ncols, sh, (u32*)p_cur, (u32*)p_ent);
       EON_LAUNCHED(ctx);
+      phase_end(ctx, PH_MSM_SCATTER);
     }
   }
-  phase_end(ctx, PH_MSM_SCATTER);
 
   phase_begin(ctx, PH_MSM_ACCUM);
   {

@@ -46,16 +46,19 @@ int msm_tree_rounds(eon_ctx* ctx, const G1Affine* d_bases, const SlicePlan& plan
                     u64 total_slots, u32 rounds, const G1Affine** out_pts);
 
 
-// Counting sort of the (point, window) entries by bucket in two coalesced passes (msm_sort.cu):
-// coarse scatter by the high bucket bits into a temporary array, then a per-bin fine placement.
-// In: starts[] (aligned exclusive scan of the bucket histogram), seg_total[] (aligned slots used per
-// segment).  Out: entries[] sorted by bucket,
-// ends[g] = starts[g] + count(g).  Returns EON_OK, or a positive value if the shape is not supported
-// (caller falls back to the one-pass atomic scatter).
+// Counting sort of the (point, window) entries by bucket in coalesced passes (msm_sort.cu): bin histogram,
+// coarse scatter by the high bucket bits into a temporary array, bucket histogram of every bin, aligned scan,
+// per-bin fine placement.  Does the whole digits / scan / scatter part of an MSM batch on its own.
+// Out: hist[] = bucket starts (aligned exclusive scan), seg_total[] = aligned slots used per segment,
+// cur[g] = starts[g] + count(g), entries[] sorted by bucket (unused slots = ENTRY_NONE when sh.rounds > 0).
+// Returns EON_OK, or a positive value WITHOUT having launched anything if the shape is not supported (the
+// caller falls back to the global histogram + one-pass atomic scatter).
 // plan.on: the entries of every bucket are additionally ordered by table slice (so that round 0 pairs operands
 // of the same slice); any order inside a bucket gives the same sums.
 int msm_sort_entries(eon_ctx* ctx, const Fr* d_scalars, size_t n, size_t ncols, size_t ld, const MsmShape& sh,
-                     const SlicePlan& plan, const u32* d_starts, const u32* d_seg_total, u32* d_ends, u32* d_entries);
+                     const SlicePlan& plan, u32* d_hist, u32* d_seg_total, u32* d_cur, u32* d_entries);
+// aligned exclusive scan of the bucket histogram, one block per segment (k_msm_scan, msm.cu)
+int msm_scan_run(eon_ctx* ctx, u32* d_hist, u32* d_cur, u32 NB, u32 align, u32* d_seg_total, size_t nseg);
 
 #if defined(__CUDACC__)
 // ---- 1. scalar -> signed window digits --------------------------------------------------------

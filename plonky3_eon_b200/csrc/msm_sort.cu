@@ -18,8 +18,13 @@
 // (An SM retires scattered 4-byte stores at about one sector per clock whatever L2 merges afterwards;
 // that, not DRAM, bounded the one-pass scatter and a first version of this file without staging.)
 //
-// The bucket histogram / aligned scan (k_msm_hist, k_msm_scan) stay as they are: the bin regions are
-// simply [starts[bin * 128], starts[(bin + 1) * 128]), so no second scan is needed.
+// The bucket histogram comes out of the sort itself: k_msm_hist's 2.5e8 global atomics (1.2 ms at 2^20 x 16)
+// are replaced by
+//   k_bin_hist     the same tiles counted by BIN in shared memory (512 global atomics per tile), then a
+//                  per-segment scan gives every bin an exact, unpadded run of the temporary array;
+//   k_sort_count   after the coarse pass, one CTA per bin counts its entries by bucket (shared memory,
+//                  coalesced 2-byte key reads) and writes the bucket histogram without atomics;
+// the aligned scan (k_msm_scan) then runs on that histogram as before and k_sort_fine places.
 #include <stdlib.h>
 
 #include "msm.cuh"
@@ -49,14 +54,99 @@ __device__ __forceinline__ u32 smem_rank(u32* counter, u32 key) {
   return atomicAdd(counter + key, 1u);
 }
 
-// region_cursor[seg * nbins + k] = starts[seg * NB + (k << fb)]
-__global__ void k_sort_init(const u32* __restrict__ starts, u32 NB, u32 nbins, u32 fb, size_t total_bins,
-                            u32* __restrict__ region_cursor) {
-  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-  if (i >= total_bins) return;
-  size_t seg = i / nbins;
-  u32 k = (u32)(i % nbins);
-  region_cursor[i] = starts[seg * NB + ((size_t)k << fb)];
+// Bin histogram.  grid: ncols * ceil(n / tile) blocks, column index fastest (as the coarse pass).
+// bin_count[(col * nsets + set) * nbins + k] += entries of the tile whose bucket >> fb == k
+template <bool MERGED>
+__global__ void __launch_bounds__(SORT_THREADS)
+k_bin_hist(const Fr* __restrict__ scalars, size_t n, size_t ld, u32 ncols, MsmShape sh, u32 nbins, u32 fb, u32 tile,
+           u32* __restrict__ bin_count) {
+  extern __shared__ u32 smem[];
+  const u32 tile_bins = sh.nsets * nbins;
+  const u32 tid = threadIdx.x;
+  const u32 col = blockIdx.x % ncols;
+  const size_t i0 = (size_t)(blockIdx.x / ncols) * tile;
+  for (u32 k = tid; k < tile_bins; k += SORT_THREADS) smem[k] = 0;
+  __syncthreads();
+  // the tile's scalars of this thread are loaded together (tile <= 4 * SORT_THREADS), then digitised
+  Fr sc[4];
+#pragma unroll
+  for (int q = 0; q < 4; q++) {
+    const u32 t = tid + q * SORT_THREADS;
+    const size_t i = i0 + t;
+    sc[q] = (t < tile && i < n) ? load_scalar(scalars, i, ld, col) : Fr::zero();  // zero scalar: no digits
+  }
+#pragma unroll
+  for (int q = 0; q < 4; q++) {
+    u32 kk[8];
+    fp_from_mont(kk, sc[q]);
+    for_each_digit_canonical(kk, sh, [&](u32 w, int d) {
+      u32 b = (u32)(d < 0 ? -d : d) - 1;
+      atomicAdd(&smem[(MERGED ? 0 : w * nbins) + (b >> fb)], 1u);
+    });
+  }
+  __syncthreads();
+  u32* dst = bin_count + (size_t)col * sh.nsets * nbins;
+  for (u32 k = tid; k < tile_bins; k += SORT_THREADS)
+    if (smem[k]) atomicAdd(dst + k, smem[k]);
+}
+
+// Per segment (one block): tmp_start[k] = region_cursor[k] = exclusive scan of bin_count over the segment's
+// bins (nbins <= 1024).
+__global__ void __launch_bounds__(1024) k_bin_scan(const u32* __restrict__ bin_count, u32 nbins,
+                                                   u32* __restrict__ tmp_start, u32* __restrict__ region_cursor) {
+  __shared__ u32 warp_sums[32];
+  const u32 tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const size_t base = (size_t)blockIdx.x * nbins;
+  const u32 v = tid < nbins ? bin_count[base + tid] : 0;
+  u32 x = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    u32 y = __shfl_up_sync(0xffffffffu, x, o);
+    if (lane >= (u32)o) x += y;
+  }
+  if (lane == 31) warp_sums[wid] = x;
+  __syncthreads();
+  u32 wbase = 0;
+  for (u32 j = 0; j < wid; j++) wbase += warp_sums[j];
+  if (tid < nbins) {
+    tmp_start[base + tid] = wbase + x - v;
+    region_cursor[base + tid] = wbase + x - v;
+  }
+}
+
+// Bucket histogram of one bin from the coarse pass's output.  grid: nseg * nbins blocks.
+__global__ void __launch_bounds__(SORT_THREADS)
+k_sort_count(const unsigned short* __restrict__ tmp_key, const u32* __restrict__ tmp_start,
+             const u32* __restrict__ region_cursor, u32 NB, u32 nbins, u32 fb, u64 seg_cap, u32* __restrict__ hist) {
+  __shared__ u32 s_cnt[1u << 7];
+  const u32 fine = 1u << fb;
+  const size_t seg = blockIdx.x / nbins;
+  const u32 k = blockIdx.x % nbins;
+  const u32 tid = threadIdx.x;
+  for (u32 f = tid; f < fine; f += SORT_THREADS) s_cnt[f] = 0;
+  __syncthreads();
+  const u32 begin = tmp_start[seg * nbins + k], end = region_cursor[seg * nbins + k];
+  // 8 keys per 16-byte load over the aligned interior of the run, single keys at its two ends
+  const u64 g0 = seg * seg_cap + begin, g1 = seg * seg_cap + end;
+  u64 a0 = (g0 + 7) & ~7ull, a1 = g1 & ~7ull;
+  if (a0 > g1) a0 = g1;
+  if (a1 < a0) a1 = a0;
+  for (u64 i = g0 + tid; i < a0; i += SORT_THREADS) atomicAdd(&s_cnt[tmp_key[i]], 1u);
+  for (u64 i = a1 + tid; i < g1; i += SORT_THREADS) atomicAdd(&s_cnt[tmp_key[i]], 1u);
+  const uint4* kv = reinterpret_cast<const uint4*>(tmp_key + a0);
+  const u64 nv = (a1 - a0) >> 3;
+  for (u64 v = tid; v < nv; v += SORT_THREADS) {
+    const uint4 q = __ldg(kv + v);
+    const u32 w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      atomicAdd(&s_cnt[w[j] & 0xffffu], 1u);
+      atomicAdd(&s_cnt[w[j] >> 16], 1u);
+    }
+  }
+  __syncthreads();
+  u32* h = hist + seg * NB + ((size_t)k << fb);
+  for (u32 f = tid; f < fine; f += SORT_THREADS) h[f] = s_cnt[f];
 }
 
 // Coarse pass.  grid: ncols * ceil(n / tile) blocks, column index fastest (cf. k_msm_hist).
@@ -169,7 +259,8 @@ k_sort_coarse(const Fr* __restrict__ scalars, size_t n, size_t ld, u32 ncols, Ms
 template <bool ORDERED>
 __global__ void __launch_bounds__(SORT_FINE_THREADS)
 k_sort_fine(const u32* __restrict__ tmp_pay, const unsigned short* __restrict__ tmp_key,
-            const u32* __restrict__ region_cursor, const u32* __restrict__ starts, const u32* __restrict__ seg_total,
+            const u32* __restrict__ tmp_start, const u32* __restrict__ region_cursor, const u32* __restrict__ starts,
+            const u32* __restrict__ seg_total,
             u32 NB, u32 nbins, u32 fb, u64 seg_cap, u32 slice_shift, u32 ns, u32* __restrict__ ends,
             u32* __restrict__ entries) {
   extern __shared__ u32 smem[];
@@ -182,7 +273,8 @@ k_sort_fine(const u32* __restrict__ tmp_pay, const unsigned short* __restrict__ 
   const size_t g0 = seg * NB + ((size_t)k << fb);
   const size_t off = seg * seg_cap;
   const u32 tid = threadIdx.x;
-  const u32 begin = starts[g0], end = region_cursor[seg * nbins + k];
+  const u32 begin = starts[g0];  // first slot of the bin's window of the final array
+  const u32 tbegin = tmp_start[seg * nbins + k], tend = region_cursor[seg * nbins + k];  // its run of the temporary array
   for (u32 f = tid; f < fine; f += SORT_FINE_THREADS) s_cur[f] = starts[g0 + f];
   // window end: the next bin's first start, or (last bin) the aligned end of the segment
   const u32 wend = (k + 1 < nbins) ? starts[g0 + fine] : seg_total[seg];
@@ -193,7 +285,7 @@ k_sort_fine(const u32* __restrict__ tmp_pay, const unsigned short* __restrict__ 
   if (ORDERED && staged) {
     for (u32 j = tid; j < fine * ns; j += SORT_FINE_THREADS) s_cnt2[j] = 0;
     __syncthreads();
-    for (u32 i = begin + tid; i < end; i += SORT_FINE_THREADS) {
+    for (u32 i = tbegin + tid; i < tend; i += SORT_FINE_THREADS) {
       const u32 key = tmp_key[off + i];
       const u32 sl = min((tmp_pay[off + i] & ~SIGN_BIT) >> slice_shift, ns - 1);
       atomicAdd(&s_cnt2[key * ns + sl], 1u);
@@ -209,7 +301,7 @@ k_sort_fine(const u32* __restrict__ tmp_pay, const unsigned short* __restrict__ 
       s_cur[f] = run;  // the bucket's end
     }
     __syncthreads();
-    for (u32 i = begin + tid; i < end; i += SORT_FINE_THREADS) {
+    for (u32 i = tbegin + tid; i < tend; i += SORT_FINE_THREADS) {
       const u32 key = tmp_key[off + i];
       const u32 pay = tmp_pay[off + i];
       const u32 sl = min((pay & ~SIGN_BIT) >> slice_shift, ns - 1);
@@ -217,7 +309,7 @@ k_sort_fine(const u32* __restrict__ tmp_pay, const unsigned short* __restrict__ 
     }
   } else {
     __syncthreads();
-    for (u32 i = begin + tid; i < end; i += SORT_FINE_THREADS) {
+    for (u32 i = tbegin + tid; i < tend; i += SORT_FINE_THREADS) {
       u32 key = tmp_key[off + i];
       u32 pay = tmp_pay[off + i];
       u32 pos = smem_rank(s_cur, key);
@@ -234,7 +326,7 @@ k_sort_fine(const u32* __restrict__ tmp_pay, const unsigned short* __restrict__ 
 static bool g_sort_attr_set = false;
 
 int msm_sort_entries(eon_ctx* ctx, const Fr* d_scalars, size_t n, size_t ncols, size_t ld, const MsmShape& sh,
-                     const SlicePlan& plan, const u32* d_starts, const u32* d_seg_total, u32* d_ends, u32* d_entries) {
+                     const SlicePlan& plan, u32* d_hist, u32* d_seg_total, u32* d_cur, u32* d_entries) {
   // Worth it only while a tile still fills runs of tens of entries per bin (<= 1024 bins per tile) and a
   // bin's window fits the shared-memory image; otherwise (2^22+ points per column at c = 20, or many
   // bucket sets per column) the one-pass scatter is faster (measured: 2^24 x 1, 4.2 vs 14.6 ms).
@@ -269,30 +361,60 @@ int msm_sort_entries(eon_ctx* ctx, const Fr* d_scalars, size_t n, size_t ncols, 
     g_sort_attr_set = true;
   }
   void *p_reg, *p_pay, *p_key;
-  EON_TRY(scratch_get(ctx, SC_MSM_SORT_REGION, total_bins * sizeof(u32), &p_reg));
+  // per bin: count | start of its run in the temporary array | cursor (ends as the end of that run)
+  EON_TRY(scratch_get(ctx, SC_MSM_SORT_REGION, 3 * total_bins * sizeof(u32), &p_reg));
   EON_TRY(scratch_get(ctx, SC_MSM_SORT_PAY, nseg * sh.seg_cap * sizeof(u32), &p_pay));
   EON_TRY(scratch_get(ctx, SC_MSM_SORT_KEY, nseg * sh.seg_cap * sizeof(unsigned short), &p_key));
+  u32* bin_count = (u32*)p_reg;
+  u32* tmp_start = bin_count + total_bins;
+  u32* region_cursor = tmp_start + total_bins;
   cudaStream_t st = ctx->stream;
-  k_sort_init<<<(unsigned)((total_bins + 255) / 256), 256, 0, st>>>(d_starts, sh.NB, nbins, fb, total_bins,
-                                                                    (u32*)p_reg);
-  EON_LAUNCHED(ctx);
+  const unsigned grid_tiles = (unsigned)(tiles * ncols);
+
+  phase_begin(ctx, PH_MSM_DIGITS);
+  EON_CUDA(ctx, cudaMemsetAsync(bin_count, 0, total_bins * sizeof(u32), st));
   if (sh.merged)
-    k_sort_coarse<true><<<(unsigned)(tiles * ncols), SORT_THREADS, smem_coarse, st>>>(
-        d_scalars, n, ld, (u32)ncols, sh, nbins, fb, tile, (u32*)p_reg, (u32*)p_pay, (unsigned short*)p_key);
+    k_bin_hist<true><<<grid_tiles, SORT_THREADS, tile_bins * sizeof(u32), st>>>(d_scalars, n, ld, (u32)ncols, sh, nbins,
+                                                                                fb, tile, bin_count);
   else
-    k_sort_coarse<false><<<(unsigned)(tiles * ncols), SORT_THREADS, smem_coarse, st>>>(
-        d_scalars, n, ld, (u32)ncols, sh, nbins, fb, tile, (u32*)p_reg, (u32*)p_pay, (unsigned short*)p_key);
+    k_bin_hist<false><<<grid_tiles, SORT_THREADS, tile_bins * sizeof(u32), st>>>(d_scalars, n, ld, (u32)ncols, sh, nbins,
+                                                                                 fb, tile, bin_count);
   EON_LAUNCHED(ctx);
+  k_bin_scan<<<(unsigned)nseg, 1024, 0, st>>>(bin_count, nbins, tmp_start, region_cursor);
+  EON_LAUNCHED(ctx);
+  phase_end(ctx, PH_MSM_DIGITS);
+
+  phase_begin(ctx, PH_MSM_SCATTER);
+  if (sh.rounds)  // unused slots (bucket padding, segment tails) must read as ENTRY_NONE
+    EON_CUDA(ctx, cudaMemsetAsync(d_entries, 0xff, nseg * sh.seg_cap * sizeof(u32), st));
+  if (sh.merged)
+    k_sort_coarse<true><<<grid_tiles, SORT_THREADS, smem_coarse, st>>>(
+        d_scalars, n, ld, (u32)ncols, sh, nbins, fb, tile, region_cursor, (u32*)p_pay, (unsigned short*)p_key);
+  else
+    k_sort_coarse<false><<<grid_tiles, SORT_THREADS, smem_coarse, st>>>(
+        d_scalars, n, ld, (u32)ncols, sh, nbins, fb, tile, region_cursor, (u32*)p_pay, (unsigned short*)p_key);
+  EON_LAUNCHED(ctx);
+  phase_end(ctx, PH_MSM_SCATTER);
+
+  phase_begin(ctx, PH_MSM_SCAN);
+  k_sort_count<<<(unsigned)total_bins, SORT_THREADS, 0, st>>>((const unsigned short*)p_key, tmp_start, region_cursor,
+                                                              sh.NB, nbins, fb, sh.seg_cap, d_hist);
+  EON_LAUNCHED(ctx);
+  EON_TRY(msm_scan_run(ctx, d_hist, d_cur, sh.NB, 1u << sh.rounds, d_seg_total, nseg));
+  phase_end(ctx, PH_MSM_SCAN);
+
+  phase_begin(ctx, PH_MSM_SCATTER);
   static const int order_env = getenv("EON_SORT_ORDERED") ? atoi(getenv("EON_SORT_ORDERED")) : 1;
   if (plan.on && plan.nbins > 1 && plan.nbins <= SLICE_ORDER_MAX && order_env)
     k_sort_fine<true><<<(unsigned)total_bins, SORT_FINE_THREADS, smem_fine + ((size_t)plan.nbins << fb) * sizeof(u32), st>>>(
-        (const u32*)p_pay, (const unsigned short*)p_key, (const u32*)p_reg, d_starts, d_seg_total, sh.NB, nbins, fb,
-        sh.seg_cap, plan.shift, plan.nbins, d_ends, d_entries);
+        (const u32*)p_pay, (const unsigned short*)p_key, tmp_start, region_cursor, d_hist, d_seg_total, sh.NB, nbins, fb,
+        sh.seg_cap, plan.shift, plan.nbins, d_cur, d_entries);
   else
     k_sort_fine<false><<<(unsigned)total_bins, SORT_FINE_THREADS, smem_fine, st>>>(
-        (const u32*)p_pay, (const unsigned short*)p_key, (const u32*)p_reg, d_starts, d_seg_total, sh.NB, nbins, fb,
-        sh.seg_cap, 0u, 1u, d_ends, d_entries);
+        (const u32*)p_pay, (const unsigned short*)p_key, tmp_start, region_cursor, d_hist, d_seg_total, sh.NB, nbins, fb,
+        sh.seg_cap, 0u, 1u, d_cur, d_entries);
   EON_LAUNCHED(ctx);
+  phase_end(ctx, PH_MSM_SCATTER);
   return EON_OK;
 }
 
