@@ -192,6 +192,21 @@ int eon_kzg_commit_lde_dev(eon_ctx* ctx, const uint64_t* d_evals, unsigned log_h
 int eon_kzg_commit_lde(eon_ctx* ctx, const uint64_t* h_evals, unsigned log_h, size_t width, const uint64_t shift[4],
                        uint64_t* h_commit_xy, eon_handle* out_handle, unsigned lde_log_size,
                        const uint64_t lde_shift[4], uint64_t* h_lde_out);
+/* Pcs::commit_quotient (trait default, commit/src/pcs.rs:82-102) in one call.  `evals`: the quotient
+ * evaluations on shift*<omega_{2^log_size}>, natural order, (1 << log_size) x width.  Chunk i (of
+ * 2^log_chunks) is rows i, i + 2^log_chunks, ... (split_evals, commit/src/domain.rs:188-221) on the coset
+ * shift*omega^i of size 2^(log_size - log_chunks) (split_domains, domain.rs:174-186); each chunk is committed
+ * exactly as eon_kzg_commit would commit it, but nothing is de-interleaved on the host (a chunk is a pitched
+ * view of the same device buffer) and ONE batched MSM covers every column of every chunk.
+ *   h_commit_xy[(i*width + c)*8]  = commitment of column c of chunk i
+ *   out_handles[i]               = prover data (coefficients) of chunk i, as from eon_kzg_commit
+ * Fails with EON_ERR_SRS_TOO_SHORT if srs_size < 2^(log_size - log_chunks). */
+int eon_kzg_commit_quotient(eon_ctx* ctx, const uint64_t* h_evals, unsigned log_size, size_t width,
+                            unsigned log_chunks, const uint64_t shift[4], uint64_t* h_commit_xy,
+                            eon_handle* out_handles);
+int eon_kzg_commit_quotient_dev(eon_ctx* ctx, const uint64_t* d_evals, unsigned log_size, size_t width,
+                                unsigned log_chunks, const uint64_t shift[4], uint64_t* h_commit_xy,
+                                eon_handle* out_handles);
 /* KzgMmcs::commit (kzg/src/mmcs.rs:155-190) for ONE matrix: the columns are taken as polynomials
  * in COEFFICIENT form (no iDFT); `rows` may be any height (not only powers of two).
  * commitment[c] = commit_column(matrix[:, c]) (mmcs.rs:155-165).  The matrix is kept on the device
@@ -214,6 +229,14 @@ int eon_kzg_evals_on_coset_dev(eon_ctx* ctx, eon_handle h, unsigned log_size, co
  * (quotient_and_eval, util.rs:100-111, then commit_column). */
 int eon_kzg_open(eon_ctx* ctx, eon_handle h, const uint64_t* h_points, size_t npoints, uint64_t* h_values,
                  uint64_t* h_witness_xy);
+/* open (pcs.rs:289-335) of `nmat` committed matrices in one call: matrix m (handles[m]) is opened at its
+ * npoints[m] points, taken in order from h_points (4 limbs each, concatenated over the matrices).  Outputs are
+ * laid out [matrix][point][column] like the nested OpenedValues / KzgProof of the reference:
+ *   h_values[k*4], h_witness_xy[k*8]  with  k = sum_{m' < m} npoints[m']*width[m'] + p*width[m] + c
+ * Every quotient is written beside the others and ONE batched MSM yields all witnesses (heights may differ;
+ * results are identical to eon_kzg_open per matrix). */
+int eon_kzg_open_batch(eon_ctx* ctx, size_t nmat, const eon_handle* handles, const size_t* npoints,
+                       const uint64_t* h_points, uint64_t* h_values, uint64_t* h_witness_xy);
 int eon_handle_dims(eon_ctx* ctx, eon_handle h, unsigned* log_h, size_t* width);
 int eon_handle_free(eon_ctx* ctx, eon_handle h);
 

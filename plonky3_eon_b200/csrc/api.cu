@@ -791,6 +791,95 @@ int eon_kzg_commit_lde(eon_ctx* ctx, const uint64_t* h_evals, unsigned log_h, si
                          h_lde_out);
 }
 
+// ---- Pcs::commit_quotient (commit/src/pcs.rs:82-102) ---------------------------------------------
+// The trait default splits the quotient evaluations on shift*<omega_{2^log_size}> into 2^log_chunks matrices
+// (row r -> chunk r mod 2^log_chunks, commit/src/domain.rs:188-221), pairs chunk i with the coset
+// shift*omega^i of size 2^(log_size - log_chunks) (domain.rs:174-186) and commits them one after the other.
+// Here nothing is de-interleaved: chunk i IS the column group [i*width, (i+1)*width) of the same buffer
+// read with a row pitch of 2^log_chunks * width, the coset iDFTs write side by side into one
+// h x (chunks*width) coefficient matrix, and ONE batched MSM commits every column of every chunk.
+static int kzg_commit_quotient_locked(eon_ctx* ctx, const Fr* d_evals, unsigned log_size, size_t width,
+                                      unsigned log_chunks, const uint64_t shift[4], uint64_t* h_commit_xy,
+                                      eon_handle* out_handles) {
+  if (log_chunks > log_size) return fail(ctx, EON_ERR_BAD_ARG, "more chunks than quotient rows");
+  if (log_chunks > 16) return fail(ctx, EON_ERR_BAD_ARG, "too many quotient chunks");
+  EON_TRY(check_dims(ctx, log_size, width));
+  Fr s;
+  EON_TRY(check_shift(ctx, shift, &s));
+  if (!out_handles) return fail(ctx, EON_ERR_BAD_ARG, "null handle pointer");
+  const size_t nchunks = (size_t)1 << log_chunks;
+  for (size_t i = 0; i < nchunks; i++) out_handles[i] = 0;
+  const unsigned log_h = log_size - log_chunks;
+  const size_t h = (size_t)1 << log_h;
+  const size_t cw = nchunks * width;
+  if (cw > 0xffffffffull) return fail(ctx, EON_ERR_BAD_ARG, "width too large");
+  if (h > ctx->srs_n) {  // ensure_supported(height - 1) of every chunk, kzg/src/pcs.rs:238-240
+    char b[128];
+    snprintf(b, sizeof(b), "DegreeTooLarge: degree %zu > max %zu", h - 1, ctx->srs_n ? ctx->srs_n - 1 : 0);
+    return fail(ctx, EON_ERR_SRS_TOO_SHORT, b);
+  }
+  if (width && (!d_evals || !h_commit_xy)) return fail(ctx, EON_ERR_BAD_ARG, "null buffer");
+  void *d_comb = nullptr, *d_res = nullptr;
+  EON_TRY(scratch_get(ctx, SC_QUOT, h * cw * sizeof(Fr) + 32, &d_comb));
+  EON_TRY(scratch_get(ctx, SC_MSM_RESULT, cw * sizeof(G1Affine) + 64, &d_res));
+  const Fr g = fr_two_adic_generator(log_size);
+  Fr si = s;
+  for (size_t i = 0; i < nchunks; i++) {
+    EON_TRY(ntt_inverse(ctx, d_evals + i * width, (Fr*)d_comb + i * width, log_h, width, si, LAYOUT_NATURAL, cw, cw));
+    si = fp_mul(si, g);
+  }
+  EON_TRY(msm_run(ctx, ctx->d_srs, (const Fr*)d_comb, h, cw, cw, (G1Affine*)d_res));
+  if (cw)
+    EON_CUDA(ctx, cudaMemcpyAsync(h_commit_xy, d_res, cw * sizeof(G1Affine), cudaMemcpyDeviceToHost, ctx->stream));
+  // MatrixProverData.coeffs of every chunk (pcs.rs:252-256): dense h x width matrices behind their own handles
+  std::vector<std::pair<Fr*, size_t>> bufs;
+  int rc = EON_OK;
+  for (size_t i = 0; rc == EON_OK && i < nchunks; i++) {
+    Fr* d_coeffs = nullptr;
+    size_t cap = 0;
+    rc = coeff_buffer_get(ctx, mat_bytes(log_h, width) + 32, &d_coeffs, &cap);
+    if (rc != EON_OK) break;
+    bufs.push_back(std::make_pair(d_coeffs, cap));
+    if (width) {
+      cudaError_t e = cudaMemcpy2DAsync(d_coeffs, width * sizeof(Fr), (const Fr*)d_comb + i * width, cw * sizeof(Fr),
+                                        width * sizeof(Fr), h, cudaMemcpyDeviceToDevice, ctx->stream);
+      if (e != cudaSuccess) rc = fail(ctx, EON_ERR_CUDA, std::string("chunk coefficient copy failed: ") + cudaGetErrorString(e));
+    }
+  }
+  if (rc == EON_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = fail(ctx, EON_ERR_CUDA, "commit_quotient failed");
+  if (rc != EON_OK) {
+    cudaStreamSynchronize(ctx->stream);
+    for (auto& b : bufs) cudaFree(b.first);
+    return rc;
+  }
+  for (size_t i = 0; i < nchunks; i++) out_handles[i] = handle_new(ctx, bufs[i].first, h, log_h, width, bufs[i].second);
+  return EON_OK;
+}
+
+int eon_kzg_commit_quotient_dev(eon_ctx* ctx, const uint64_t* d_evals, unsigned log_size, size_t width,
+                                unsigned log_chunks, const uint64_t shift[4], uint64_t* h_commit_xy,
+                                eon_handle* out_handles) {
+  if (!ctx) return EON_ERR_BAD_ARG;
+  Lock lk(ctx);
+  EON_TRY(set_device(ctx));
+  return kzg_commit_quotient_locked(ctx, (const Fr*)d_evals, log_size, width, log_chunks, shift, h_commit_xy,
+                                    out_handles);
+}
+
+int eon_kzg_commit_quotient(eon_ctx* ctx, const uint64_t* h_evals, unsigned log_size, size_t width, unsigned log_chunks,
+                            const uint64_t shift[4], uint64_t* h_commit_xy, eon_handle* out_handles) {
+  if (!ctx) return EON_ERR_BAD_ARG;
+  Lock lk(ctx);
+  EON_TRY(set_device(ctx));
+  EON_TRY(check_dims(ctx, log_size, width));
+  const size_t b = mat_bytes(log_size, width);
+  if (b && !h_evals) return fail(ctx, EON_ERR_BAD_ARG, "null evals");
+  void* d_in = nullptr;
+  EON_TRY(scratch_get(ctx, SC_IO_A, b + 32, &d_in));
+  if (b) EON_CUDA(ctx, cudaMemcpyAsync(d_in, h_evals, b, cudaMemcpyHostToDevice, ctx->stream));
+  return kzg_commit_quotient_locked(ctx, (const Fr*)d_in, log_size, width, log_chunks, shift, h_commit_xy, out_handles);
+}
+
 static int find_handle(eon_ctx* ctx, eon_handle h, ProverMatrix* pm) {
   auto it = ctx->handles.find(h);
   if (it == ctx->handles.end()) return fail(ctx, EON_ERR_BAD_HANDLE, "unknown prover-data handle");
@@ -950,6 +1039,64 @@ int eon_kzg_open(eon_ctx* ctx, eon_handle h, const uint64_t* h_points, size_t np
   EON_TRY(msm_run(ctx, ctx->d_srs, (const Fr*)d_quot, rows ? rows - 1 : 0, ncols, ncols, (G1Affine*)d_wit));
   EON_CUDA(ctx, cudaMemcpyAsync(h_values, d_vals, ncols * sizeof(Fr), cudaMemcpyDeviceToHost, ctx->stream));
   EON_CUDA(ctx, cudaMemcpyAsync(h_witness_xy, d_wit, ncols * sizeof(G1Affine), cudaMemcpyDeviceToHost, ctx->stream));
+  EON_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return EON_OK;
+}
+
+// KzgPcs::open over every (matrix, point) of a call at once (kzg/src/pcs.rs:289-335 walks rounds, matrices, points
+// and columns one commit_column at a time): all quotients land side by side in one matrix and ONE batched MSM
+// produces every witness.  Columns of shorter matrices are zero below their own length.
+int eon_kzg_open_batch(eon_ctx* ctx, size_t nmat, const eon_handle* handles, const size_t* npoints,
+                       const uint64_t* h_points, uint64_t* h_values, uint64_t* h_witness_xy) {
+  if (!ctx) return EON_ERR_BAD_ARG;
+  Lock lk(ctx);
+  EON_TRY(set_device(ctx));
+  if (nmat == 0) return EON_OK;
+  if (!handles || !npoints) return fail(ctx, EON_ERR_BAD_ARG, "null handle / point-count array");
+  std::vector<ProverMatrix> pms(nmat);
+  size_t total_cols = 0, total_points = 0, max_rows = 0;
+  bool ragged = false;
+  for (size_t m = 0; m < nmat; m++) {
+    EON_TRY(find_handle(ctx, handles[m], &pms[m]));
+    if (npoints[m] == 0 || pms[m].width == 0) {
+      total_points += npoints[m];
+      continue;
+    }
+    if (npoints[m] > (~(size_t)0 - total_cols) / pms[m].width) return fail(ctx, EON_ERR_BAD_ARG, "too many openings");
+    total_cols += npoints[m] * pms[m].width;
+    total_points += npoints[m];
+    max_rows = std::max(max_rows, pms[m].rows);
+  }
+  if (total_cols == 0) return EON_OK;
+  if (!h_points || !h_values || !h_witness_xy) return fail(ctx, EON_ERR_BAD_ARG, "null buffer");
+  for (size_t p = 0; p < total_points; p++)
+    if (!fr_wire_is_canonical(h_points + 4 * p)) return fail(ctx, EON_ERR_BAD_ARG, "opening point is not canonical");
+  for (size_t m = 0; m < nmat; m++)
+    if (npoints[m] && pms[m].width && pms[m].rows != max_rows) ragged = true;
+  // the quotient of a length-h polynomial has h-1 coefficients (commit_column(&quotient), pcs.rs:316; util.rs:38)
+  if (max_rows && max_rows - 1 > ctx->srs_n)
+    return fail(ctx, EON_ERR_SRS_TOO_SHORT, "DegreeTooLarge: quotient longer than the SRS");
+  if (total_cols > 0xffffffffull || (max_rows && total_cols > (~(size_t)0) / (max_rows * sizeof(Fr))))
+    return fail(ctx, EON_ERR_BAD_ARG, "opening too large");
+  void *d_quot = nullptr, *d_vals = nullptr;
+  EON_TRY(scratch_get(ctx, SC_QUOT, max_rows * total_cols * sizeof(Fr) + 32, &d_quot));
+  EON_TRY(scratch_get(ctx, SC_IO_B, total_cols * (sizeof(Fr) + sizeof(G1Affine)) + 64, &d_vals));
+  void* d_wit = (char*)d_vals + total_cols * sizeof(Fr);
+  if (ragged) EON_CUDA(ctx, cudaMemsetAsync(d_quot, 0, max_rows * total_cols * sizeof(Fr), ctx->stream));
+  size_t col = 0, pt = 0;
+  for (size_t m = 0; m < nmat; m++) {
+    const ProverMatrix& pm = pms[m];
+    for (size_t p = 0; p < npoints[m]; p++, pt++) {
+      if (pm.width == 0) continue;
+      Fr z = fr_from_wire(h_points + 4 * pt);
+      EON_TRY(quotient_run(ctx, pm.d_coeffs, pm.rows, pm.width, total_cols, z, (Fr*)d_quot + col, (Fr*)d_vals + col));
+      col += pm.width;
+    }
+  }
+  EON_TRY(msm_run(ctx, ctx->d_srs, (const Fr*)d_quot, max_rows ? max_rows - 1 : 0, total_cols, total_cols,
+                  (G1Affine*)d_wit));
+  EON_CUDA(ctx, cudaMemcpyAsync(h_values, d_vals, total_cols * sizeof(Fr), cudaMemcpyDeviceToHost, ctx->stream));
+  EON_CUDA(ctx, cudaMemcpyAsync(h_witness_xy, d_wit, total_cols * sizeof(G1Affine), cudaMemcpyDeviceToHost, ctx->stream));
   EON_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return EON_OK;
 }

@@ -73,6 +73,10 @@ _SIGS = {
     "eon_kzg_commit_dev": (C.c_int, [C.c_void_p, _u64p, C.c_uint, C.c_size_t, _u64p, _u64p, C.POINTER(C.c_uint64)]),
     "eon_kzg_commit_coeffs": (C.c_int, [C.c_void_p, _u64p, C.c_size_t, C.c_size_t, _u64p, C.POINTER(C.c_uint64)]),
     "eon_kzg_commit_coeffs_dev": (C.c_int, [C.c_void_p, _u64p, C.c_size_t, C.c_size_t, _u64p, C.POINTER(C.c_uint64)]),
+    # handle / point-count arrays are numpy uint64 buffers (eon_handle and size_t are both 64-bit here)
+    "eon_kzg_commit_quotient": (C.c_int, [C.c_void_p, _u64p, C.c_uint, C.c_size_t, C.c_uint, _u64p, _u64p, _u64p]),
+    "eon_kzg_commit_quotient_dev": (C.c_int, [C.c_void_p, _u64p, C.c_uint, C.c_size_t, C.c_uint, _u64p, _u64p, _u64p]),
+    "eon_kzg_open_batch": (C.c_int, [C.c_void_p, C.c_size_t, _u64p, _u64p, _u64p, _u64p, _u64p]),
     "eon_kzg_read_coeffs": (C.c_int, [C.c_void_p, C.c_uint64, _u64p]),
     "eon_kzg_evals_on_coset": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint, _u64p, _u64p]),
     "eon_kzg_evals_on_coset_dev": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint, _u64p, _u64p]),

@@ -86,16 +86,25 @@ class GpuKzgMmcs:
         witnesses[matrix] = uint64 [w, 8])."""
         max_height = max((m.shape[0] for m in prover_data.matrices), default=0)
         lmax = _log2_ceil(max_height)
-        opened, witnesses = [], []
-        for m, handle in zip(prover_data.matrices, prover_data.handles):
-            h, w = m.shape[0], m.shape[1]
-            li = self.local_index(index, h, lmax)
-            pts = field.to_wire(li).reshape(1, 4)           # Fr::new(local_index as u64)
-            vals = np.zeros((1, w, 4), dtype=np.uint64)
-            wits = np.zeros((1, w, 8), dtype=np.uint64)
-            self.ctx.call("eon_kzg_open", C.c_uint64(handle), pts, 1, vals, wits)
-            opened.append(vals[0])
-            witnesses.append(wits[0])
+        # every matrix at its own local index through ONE eon_kzg_open_batch (heights differ: the shorter
+        # quotients are zero-filled below their length and share the single batched MSM)
+        mats = prover_data.matrices
+        if not mats:
+            return [], []
+        pts = np.zeros((len(mats), 4), dtype=np.uint64)
+        for i, m in enumerate(mats):
+            pts[i] = field.to_wire(self.local_index(index, m.shape[0], lmax))   # Fr::new(local_index as u64)
+        total = sum(m.shape[1] for m in mats)
+        vals = np.zeros((max(total, 1), 4), dtype=np.uint64)
+        wits = np.zeros((max(total, 1), 8), dtype=np.uint64)
+        self.ctx.call("eon_kzg_open_batch", len(mats), np.array(prover_data.handles, dtype=np.uint64),
+                      np.ones(len(mats), dtype=np.uint64), pts, vals, wits)
+        opened, witnesses, k = [], [], 0
+        for m in mats:
+            w = m.shape[1]
+            opened.append(vals[k:k + w])
+            witnesses.append(wits[k:k + w])
+            k += w
         return opened, witnesses
 
     def get_matrices(self, prover_data):

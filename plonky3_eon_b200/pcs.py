@@ -192,9 +192,20 @@ class GpuKzgPcs:
 
     def commit_quotient(self, quotient_domain, quotient_evaluations, num_chunks):
         """commit/src/pcs.rs:82-102 (trait default)."""
-        subs = quotient_domain.split_evals(num_chunks, quotient_evaluations)
         doms = quotient_domain.split_domains(num_chunks)
-        return self.commit(zip(doms, subs), _use_hint=False)   # nobody evaluates quotient chunks on a larger coset
+        a = _as_matrix(quotient_evaluations)
+        assert a.shape[0] == quotient_domain.size(), "evaluation height must match domain size"
+        w = a.shape[1]
+        # one call: the chunks are pitched views of the uploaded matrix (no split_evals copy on the host,
+        # domain.rs:188-221) and one batched MSM commits all of their columns (eon_kzg_commit_quotient)
+        cols = np.zeros((num_chunks, w, 8), dtype=np.uint64)
+        handles = np.zeros(num_chunks, dtype=np.uint64)
+        self.ctx.call("eon_kzg_commit_quotient", a, quotient_domain.log_size, w, field.log2_strict(num_chunks),
+                      field.to_wire(quotient_domain.shift), cols, handles)
+        # MatrixProverData.evals of chunk i = rows i, i + num_chunks, ... (a strided view, not a copy)
+        prover = [MatrixProverData(doms[i], a[i::num_chunks], int(handles[i]), self.ctx, None)
+                  for i in range(num_chunks)]
+        return [cols[i] for i in range(num_chunks)], prover
 
     def get_evaluations_on_domain(self, prover_data, idx, domain):
         """pcs.rs:267-287; the quadratic Horner loop of the reference is replaced by
@@ -214,24 +225,49 @@ class GpuKzgPcs:
         """pcs.rs:289-335.  Input: list of (prover_data, points_per_matrix).  Returns
         (opened_values[round][matrix][point] = uint64 [w, 4],
          proof[round][matrix][point]        = uint64 [w, 8] witnesses)."""
-        opened_values, rounds = [], []
+        # every (round, matrix, point, column) of the call goes through ONE eon_kzg_open_batch: all quotients
+        # side by side, one batched MSM for all witnesses (the reference commits them one column at a time)
+        mats, counts, pts = [], [], []
         for prover_data, points_per_matrix in commitment_data_with_opening_points:
             assert len(prover_data) == len(points_per_matrix)
-            mv, mp = [], []
             for m, points in zip(prover_data, points_per_matrix):
-                w = m.evals.shape[1]
-                npts = len(points)
-                pts = np.zeros((max(npts, 1), 4), dtype=np.uint64)
-                for i, z in enumerate(points):
-                    pts[i] = _shift_wire(z)
-                vals = np.zeros((npts, w, 4), dtype=np.uint64)
-                wits = np.zeros((npts, w, 8), dtype=np.uint64)
-                self.ctx.call("eon_kzg_open", C.c_uint64(m.handle), pts, npts, vals, wits)
-                mv.append([vals[i] for i in range(npts)])
-                mp.append([wits[i] for i in range(npts)])
+                mats.append(m)
+                counts.append(len(points))
+                pts.extend(_shift_wire(z) for z in points)
+        widths = [m.evals.shape[1] for m in mats]
+        total = sum(c * w for c, w in zip(counts, widths))
+        vals = np.zeros((max(total, 1), 4), dtype=np.uint64)
+        wits = np.zeros((max(total, 1), 8), dtype=np.uint64)
+        if mats:
+            handles = np.array([m.handle for m in mats], dtype=np.uint64)
+            npts = np.array(counts, dtype=np.uint64)
+            parr = np.ascontiguousarray(np.array(pts, dtype=np.uint64).reshape(-1, 4)) if pts else np.zeros((1, 4), np.uint64)
+            self.ctx.call("eon_kzg_open_batch", len(mats), handles, npts, parr, vals, wits)
+        opened_values, rounds, k, i = [], [], 0, 0
+        for prover_data, _ in commitment_data_with_opening_points:
+            mv, mp = [], []
+            for _m in prover_data:
+                w, c = widths[i], counts[i]
+                mv.append([vals[k + p * w:k + (p + 1) * w] for p in range(c)])
+                mp.append([wits[k + p * w:k + (p + 1) * w] for p in range(c)])
+                k += c * w
+                i += 1
             opened_values.append(mv)
             rounds.append(mp)
         return opened_values, rounds
+
+    def open_matrix(self, m, points):
+        """One matrix at `points` through eon_kzg_open (what open() did before the batched call; kept for the
+        parity tests of the two entry points against each other)."""
+        w = m.evals.shape[1]
+        npts = len(points)
+        pts = np.zeros((max(npts, 1), 4), dtype=np.uint64)
+        for i, z in enumerate(points):
+            pts[i] = _shift_wire(z)
+        vals = np.zeros((npts, w, 4), dtype=np.uint64)
+        wits = np.zeros((npts, w, 8), dtype=np.uint64)
+        self.ctx.call("eon_kzg_open", C.c_uint64(m.handle), pts, npts, vals, wits)
+        return [vals[i] for i in range(npts)], [wits[i] for i in range(npts)]
 
     def verify(self, *a, **k):  # pragma: no cover
         raise NotImplementedError("verification (pairings) stays on the CPU side: kzg/src/pcs.rs:337-401")
