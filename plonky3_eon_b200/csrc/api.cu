@@ -1115,7 +1115,7 @@ int eon_bench_modmul(eon_ctx* ctx, int field, double* out_gmuls) {
   return bench_modmul(ctx, field, 0, out_gmuls);
 }
 int eon_bench_modmul_variant(eon_ctx* ctx, int field, int variant, double* out_gmuls) {
-  if (!ctx || !out_gmuls || variant < 0 || variant > 3) return EON_ERR_BAD_ARG;
+  if (!ctx || !out_gmuls || variant < 0 || variant > 5) return EON_ERR_BAD_ARG;
   Lock lk(ctx);
   EON_TRY(set_device(ctx));
   return bench_modmul(ctx, field, variant, out_gmuls);

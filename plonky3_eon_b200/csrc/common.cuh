@@ -100,6 +100,7 @@ struct eon_ctx {
 
   eon::Scratch scratch[eon::SC_COUNT];
   std::map<eon::TwiddleKey, eon::Fr*> twiddles;
+  size_t twiddle_bytes = 0;  // device bytes behind `twiddles` (bounded: see get_twiddles)
 
   eon::G1Affine* d_srs = nullptr;
   size_t srs_n = 0;

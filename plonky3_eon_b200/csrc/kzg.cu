@@ -8,6 +8,7 @@
 //   C  replay every chunk from its incoming carry, emit q      (thread per chunk x column)
 // ~2 modmul per coefficient; exact field arithmetic => identical quotient and evaluation.
 #include "common.cuh"
+#include "fp_shoup.cuh"
 
 namespace eon {
 
@@ -217,6 +218,32 @@ __global__ void __launch_bounds__(256) k_modmul_peak(Fp<PP>* out, u32 iters, u32
   Fp<PP> a = fp_from_u64<PP>(seed + threadIdx.x + 1);
   Fp<PP> b = fp_from_u64<PP>(seed * 3 + blockIdx.x + 7);
   Fp<PP> c = fp_from_u64<PP>(seed * 5 + threadIdx.x * 11 + 13);
+  if (VARIANT >= 4) {
+    // fixed-operand products as the NTT butterflies would use them: the multiplier (b, b2) never changes, the
+    // running values stay lazily reduced.  4 = Shoup form (fp_shoup.cuh; bq / b2q stand in for the precomputed
+    // floor(w 2^256 / p): the instruction stream does not depend on their values), 5 = word-serial Montgomery
+    // product without the final correction (fp_mul_lazy, what k_ntt_pass runs today).
+    Fp<PP> b2 = fp_from_u64<PP>(seed * 7 + blockIdx.x + 3);
+    Fp<PP> bq = fp_from_u64<PP>(seed * 9 + threadIdx.x + 5), b2q = fp_from_u64<PP>(seed * 11 + threadIdx.x + 9);
+    for (u32 it = 0; it < iters; it++) {
+      u32 t[8], u[8];
+      if (VARIANT == 4) {
+        shoup::mul_lazy<PP>(t, a.v, b.v, bq.v);
+        shoup::mul_lazy<PP>(u, c.v, b2.v, b2q.v);
+      } else {
+        fp_mul_lazy_cios<PP>(t, b.v, a.v);
+        fp_mul_lazy_cios<PP>(u, b2.v, c.v);
+      }
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        a.v[i] = t[i];
+        c.v[i] = u[i];
+      }
+      c.v[0] ^= a.v[7];  // the two chains stay in step, like a = f(a, b); c = f(c, a) below
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = fp_add(shoup::canon_3p<PP>(a.v), shoup::canon_3p<PP>(c.v));
+    return;
+  }
   for (u32 it = 0; it < iters; it++) {
     a = bench_product<PP, VARIANT>(a, b);
     c = bench_product<PP, VARIANT>(c, a);
@@ -229,6 +256,8 @@ static void launch_modmul_peak(int variant, unsigned blocks, cudaStream_t st, Fp
   if (variant == 1) k_modmul_peak<PP, 1><<<blocks, 256, 0, st>>>(out, iters, seed);
   else if (variant == 2) k_modmul_peak<PP, 2><<<blocks, 256, 0, st>>>(out, iters, seed);
   else if (variant == 3) k_modmul_peak<PP, 3><<<blocks, 256, 0, st>>>(out, iters, seed);
+  else if (variant == 4) k_modmul_peak<PP, 4><<<blocks, 256, 0, st>>>(out, iters, seed);
+  else if (variant == 5) k_modmul_peak<PP, 5><<<blocks, 256, 0, st>>>(out, iters, seed);
   else k_modmul_peak<PP, 0><<<blocks, 256, 0, st>>>(out, iters, seed);
 }
 

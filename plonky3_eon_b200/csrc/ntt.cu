@@ -99,7 +99,23 @@ static int get_twiddles(eon_ctx* ctx, unsigned log_n, const Fr& shift, int inver
   }
   Fr* d_tab = nullptr;
   size_t entries = ((size_t)1 << log_n) - 1;
-  EON_CUDA(ctx, cudaMalloc(&d_tab, (entries + 1) * sizeof(Fr)));
+  // the cache is keyed by (size, shift, direction); callers with ever-changing shifts must not grow it without
+  // bound: past the budget every cached table is dropped (stream-ordered work on them finishes first)
+  static size_t budget = 0;
+  if (!budget) {
+    const char* e = getenv("EON_TWIDDLE_CACHE_MB");
+    budget = (e && atoll(e) > 0 ? (size_t)atoll(e) : (size_t)8192) << 20;
+  }
+  const size_t tab_bytes = (entries + 1) * sizeof(Fr);
+  if (ctx->twiddle_bytes + tab_bytes > budget && !ctx->twiddles.empty()) {
+    EON_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->aux_stream) EON_CUDA(ctx, cudaStreamSynchronize(ctx->aux_stream));
+    for (auto& kv : ctx->twiddles) cudaFree(kv.second);
+    ctx->twiddles.clear();
+    ctx->twiddle_bytes = 0;
+  }
+  EON_CUDA(ctx, cudaMalloc(&d_tab, tab_bytes));
+  ctx->twiddle_bytes += tab_bytes;
   void* d_small = nullptr;
   EON_TRY(scratch_get(ctx, SC_SMALL, 2 * 32 * sizeof(Fr), &d_small));
   EON_CUDA(ctx, cudaMemcpyAsync(d_small, hb.data(), hb.size() * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));

@@ -1,6 +1,7 @@
 // Host-compiled view of csrc/fp.cuh + ec.cuh (software carry flag) so that the field and
 // curve arithmetic shipped in the CUDA library can be checked against the oracle without a GPU.
 #include "../../plonky3_eon_b200/csrc/ec.cuh"
+#include "../../plonky3_eon_b200/csrc/fp_shoup.cuh"
 #include <string.h>
 using namespace eon;
 
@@ -55,6 +56,21 @@ void host_fp_mul_lazy(int which, int variant, const uint32_t* a, const uint32_t*
       else if (variant == 1) fp_mul_lazy_split<FqParams>(r, a, b);
       else fp_sqr_lazy_split<FqParams>(r, a);
     }
+  }
+}
+// Fixed-operand product (fp_shoup.cuh): r = a*w - q~*p in [0, 3p) for a = any 256-bit value, w < p and
+// wq = floor(w 2^256 / p); canon != 0 additionally reduces r to [0, p).
+void host_shoup_mul(int which, int canon, const uint32_t* a, const uint32_t* w, const uint32_t* wq, uint32_t* r, int n) {
+  for (int i = 0; i < n; i++, a += 8, w += 8, wq += 8, r += 8) {
+    uint32_t t[8];
+    if (which == 0) {
+      shoup::mul_lazy<FrParams>(t, a, w, wq);
+      if (canon) { Fr c = shoup::canon_3p<FrParams>(t); memcpy(t, c.v, 32); }
+    } else {
+      shoup::mul_lazy<FqParams>(t, a, w, wq);
+      if (canon) { Fq c = shoup::canon_3p<FqParams>(t); memcpy(t, c.v, 32); }
+    }
+    memcpy(r, t, 32);
   }
 }
 // T[0..16) = a * b (variant 0) or a^2 (variant 1) over full 256-bit operands

@@ -17,7 +17,7 @@ LIB = os.path.join(HERE, "host", "libhosteon.so")
 @pytest.fixture(scope="module")
 def lib():
     csrc = os.path.join(HERE, "..", "plonky3_eon_b200", "csrc")
-    deps = [SRC] + [os.path.join(csrc, f) for f in ("fp.cuh", "ec.cuh", "consts.cuh")]
+    deps = [SRC] + [os.path.join(csrc, f) for f in ("fp.cuh", "ec.cuh", "consts.cuh", "fp_shoup.cuh")]
     if not os.path.exists(LIB) or any(os.path.getmtime(d) > os.path.getmtime(LIB) for d in deps):
         subprocess.check_call(["g++", "-O2", "-shared", "-fPIC", "-o", LIB, SRC])
     return ctypes.CDLL(LIB)
@@ -222,3 +222,38 @@ def test_split_product_equals_word_serial(lib, which, mod):
         assert to_int(r1[i]) == to_int(r0[i]), (which, i, hex(x), hex(y))
         assert to_int(r1[i]) < 2 * mod and to_int(r1[i]) % mod == x * y * Rinv % mod
         assert to_int(r2[i]) < 2 * mod and to_int(r2[i]) % mod == x * x * Rinv % mod
+
+
+@pytest.mark.parametrize("which,mod", [(0, fr.P), (1, g1.Q)])
+def test_shoup_fixed_operand_product(lib, which, mod):
+    """fp_shoup.cuh: r = a*w - q~*p with q~ from the truncated high product of a and wq = floor(w 2^256 / p).
+    Checked limb for limb against the same truncated formula in big ints, and: r == a*w (mod p), r < 3p,
+    for a anywhere in [0, 2^256) (all-ones limbs, 4p-1, ...) and w over random and edge twiddles."""
+    rng = np.random.default_rng(77 + which)
+    as_ = _wide_cases(rng, 700)
+    ws = [v % mod for v in _wide_cases(rng, len(as_) - 18)]
+    ws = (ws + EDGE(mod) * 2)[:len(as_)]
+    n = len(as_)
+    wqs = [(w << 256) // mod for w in ws]
+    a = np.array([from_int(x) for x in as_])
+    w = np.array([from_int(x) for x in ws])
+    wq = np.array([from_int(x) for x in wqs])
+    r = np.zeros_like(a)
+    rc = np.zeros_like(a)
+    lib.host_shoup_mul(which, 0, _ptr(a), _ptr(w), _ptr(wq), _ptr(r), n)
+    lib.host_shoup_mul(which, 1, _ptr(a), _ptr(w), _ptr(wq), _ptr(rc), n)
+    M32 = (1 << 32) - 1
+    worst = 0
+    for k in range(n):
+        x, y, yq = as_[k], ws[k], wqs[k]
+        xl = [(x >> (32 * i)) & M32 for i in range(8)]
+        ql = [(yq >> (32 * i)) & M32 for i in range(8)]
+        trunc = sum(xl[i] * ql[j] << (32 * (i + j)) for i in range(8) for j in range(8) if i + j >= 6)
+        qt = trunc >> 256
+        want = (x * y - qt * mod) % (1 << 256)
+        got = to_int(r[k])
+        assert got == want, (which, k, hex(x), hex(y))
+        assert got < 3 * mod and got % mod == x * y % mod
+        assert to_int(rc[k]) == x * y % mod
+        worst = max(worst, got // mod)
+    assert worst <= 2

@@ -11,7 +11,8 @@ import plonky3_eon_b200 as eon  # noqa: E402
 
 ctx = eon.Context(0)
 out = {"imad_tops": ctx.imad_peak_tops(0), "imad_hi_tops": ctx.imad_peak_tops(1), "imad_wide_tops": ctx.imad_peak_tops(2)}
-names = {0: "library", 1: "word_serial", 2: "split", 3: "square_plus_add"}
+names = {0: "library", 1: "word_serial", 2: "split", 3: "square_plus_add", 4: "shoup_fixed_operand_lazy",
+         5: "word_serial_lazy"}
 for field, fname in ((0, "fr"), (1, "fq")):
     for v, vname in names.items():
         out[f"{fname}_{vname}_gmul_s"] = ctx.modmul_gmuls(field, v)
