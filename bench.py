@@ -227,6 +227,8 @@ def run_eon(args):
         ctx.call("eon_srs_set_window_tables", args.window_bits)
     if args.slice_schedule >= 0:                                 # default: the library's own policy
         ctx.call("eon_msm_set_slice_schedule", args.slice_schedule)
+    if args.msm_rounds >= 0:                                     # default: the library's own policy (3 rounds)
+        ctx.call("eon_msm_set_rounds", args.msm_rounds)
     shift_one = field.to_wire(1)
     shift_lde = field.to_wire(SHIFT_LDE)
 
@@ -497,6 +499,8 @@ def run_msm(args):
         ctx.call("eon_srs_set_window_tables", args.window_bits)
     if args.slice_schedule >= 0:
         ctx.call("eon_msm_set_slice_schedule", args.slice_schedule)
+    if args.msm_rounds >= 0:
+        ctx.call("eon_msm_set_rounds", args.msm_rounds)
     first, cnt = edist.index_shard(n, world, rank)
     host = synth_trace(42, cnt, cols)                            # seed 42: bn254/benches/bench_curve.rs:40
     d_sc = torch.from_numpy(host.view(np.int64)).to(dev)
@@ -718,6 +722,8 @@ def main():
                     help="MSM window tables: -1 library default, 0 none (plain c=16), 8..20 explicit")
     ap.add_argument("--slice-schedule", type=int, default=-1,
                     help="MSM round 0 walked by 64 MiB table slice: 1 on, 0 off, -1 the library's policy")
+    ap.add_argument("--msm-rounds", type=int, default=-1,
+                    help="batched-affine pairwise rounds before the XYZZ finisher: -1 the library's policy, 0..6 explicit")
     ap.add_argument("--workload", default="commit", choices=["commit", "msm", "open", "prove-pcs"],
                     help="commit: KZG commit + LDE (the headline metric); msm: standalone MSM (configs[2]); "
                          "open: KzgPcs::open at 2 points")
