@@ -130,6 +130,43 @@ EON_HD void mul_lazy(u32 r[8], const u32 a[8], const u32 w[8], const u32 wq[8]) 
   r[7] = cc::addc(L[7], M[6]);
 }
 
+// limb i of p^-1 mod 2^256
+template <class PP>
+EON_HD constexpr u32 pinv256(int i);
+template <>
+EON_HD constexpr u32 pinv256<FrParams>(int i) { constexpr u32 m[8] = EON_FR_PINV256; return m[i]; }
+template <>
+EON_HD constexpr u32 pinv256<FqParams>(int i) { constexpr u32 m[8] = EON_FQ_PINV256; return m[i]; }
+
+// The operand pair of a twiddle from its Montgomery form rho = w * 2^256 mod p:
+//   w  = rho / 2^256 mod p                      (plain form)
+//   wq = floor(w * 2^256 / p) = (w 2^256 - rho) / p, an exact division, hence = -rho * p^-1 (mod 2^256)
+template <class PP>
+EON_HD void precompute(u32 w[8], u32 wq[8], const Fp<PP>& rho) {
+  fp_from_mont<PP>(w, rho);
+  u32 n[8];
+  n[0] = cc::sub_cc(0u, rho.v[0]);
+#pragma unroll
+  for (int i = 1; i < 7; i++) n[i] = cc::subc_cc(0u, rho.v[i]);
+  n[7] = cc::subc(0u, rho.v[7]);
+  u32 L[8], M[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) L[i] = M[i] = 0;
+  lo_row<0>(L, M, n, pinv256<PP>(0));
+  lo_row<1>(L, M, n, pinv256<PP>(1));
+  lo_row<2>(L, M, n, pinv256<PP>(2));
+  lo_row<3>(L, M, n, pinv256<PP>(3));
+  lo_row<4>(L, M, n, pinv256<PP>(4));
+  lo_row<5>(L, M, n, pinv256<PP>(5));
+  lo_row<6>(L, M, n, pinv256<PP>(6));
+  lo_row<7>(L, M, n, pinv256<PP>(7));
+  wq[0] = L[0];
+  wq[1] = cc::add_cc(L[1], M[0]);
+#pragma unroll
+  for (int k = 2; k < 7; k++) wq[k] = cc::addc_cc(L[k], M[k - 1]);
+  wq[7] = cc::addc(L[7], M[6]);
+}
+
 // r in [0, 3p) -> canonical
 template <class PP>
 EON_HD Fp<PP> canon_3p(const u32 a[8]) {

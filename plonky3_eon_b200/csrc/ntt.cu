@@ -18,6 +18,11 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "fp_shoup.cuh"
+
+#ifndef EON_NTT_SHOUP_DEFAULT
+#define EON_NTT_SHOUP_DEFAULT 0
+#endif
 
 namespace eon {
 
@@ -43,23 +48,53 @@ __device__ __forceinline__ Fr fr_ldg(const uint4* p) {
 __device__ __forceinline__ Fr lz_red(const Fr& a) { Fr r; fp_reduce_2p<FrParams>(r.v, a.v); return r; }
 __device__ __forceinline__ Fr lz_add(const Fr& a, const Fr& b) { Fr r; fp_add_raw(r.v, a.v, b.v); return r; }
 __device__ __forceinline__ Fr lz_sub(const Fr& a, const Fr& b) { Fr r; fp_sub_plus_2p<FrParams>(r.v, a.v, b.v); return r; }
+// A twiddle as the butterflies consume it.  TwM: Montgomery form, multiplied with the word-serial Montgomery
+// product (272 IMAD).  TwS: plain form w plus wq = floor(w 2^256 / r), multiplied with the fixed-operand product
+// of fp_shoup.cuh (214 IMAD; Montgomery-form data times a plain-form twiddle stays in Montgomery form).
+struct TwM { Fr w; };
+struct TwS { Fr w, wq; };
+template <bool SH> struct TwOf { typedef TwM T; };
+template <> struct TwOf<true> { typedef TwS T; };
 // tw canonical (< r), x any 256-bit value -> [0, 2r)
-__device__ __forceinline__ Fr lz_mul(const Fr& tw, const Fr& x) { Fr r; fp_mul_lazy<FrParams>(r.v, tw.v, x.v); return r; }
+__device__ __forceinline__ Fr lz_mul(const TwM& tw, const Fr& x) { Fr r; fp_mul_lazy<FrParams>(r.v, tw.w.v, x.v); return r; }
+__device__ __forceinline__ Fr lz_mul(const TwS& tw, const Fr& x) {
+  u32 t[8];
+  shoup::mul_lazy<FrParams>(t, x.v, tw.w.v, tw.wq.v);  // [0, 3r)
+  Fr r;
+  fp_reduce_2p<FrParams>(r.v, t);                       // -> [0, 2r)
+  return r;
+}
 // forward butterfly: a in [0, 4r), b in [0, 4r) -> both outputs in [0, 4r)
-__device__ __forceinline__ void bf_dit(Fr& a, Fr& b, const Fr& tw) {
+template <class TW>
+__device__ __forceinline__ void bf_dit(Fr& a, Fr& b, const TW& tw) {
   Fr x = lz_red(a), t = lz_mul(tw, b);
   a = lz_add(x, t);
   b = lz_sub(x, t);
 }
 // inverse butterfly: u, v in [0, 2r) -> both outputs in [0, 2r)
-__device__ __forceinline__ void bf_dif(Fr& u, Fr& v, const Fr& tw) {
+template <class TW>
+__device__ __forceinline__ void bf_dif(Fr& u, Fr& v, const TW& tw) {
   Fr s = lz_red(lz_add(u, v));
   v = lz_mul(tw, lz_sub(u, v));
   u = s;
 }
+// entry idx of a twiddle table: 32 bytes (TwM) or 64 bytes (TwS: w then wq)
+template <bool SH>
+__device__ __forceinline__ typename TwOf<SH>::T tw_ldg(const uint4* tab, u64 idx) {
+  typename TwOf<SH>::T t;
+  if constexpr (SH) {
+    t.w = fr_ldg(tab + idx * 4);
+    t.wq = fr_ldg(tab + idx * 4 + 2);
+  } else {
+    t.w = fr_ldg(tab + idx * 2);
+  }
+  return t;
+}
 
 // ---- twiddle tables ---------------------------------------------------------------------
 // tw[(1<<l) - 1 + j] = base[l] * gen[l]^j   for l < log_n, j < 2^l
+// SH: every entry is the pair (plain form, floor(plain * 2^256 / r)) for the fixed-operand product
+template <bool SH>
 __global__ void k_gen_twiddles(Fr* tw, u32 log_n, const Fr* __restrict__ base, const Fr* __restrict__ gen) {
   u64 total = (1ull << log_n) - 1;
   for (u64 idx = blockIdx.x * (u64)blockDim.x + threadIdx.x; idx < total; idx += (u64)gridDim.x * blockDim.x) {
@@ -67,14 +102,31 @@ __global__ void k_gen_twiddles(Fr* tw, u32 log_n, const Fr* __restrict__ base, c
     u64 j = idx + 1 - (1ull << l);
     Fr g = gen[l];
     Fr r = fp_mul(base[l], fp_pow_u64(g, j));
-    tw[idx] = r;
+    if constexpr (SH) {
+      Fr w, wq;
+      shoup::precompute<FrParams>(w.v, wq.v, r);
+      tw[2 * idx] = w;
+      tw[2 * idx + 1] = wq;
+    } else {
+      tw[idx] = r;
+    }
   }
 }
 
-static int get_twiddles(eon_ctx* ctx, unsigned log_n, const Fr& shift, int inverse, const Fr** out) {
+// EON_NTT_SHOUP=1: butterflies multiply by (plain, quotient) twiddle pairs with the fixed-operand product
+static int g_ntt_shoup = -1;
+static bool ntt_use_shoup() {
+  if (g_ntt_shoup < 0) {
+    const char* e = getenv("EON_NTT_SHOUP");
+    g_ntt_shoup = e ? (atoi(e) != 0) : EON_NTT_SHOUP_DEFAULT;
+  }
+  return g_ntt_shoup != 0;
+}
+
+static int get_twiddles(eon_ctx* ctx, unsigned log_n, const Fr& shift, int inverse, bool sh, const Fr** out) {
   TwiddleKey key;
   key.log_n = log_n;
-  key.inverse = inverse;
+  key.inverse = inverse | (sh ? 2 : 0);  // the two table forms are cached side by side
   memcpy(key.shift, shift.v, 32);
   auto it = ctx->twiddles.find(key);
   if (it != ctx->twiddles.end()) {
@@ -106,7 +158,7 @@ static int get_twiddles(eon_ctx* ctx, unsigned log_n, const Fr& shift, int inver
     const char* e = getenv("EON_TWIDDLE_CACHE_MB");
     budget = (e && atoll(e) > 0 ? (size_t)atoll(e) : (size_t)8192) << 20;
   }
-  const size_t tab_bytes = (entries + 1) * sizeof(Fr);
+  const size_t tab_bytes = (entries + 1) * sizeof(Fr) * (sh ? 2 : 1);
   if (ctx->twiddle_bytes + tab_bytes > budget && !ctx->twiddles.empty()) {
     EON_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     if (ctx->aux_stream) EON_CUDA(ctx, cudaStreamSynchronize(ctx->aux_stream));
@@ -123,7 +175,8 @@ static int get_twiddles(eon_ctx* ctx, unsigned log_n, const Fr& shift, int inver
   // pageable memory is staged before returning, so this is safe.
   unsigned blocks = (unsigned)std::min<size_t>((entries + 255) / 256, (size_t)ctx->num_sms * 16);
   if (blocks == 0) blocks = 1;
-  k_gen_twiddles<<<blocks, 256, 0, ctx->stream>>>(d_tab, log_n, (const Fr*)d_small, (const Fr*)d_small + log_n);
+  if (sh) k_gen_twiddles<true><<<blocks, 256, 0, ctx->stream>>>(d_tab, log_n, (const Fr*)d_small, (const Fr*)d_small + log_n);
+  else k_gen_twiddles<false><<<blocks, 256, 0, ctx->stream>>>(d_tab, log_n, (const Fr*)d_small, (const Fr*)d_small + log_n);
   EON_LAUNCHED(ctx);
   phase_end(ctx, PH_NTT_TWIDDLE);
   ctx->twiddles[key] = d_tab;
@@ -174,8 +227,9 @@ __device__ __forceinline__ void split_vidx(const PassParams& p, u64 vidx, u64& l
   }
 }
 
-template <int MINB, bool R4>
+template <int MINB, bool R4, bool SH>
 __global__ void __launch_bounds__(NTT_THREADS, MINB) k_ntt_pass(const PassParams p) {
+  typedef typename TwOf<SH>::T Tw;
   extern __shared__ uint4 smem[];
   const u32 R = 1u << p.r;
   const u32 cv = 1u << p.log_cv;
@@ -259,23 +313,56 @@ __global__ void __launch_bounds__(NTT_THREADS, MINB) k_ntt_pass(const PassParams
           split_vidx(p, v0 + vc, lo, col);
           j += lo;
         }
-        Fr twA = fr_ldg(p.tw + (twA_base + j) * 2);
-        Fr twB0 = fr_ldg(p.tw + (twB_base + j) * 2);
-        Fr twB1 = fr_ldg(p.tw + (twB_base + j + (1ull << (p.l0 + t))) * 2);
         Fr x0 = fr_from_units(s_lo[e0], s_hi[e0]);
         Fr x1 = fr_from_units(s_lo[e1], s_hi[e1]);
         Fr x2 = fr_from_units(s_lo[e2], s_hi[e2]);
         Fr x3 = fr_from_units(s_lo[e3], s_hi[e3]);
-        if (!p.dif) {
-          bf_dit(x0, x1, twA);
-          bf_dit(x2, x3, twA);
-          bf_dit(x0, x2, twB0);
-          bf_dit(x1, x3, twB1);
+        if constexpr (SH) {
+          // 64-byte twiddle pairs: fetched right before their use, so that at most one is live beside the quartet
+          if (!p.dif) {
+            {
+              const Tw twA = tw_ldg<SH>(p.tw, twA_base + j);
+              bf_dit(x0, x1, twA);
+              bf_dit(x2, x3, twA);
+            }
+            {
+              const Tw twB0 = tw_ldg<SH>(p.tw, twB_base + j);
+              bf_dit(x0, x2, twB0);
+            }
+            {
+              const Tw twB1 = tw_ldg<SH>(p.tw, twB_base + j + (1ull << (p.l0 + t)));
+              bf_dit(x1, x3, twB1);
+            }
+          } else {
+            {
+              const Tw twB0 = tw_ldg<SH>(p.tw, twB_base + j);
+              bf_dif(x0, x2, twB0);
+            }
+            {
+              const Tw twB1 = tw_ldg<SH>(p.tw, twB_base + j + (1ull << (p.l0 + t)));
+              bf_dif(x1, x3, twB1);
+            }
+            {
+              const Tw twA = tw_ldg<SH>(p.tw, twA_base + j);
+              bf_dif(x0, x1, twA);
+              bf_dif(x2, x3, twA);
+            }
+          }
         } else {
-          bf_dif(x0, x2, twB0);
-          bf_dif(x1, x3, twB1);
-          bf_dif(x0, x1, twA);
-          bf_dif(x2, x3, twA);
+          const Tw twA = tw_ldg<SH>(p.tw, twA_base + j);
+          const Tw twB0 = tw_ldg<SH>(p.tw, twB_base + j);
+          const Tw twB1 = tw_ldg<SH>(p.tw, twB_base + j + (1ull << (p.l0 + t)));
+          if (!p.dif) {
+            bf_dit(x0, x1, twA);
+            bf_dit(x2, x3, twA);
+            bf_dit(x0, x2, twB0);
+            bf_dit(x1, x3, twB1);
+          } else {
+            bf_dif(x0, x2, twB0);
+            bf_dif(x1, x3, twB1);
+            bf_dif(x0, x1, twA);
+            bf_dif(x2, x3, twA);
+          }
         }
         fr_to_units(x0, s_lo[e0], s_hi[e0]);
         fr_to_units(x1, s_lo[e1], s_hi[e1]);
@@ -304,7 +391,7 @@ __global__ void __launch_bounds__(NTT_THREADS, MINB) k_ntt_pass(const PassParams
         split_vidx(p, v0 + vc, lo, col);
         j += lo;
       }
-      Fr tw = fr_ldg(p.tw + (tw_base + j) * 2);
+      const Tw tw = tw_ldg<SH>(p.tw, tw_base + j);
       Fr a = fr_from_units(s_lo[e0], s_hi[e0]);
       Fr bb = fr_from_units(s_lo[e1], s_hi[e1]);
       Fr o0 = a, o1 = bb;
@@ -418,7 +505,7 @@ static std::vector<PassPlan> plan_passes(u32 first, u32 last, size_t w) {
 
 static bool g_attr_set = false;
 
-static int launch_pass(eon_ctx* ctx, PassParams& p, const PassPlan& pl, unsigned log_n, size_t w) {
+static int launch_pass(eon_ctx* ctx, PassParams& p, const PassPlan& pl, unsigned log_n, size_t w, bool p_shoup) {
   p.log_n = log_n;
   p.w = (u32)w;
   p.w_shift = (w & (w - 1)) == 0 ? (int)ilog2_u32((u32)w) : -1;
@@ -444,20 +531,25 @@ static int launch_pass(eon_ctx* ctx, PassParams& p, const PassPlan& pl, unsigned
   }
   if (!g_attr_set) {
     const int mx = (int)(NTT_TILE_MAX * 32 + 64);
-    EON_CUDA(ctx, cudaFuncSetAttribute(k_ntt_pass<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
-    EON_CUDA(ctx, cudaFuncSetAttribute(k_ntt_pass<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
-    EON_CUDA(ctx, cudaFuncSetAttribute(k_ntt_pass<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
-    EON_CUDA(ctx, cudaFuncSetAttribute(k_ntt_pass<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
-    EON_CUDA(ctx, cudaFuncSetAttribute(k_ntt_pass<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+    EON_CUDA(ctx, cudaFuncSetAttribute(k_ntt_pass<3, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+    EON_CUDA(ctx, cudaFuncSetAttribute(k_ntt_pass<4, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+    EON_CUDA(ctx, cudaFuncSetAttribute(k_ntt_pass<2, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+    EON_CUDA(ctx, cudaFuncSetAttribute(k_ntt_pass<3, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+    EON_CUDA(ctx, cudaFuncSetAttribute(k_ntt_pass<4, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+    EON_CUDA(ctx, cudaFuncSetAttribute(k_ntt_pass<3, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+    EON_CUDA(ctx, cudaFuncSetAttribute(k_ntt_pass<2, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
     g_attr_set = true;
   }
-  if (radix4) {
-    if (minb >= 4) k_ntt_pass<4, true><<<(unsigned)grid, NTT_THREADS, smem, ctx->stream>>>(p);
-    else if (minb == 3) k_ntt_pass<3, true><<<(unsigned)grid, NTT_THREADS, smem, ctx->stream>>>(p);
-    else k_ntt_pass<2, true><<<(unsigned)grid, NTT_THREADS, smem, ctx->stream>>>(p);
+  if (p_shoup) {  // fixed-operand twiddles: radix-4 quartets only, 3 (or 2) CTAs per SM
+    if (minb >= 3) k_ntt_pass<3, true, true><<<(unsigned)grid, NTT_THREADS, smem, ctx->stream>>>(p);
+    else k_ntt_pass<2, true, true><<<(unsigned)grid, NTT_THREADS, smem, ctx->stream>>>(p);
+  } else if (radix4) {
+    if (minb >= 4) k_ntt_pass<4, true, false><<<(unsigned)grid, NTT_THREADS, smem, ctx->stream>>>(p);
+    else if (minb == 3) k_ntt_pass<3, true, false><<<(unsigned)grid, NTT_THREADS, smem, ctx->stream>>>(p);
+    else k_ntt_pass<2, true, false><<<(unsigned)grid, NTT_THREADS, smem, ctx->stream>>>(p);
   } else {
-    if (minb >= 4) k_ntt_pass<4, false><<<(unsigned)grid, NTT_THREADS, smem, ctx->stream>>>(p);
-    else k_ntt_pass<3, false><<<(unsigned)grid, NTT_THREADS, smem, ctx->stream>>>(p);
+    if (minb >= 4) k_ntt_pass<4, false, false><<<(unsigned)grid, NTT_THREADS, smem, ctx->stream>>>(p);
+    else k_ntt_pass<3, false, false><<<(unsigned)grid, NTT_THREADS, smem, ctx->stream>>>(p);
   }
   EON_LAUNCHED(ctx);
   return EON_OK;
@@ -472,7 +564,8 @@ int ntt_forward(eon_ctx* ctx, const Fr* d_src, Fr* d_dst, unsigned log_n, unsign
   if (k > log_n) return fail(ctx, EON_ERR_BAD_ARG, "ntt_forward: added bits exceed transform size");
   if (width > 0xffffffffull) return fail(ctx, EON_ERR_BAD_ARG, "ntt: width too large");
   const Fr* tw = nullptr;
-  EON_TRY(get_twiddles(ctx, log_n, shift, 0, &tw));
+  const bool sh = ntt_use_shoup();
+  EON_TRY(get_twiddles(ctx, log_n, shift, 0, sh, &tw));
   std::vector<PassPlan> plan = plan_passes(k, log_n, width);
   phase_begin(ctx, PH_NTT_PASSES);
   for (size_t i = 0; i < plan.size(); i++) {
@@ -492,7 +585,7 @@ int ntt_forward(eon_ctx* ctx, const Fr* d_src, Fr* d_dst, unsigned log_n, unsign
     p.dst = (uint4*)d_dst;
     p.ld_dst = ld_dst;
     if (i + 1 == plan.size()) p.scale = 2;  // lazily reduced values leave the transform canonical
-    EON_TRY(launch_pass(ctx, p, plan[i], log_n, width));
+    EON_TRY(launch_pass(ctx, p, plan[i], log_n, width, sh));
   }
   phase_end(ctx, PH_NTT_PASSES);
   return EON_OK;
@@ -506,7 +599,8 @@ int ntt_inverse(eon_ctx* ctx, const Fr* d_src, Fr* d_dst, unsigned log_n, size_t
   if (log_n > 28) return fail(ctx, EON_ERR_TWO_ADICITY, "transform size exceeds 2^28 (Fr::TWO_ADICITY)");
   if (width > 0xffffffffull) return fail(ctx, EON_ERR_BAD_ARG, "ntt: width too large");
   const Fr* tw = nullptr;
-  EON_TRY(get_twiddles(ctx, log_n, shift, 1, &tw));
+  const bool sh = ntt_use_shoup();
+  EON_TRY(get_twiddles(ctx, log_n, shift, 1, sh, &tw));
   std::vector<PassPlan> plan = plan_passes(0, log_n, width);
   const size_t np = plan.size();
   const bool out_rev = (dst_layout == LAYOUT_NATURAL);
@@ -541,7 +635,7 @@ int ntt_inverse(eon_ctx* ctx, const Fr* d_src, Fr* d_dst, unsigned log_n, size_t
         p.scale = 2;
       }
     }
-    EON_TRY(launch_pass(ctx, p, pl, log_n, width));
+    EON_TRY(launch_pass(ctx, p, pl, log_n, width, sh));
   }
   phase_end(ctx, PH_NTT_PASSES);
   return EON_OK;

@@ -73,6 +73,13 @@ void host_shoup_mul(int which, int canon, const uint32_t* a, const uint32_t* w, 
     memcpy(r, t, 32);
   }
 }
+// (w, wq) of a twiddle given in Montgomery form (fp_shoup.cuh precompute)
+void host_shoup_precompute(int which, const uint32_t* rho, uint32_t* w, uint32_t* wq, int n) {
+  for (int i = 0; i < n; i++, rho += 8, w += 8, wq += 8) {
+    if (which == 0) shoup::precompute<FrParams>(w, wq, ld<Fr>(rho));
+    else shoup::precompute<FqParams>(w, wq, ld<Fq>(rho));
+  }
+}
 // T[0..16) = a * b (variant 0) or a^2 (variant 1) over full 256-bit operands
 void host_wide_product(int variant, const uint32_t* a, const uint32_t* b, uint32_t* T, int n) {
   for (int i = 0; i < n; i++, a += 8, b += 8, T += 16) {
@@ -97,6 +104,33 @@ void host_lazy_butterfly(int dif, const uint32_t* a, const uint32_t* b, const ui
     fp_sub_plus_2p<FrParams>(x, a, b);
     fp_mul_lazy<FrParams>(d, tw, x);
   }
+  st(o0, fp_canon_4p<FrParams>(s));
+  st(o1, fp_canon_4p<FrParams>(d));
+}
+
+// The same butterflies with the twiddle as a (plain, quotient) pair and the fixed-operand product, exactly as
+// k_ntt_pass<.., SH = true> runs them: t = reduce_2p(shoup(b)), everything else unchanged.  tw: Montgomery form
+// (what k_gen_twiddles starts from); raw != 0 additionally returns the un-canonicalised outputs in r0 / r1.
+void host_lazy_butterfly_shoup(int dif, const uint32_t* a, const uint32_t* b, const uint32_t* tw, uint32_t* o0,
+                               uint32_t* o1, uint32_t* r0, uint32_t* r1) {
+  uint32_t w[8], wq[8], x[8], t3[8], t[8], s[8], d[8];
+  shoup::precompute<FrParams>(w, wq, ld<Fr>(tw));
+  if (!dif) {
+    fp_reduce_2p<FrParams>(x, a);
+    shoup::mul_lazy<FrParams>(t3, b, w, wq);
+    fp_reduce_2p<FrParams>(t, t3);
+    fp_add_raw(s, x, t);
+    fp_sub_plus_2p<FrParams>(d, x, t);
+  } else {
+    uint32_t u[8];
+    fp_add_raw(u, a, b);
+    fp_reduce_2p<FrParams>(s, u);
+    fp_sub_plus_2p<FrParams>(x, a, b);
+    shoup::mul_lazy<FrParams>(t3, x, w, wq);
+    fp_reduce_2p<FrParams>(d, t3);
+  }
+  memcpy(r0, s, 32);
+  memcpy(r1, d, 32);
   st(o0, fp_canon_4p<FrParams>(s));
   st(o1, fp_canon_4p<FrParams>(d));
 }

@@ -257,3 +257,47 @@ def test_shoup_fixed_operand_product(lib, which, mod):
         assert to_int(rc[k]) == x * y % mod
         worst = max(worst, got // mod)
     assert worst <= 2
+
+
+@pytest.mark.parametrize("which,mod", [(0, fr.P), (1, g1.Q)])
+def test_shoup_precompute(lib, which, mod):
+    """(w, floor(w 2^256 / p)) from the Montgomery form of w: the exact division by p done as a multiplication
+    by p^-1 mod 2^256."""
+    rng = np.random.default_rng(5 + which)
+    ws = [int.from_bytes(rng.bytes(40), "little") % mod for _ in range(300)] + EDGE(mod)
+    rho = np.array([from_int(w * (1 << 256) % mod) for w in ws])
+    w = np.zeros_like(rho)
+    wq = np.zeros_like(rho)
+    lib.host_shoup_precompute(which, _ptr(rho), _ptr(w), _ptr(wq), len(ws))
+    for k, x in enumerate(ws):
+        assert to_int(w[k]) == x
+        assert to_int(wq[k]) == (x << 256) // mod
+
+
+def test_lazy_ntt_butterflies_shoup_twiddles(lib):
+    """The butterflies of k_ntt_pass with fixed-operand (Shoup) twiddles: same canonical results as the
+    definitions, and the lazily reduced outputs stay inside the ranges the next layer assumes
+    ([0, 4r) forward, [0, 2r) inverse), for inputs over the whole admissible range."""
+    P = fr.P
+    R = 1 << 256
+    rng = np.random.default_rng(19)
+    rinv = pow(R, -1, P)
+    for dif in (0, 1):
+        top = 2 * P if dif else 4 * P
+        cases = [(0, 0), (top - 1, top - 1), (top - 1, 0), (0, top - 1), (P, P - 1), (2 * P - 1, 1), (top - 1, 1)]
+        cases += [(int.from_bytes(rng.bytes(40), "little") % top, int.from_bytes(rng.bytes(40), "little") % top)
+                  for _ in range(300)]
+        tws = [0, 1, P - 1, R % P] + [int.from_bytes(rng.bytes(40), "little") % P for _ in range(len(cases))]
+        for k, (a, b) in enumerate(cases):
+            tw = tws[k % len(tws)]                                   # Montgomery form of the twiddle
+            A, B, T = from_int(a), from_int(b), from_int(tw)
+            o0, o1, r0, r1 = (np.zeros(4, dtype=np.uint64) for _ in range(4))
+            lib.host_lazy_butterfly_shoup(dif, _ptr(A), _ptr(B), _ptr(T), _ptr(o0), _ptr(o1), _ptr(r0), _ptr(r1))
+            if not dif:
+                t = tw * b * rinv % P
+                want = ((a + t) % P, (a - t) % P)
+            else:
+                want = ((a + b) % P, (a - b) * tw * rinv % P)
+            assert (to_int(o0), to_int(o1)) == want, (dif, a, b, tw)
+            assert to_int(r0) < top and to_int(r1) < top, (dif, a, b, tw)
+            assert to_int(r0) % P == want[0] and to_int(r1) % P == want[1]
