@@ -414,6 +414,8 @@ def run_eon(args):
         roofline = dict(common, kernel="k_msm_accumulate (XYZZ mixed adds, one thread per bucket)",
                         achieved=achieved, frac=achieved / imad_peak,
                         algorithmic_ops_per_launch=adds * MODMUL_PER_MIXED_ADD * IMAD_PER_MODMUL, launch_ms=acc_ms)
+    # fixed-operand (Shoup) twiddle product: 43 + 36 + 36 limb products = 214 IMAD (csrc/fp_shoup.cuh)
+    imad_bf = 214 if int(ctx.lib.eon_ntt_twiddle_form()) == 1 else IMAD_PER_MODMUL
     roofline_ntt = {
         "kernel": "k_ntt_pass (3 HBM passes for the 2^20 iDFT + 3 for the 2^21 LDE)",
         "bound": "hbm", "achieved": ntt_bytes / (ntt_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
@@ -421,8 +423,11 @@ def run_eon(args):
         # ncu --set full (profiles/r01h_ncu_full_summary.txt): 1.05-1.07 GB per 2^20 pass, 1.57-2.1 GB per 2^21 pass
         "traffic": (3.20e9 + 5.76e9) if (log_rows == 20 and cols == 16) else None, "launch_ms_total": ntt_ms,
         "peak_source": peak_src,
-        "imad_frac": ((rows // 2) * log_rows * cols + ((rows << ab) // 2) * log_rows * cols + rows * cols) * IMAD_PER_MODMUL
-        / (ntt_ms * 1e-3) / 1e12 / imad_peak,
+        # butterflies of the iDFT and of the LDE (its first `ab` layers are replication) at the IMAD count of the
+        # product in use, plus the 1/n Montgomery product on every iDFT output
+        "imad_per_butterfly": imad_bf,
+        "imad_frac": (((rows // 2) * log_rows * cols + ((rows << ab) // 2) * log_rows * cols) * imad_bf
+                      + rows * cols * IMAD_PER_MODMUL) / (ntt_ms * 1e-3) / 1e12 / imad_peak,
     }
 
     # ---- CPU baseline: the port on the host cores, bounded sample (N = 1 only) -------------------

@@ -261,6 +261,10 @@ int eon_bench_modmul(eon_ctx* ctx, int field, double* out_gmuls);
  * experiment for the NTT butterflies, 214 instead of 272 IMAD), 5 = the word-serial product without its final
  * correction (what the NTT passes run today), for comparison with 4. */
 int eon_bench_modmul_variant(eon_ctx* ctx, int field, int variant, double* out_gmuls);
+/* Which multiplier the NTT butterflies use in this process: 1 = fixed-operand (Shoup) product on (plain,
+ * quotient) twiddle pairs, 214 IMAD per butterfly (the default); 0 = word-serial Montgomery product on
+ * Montgomery-form twiddles, 272 IMAD (EON_NTT_SHOUP=0).  Results are identical either way. */
+int eon_ntt_twiddle_form(void);
 /* per-phase device time (ms, CUDA events on the ctx stream) summed over every call since the last
  * eon_phase_reset; names via eon_phase_name (phases 0 .. eon_phase_count() - 1).  The msm_tree_* and
  * msm_finish phases are sub-intervals of msm_accumulate. */

@@ -1121,6 +1121,8 @@ int eon_bench_modmul_variant(eon_ctx* ctx, int field, int variant, double* out_g
   return bench_modmul(ctx, field, variant, out_gmuls);
 }
 
+int eon_ntt_twiddle_form(void) { return ntt_twiddles_are_fixed_operand() ? 1 : 0; }
+
 int eon_last_phase_ms(eon_ctx* ctx, int phase, float* out_ms) {
   if (!ctx || !out_ms || phase < 0 || phase >= PH_COUNT) return EON_ERR_BAD_ARG;
   Lock lk(ctx);

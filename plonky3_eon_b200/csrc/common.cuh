@@ -244,6 +244,8 @@ int ntt_forward(eon_ctx* ctx, const Fr* d_src, Fr* d_dst, unsigned log_n, unsign
 int ntt_inverse(eon_ctx* ctx, const Fr* d_src, Fr* d_dst, unsigned log_n, size_t width, const Fr& shift,
                 Layout dst_layout, size_t ld_src = 0, size_t ld_dst = 0);
 
+bool ntt_twiddles_are_fixed_operand();
+
 // out[c] = sum_i scalars[i*ld + c] * bases[i], c < ncols.  d_out: ncols affine points (device).
 int msm_run(eon_ctx* ctx, const G1Affine* d_bases, const Fr* d_scalars, size_t n, size_t ncols, size_t ld,
             G1Affine* d_out);

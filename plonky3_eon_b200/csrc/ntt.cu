@@ -20,8 +20,11 @@
 #include "common.cuh"
 #include "fp_shoup.cuh"
 
+// MEASURED ON B200 (profiles/r01n_bench_*.json, 2^20 x 16 commit + LDE): NTT passes 10.37 ms with Montgomery
+// twiddles (3 CTAs/SM), 9.69 ms with fixed-operand twiddles at 3 CTAs/SM (80 registers, some spills), 9.05 ms at
+// 2 CTAs/SM (128 registers, none) -> fixed-operand twiddles at 2 CTAs/SM are the default.
 #ifndef EON_NTT_SHOUP_DEFAULT
-#define EON_NTT_SHOUP_DEFAULT 0
+#define EON_NTT_SHOUP_DEFAULT 1
 #endif
 
 namespace eon {
@@ -113,7 +116,8 @@ __global__ void k_gen_twiddles(Fr* tw, u32 log_n, const Fr* __restrict__ base, c
   }
 }
 
-// EON_NTT_SHOUP=1: butterflies multiply by (plain, quotient) twiddle pairs with the fixed-operand product
+// butterflies multiply by (plain, quotient) twiddle pairs with the fixed-operand product (EON_NTT_SHOUP=0: by
+// Montgomery-form twiddles with the word-serial product, the form every other kernel uses)
 static int g_ntt_shoup = -1;
 static bool ntt_use_shoup() {
   if (g_ntt_shoup < 0) {
@@ -540,8 +544,13 @@ static int launch_pass(eon_ctx* ctx, PassParams& p, const PassPlan& pl, unsigned
     EON_CUDA(ctx, cudaFuncSetAttribute(k_ntt_pass<2, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
     g_attr_set = true;
   }
-  if (p_shoup) {  // fixed-operand twiddles: radix-4 quartets only, 3 (or 2) CTAs per SM
-    if (minb >= 3) k_ntt_pass<3, true, true><<<(unsigned)grid, NTT_THREADS, smem, ctx->stream>>>(p);
+  if (p_shoup) {  // fixed-operand twiddles: radix-4 quartets only; 2 CTAs per SM unless EON_NTT_MINB asks for 3
+    static int minb_sh = -1;
+    if (minb_sh < 0) {
+      const char* e = getenv("EON_NTT_MINB");
+      minb_sh = e ? atoi(e) : 2;
+    }
+    if (minb_sh >= 3) k_ntt_pass<3, true, true><<<(unsigned)grid, NTT_THREADS, smem, ctx->stream>>>(p);
     else k_ntt_pass<2, true, true><<<(unsigned)grid, NTT_THREADS, smem, ctx->stream>>>(p);
   } else if (radix4) {
     if (minb >= 4) k_ntt_pass<4, true, false><<<(unsigned)grid, NTT_THREADS, smem, ctx->stream>>>(p);
@@ -554,6 +563,8 @@ static int launch_pass(eon_ctx* ctx, PassParams& p, const PassPlan& pl, unsigned
   EON_LAUNCHED(ctx);
   return EON_OK;
 }
+
+bool ntt_twiddles_are_fixed_operand() { return ntt_use_shoup(); }
 
 int ntt_forward(eon_ctx* ctx, const Fr* d_src, Fr* d_dst, unsigned log_n, unsigned k, size_t width, const Fr& shift,
                 Layout src_layout, size_t ld_src, size_t ld_dst) {

@@ -87,6 +87,7 @@ _SIGS = {
     "eon_bench_imad_peak": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_double)]),
     "eon_bench_modmul": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_double)]),
     "eon_bench_modmul_variant": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_double)]),
+    "eon_ntt_twiddle_form": (C.c_int, []),
     "eon_last_phase_ms": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_float)]),
     "eon_phase_reset": (C.c_int, [C.c_void_p]),
     "eon_phase_name": (C.c_char_p, [C.c_int]),
