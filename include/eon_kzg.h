@@ -257,8 +257,8 @@ int eon_bench_modmul(eon_ctx* ctx, int field, double* out_gmuls);
 /* The same for one formulation of the product.  variant: 0 = the product the library uses, 1 = word-serial
  * (CIOS) Montgomery product, 2 = split form (one Karatsuba level + separate reduction), 3 = dedicated square
  * (each square followed by one modular add).  All variants return identical limbs.
- * 4 = fixed-operand (Shoup) product with a precomputed quotient operand, lazily reduced (csrc/fp_shoup.cuh: an
- * experiment for the NTT butterflies, 214 instead of 272 IMAD), 5 = the word-serial product without its final
+ * 4 = fixed-operand (Shoup) product with a precomputed quotient operand, lazily reduced (csrc/fp_shoup.cuh: the
+ * multiplier of the NTT butterflies, 214 instead of 272 IMAD), 5 = the word-serial product without its final
  * correction (what the NTT passes run today), for comparison with 4. */
 int eon_bench_modmul_variant(eon_ctx* ctx, int field, int variant, double* out_gmuls);
 /* Which multiplier the NTT butterflies use in this process: 1 = fixed-operand (Shoup) product on (plain,

@@ -1,6 +1,7 @@
-// Fixed-operand (Shoup / Barrett-style) modular product for 8 x 32-bit limbs: an EXPERIMENT for the NTT
-// butterflies, whose multiplier is always a precomputed twiddle.  Not used by the library yet; measured by
-// eon_bench_modmul_variant (variant 4) and checked on the host by tests/test_host_arith.py.
+// Fixed-operand (Shoup / Barrett-style) modular product for 8 x 32-bit limbs: the multiplier of the NTT
+// butterflies (csrc/ntt.cu), whose second operand is always a precomputed twiddle.  Measured by
+// eon_bench_modmul_variant (variant 4: 82.9 G products/s on B200 against 69.6 G/s for the word-serial Montgomery
+// product without its final correction) and checked on the host by tests/test_host_arith.py.
 //
 //   given   w < p  and  wq = floor(w * 2^256 / p)   (both precomputed per twiddle),  a = any 256-bit value
 //   q~ = floor( (sum_{i+j >= 6} a_i wq_j 2^(32(i+j))) / 2^256 )        43 limb products (not 64)
