@@ -164,8 +164,8 @@ static int get_twiddles(eon_ctx* ctx, unsigned log_n, const Fr& shift, int inver
   }
   const size_t tab_bytes = (entries + 1) * sizeof(Fr) * (sh ? 2 : 1);
   if (ctx->twiddle_bytes + tab_bytes > budget && !ctx->twiddles.empty()) {
-    EON_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    if (ctx->aux_stream) EON_CUDA(ctx, cudaStreamSynchronize(ctx->aux_stream));
+    // (a transform may be running on either compute stream of the context: wait for the whole device)
+    EON_CUDA(ctx, cudaDeviceSynchronize());
     for (auto& kv : ctx->twiddles) cudaFree(kv.second);
     ctx->twiddles.clear();
     ctx->twiddle_bytes = 0;
