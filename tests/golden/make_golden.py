@@ -66,5 +66,49 @@ def main():
     print("wrote kzg_small.npz:", {k: v.shape for k, v in out.items()})
 
 
+def batched():
+    """tests/golden/kzg_batched.npz: Pcs::commit_quotient (commit/src/pcs.rs:82-102) of a 16 x 2 quotient on
+    GENERATOR * <omega_16> in 2 chunks, and ONE KzgPcs::open (kzg/src/pcs.rs:289-335) over a trace round (8 x 2 at
+    zeta, zeta*omega and 8 x 1 at zeta) and the chunk round (both chunks at zeta), alpha = 12345 — laid out flat in
+    [round][matrix][point][column] order, the order eon_kzg_open_batch returns."""
+    rng = np.random.default_rng(2)
+    alpha = 12345
+    srs = kzg.init_srs_unsafe(15, alpha)
+    out = {"alpha": np.array([alpha], dtype=np.uint64)}
+    t0_w = fr.random_wire(rng, 8 * 2).reshape(8, 2, 4)
+    t1_w = fr.random_wire(rng, 8 * 1).reshape(8, 1, 4)
+    q_w = fr.random_wire(rng, 16 * 2).reshape(16, 2, 4)
+    out["trace0"], out["trace1"], out["quotient"] = t0_w, t1_w, q_w
+    dom = (1, 3)
+    c_t, pd_t = kzg.commit(srs, [(dom, dft.mat_from_wire(t0_w)), (dom, dft.mat_from_wire(t1_w))], fast=False)
+    qdom = (fr.GENERATOR, 4)
+    doms = kzg.split_domains(qdom, 2)
+    subs = kzg.split_evals(2, dft.mat_from_wire(q_w))
+    c_q, pd_q = kzg.commit(srs, list(zip(doms, subs)), fast=False)
+    out["trace_commit0"], out["trace_commit1"] = g1.to_wire(c_t[0]), g1.to_wire(c_t[1])
+    out["chunk_shifts"] = fr.to_wire([d[0] for d in doms])
+    out["chunk_commits"] = np.stack([g1.to_wire(c) for c in c_q])
+    out["chunk_coeffs"] = np.stack([dft.mat_to_wire(m["coeffs"]) for m in pd_q])
+    zeta = fr.from_wire(fr.random_wire(rng, 1))[0]
+    zeta_next = zeta * fr.two_adic_generator(3) % fr.P
+    out["points"] = fr.to_wire([zeta, zeta_next])
+    rounds = [(pd_t, [[zeta, zeta_next], [zeta]]), (pd_q, [[zeta], [zeta]])]
+    opened, wits = kzg.open_(srs, rounds)
+    flat_v, flat_w = [], []
+    for r in range(len(rounds)):
+        for m in range(len(opened[r])):
+            for pnt in range(len(opened[r][m])):
+                flat_v.extend(opened[r][m][pnt])
+                flat_w.extend(wits[r][m][pnt])
+    out["opened_flat"] = fr.to_wire(flat_v)
+    out["witness_flat"] = g1.to_wire(flat_w)
+    np.savez_compressed(os.path.join(os.path.dirname(os.path.abspath(__file__)), "kzg_batched.npz"), **out)
+    print("wrote kzg_batched.npz:", {k: v.shape for k, v in out.items()})
+
+
 if __name__ == "__main__":
-    main()
+    if "--batched-only" in sys.argv:
+        batched()
+    else:
+        main()
+        batched()
