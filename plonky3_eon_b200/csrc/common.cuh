@@ -101,6 +101,9 @@ struct eon_ctx {
   eon::Scratch scratch[eon::SC_COUNT];
   std::map<eon::TwiddleKey, eon::Fr*> twiddles;
   size_t twiddle_bytes = 0;  // device bytes behind `twiddles` (bounded: see get_twiddles)
+  // opt-in shared-memory sizes (cudaFuncSetAttribute) are per device: set once per context, not per process
+  bool ntt_attr_set = false;
+  bool sort_attr_set = false;
 
   eon::G1Affine* d_srs = nullptr;
   size_t srs_n = 0;

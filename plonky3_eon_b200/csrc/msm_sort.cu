@@ -323,7 +323,6 @@ k_sort_fine(const u32* __restrict__ tmp_pay, const unsigned short* __restrict__ 
   for (u32 f = tid; f < fine; f += SORT_FINE_THREADS) ends[g0 + f] = s_cur[f];
 }
 
-static bool g_sort_attr_set = false;
 
 int msm_sort_entries(eon_ctx* ctx, const Fr* d_scalars, size_t n, size_t ncols, size_t ld, const MsmShape& sh,
                      const SlicePlan& plan, u32* d_hist, u32* d_seg_total, u32* d_cur, u32* d_entries) {
@@ -349,7 +348,7 @@ int msm_sort_entries(eon_ctx* ctx, const Fr* d_scalars, size_t n, size_t ncols, 
   const size_t total_bins = nseg * nbins;
   const size_t tiles = (n + tile - 1) / tile;
   if (tiles * ncols > 0x7fffffffull || total_bins > 0x7fffffffull) return 1;
-  if (!g_sort_attr_set) {
+  if (!ctx->sort_attr_set) {  // per context: the attribute belongs to the context's device
     EON_CUDA(ctx, cudaFuncSetAttribute(k_sort_coarse<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)(SORT_COARSE_SMEM + 16)));
     EON_CUDA(ctx, cudaFuncSetAttribute(k_sort_coarse<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -358,7 +357,7 @@ int msm_sort_entries(eon_ctx* ctx, const Fr* d_scalars, size_t n, size_t ncols, 
                                        (int)(((size_t)(1u << 12) + SORT_WIN_CAP) * sizeof(u32))));
     EON_CUDA(ctx, cudaFuncSetAttribute(k_sort_fine<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)(((size_t)(1u << 7) * (1 + SLICE_ORDER_MAX) + SORT_WIN_CAP) * sizeof(u32))));
-    g_sort_attr_set = true;
+    ctx->sort_attr_set = true;
   }
   void *p_reg, *p_pay, *p_key;
   // per bin: count | start of its run in the temporary array | cursor (ends as the end of that run)

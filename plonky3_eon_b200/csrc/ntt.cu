@@ -507,7 +507,6 @@ static std::vector<PassPlan> plan_passes(u32 first, u32 last, size_t w) {
   return out;
 }
 
-static bool g_attr_set = false;
 
 static int launch_pass(eon_ctx* ctx, PassParams& p, const PassPlan& pl, unsigned log_n, size_t w, bool p_shoup) {
   p.log_n = log_n;
@@ -533,7 +532,7 @@ static int launch_pass(eon_ctx* ctx, PassParams& p, const PassPlan& pl, unsigned
     const char* e = getenv("EON_NTT_MINB");
     minb = e ? atoi(e) : (ntt_tile_elems() == 1024 ? 4 : 3);
   }
-  if (!g_attr_set) {
+  if (!ctx->ntt_attr_set) {  // per context: the attribute belongs to the context's device
     const int mx = (int)(NTT_TILE_MAX * 32 + 64);
     EON_CUDA(ctx, cudaFuncSetAttribute(k_ntt_pass<3, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
     EON_CUDA(ctx, cudaFuncSetAttribute(k_ntt_pass<4, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
@@ -542,7 +541,7 @@ static int launch_pass(eon_ctx* ctx, PassParams& p, const PassPlan& pl, unsigned
     EON_CUDA(ctx, cudaFuncSetAttribute(k_ntt_pass<4, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
     EON_CUDA(ctx, cudaFuncSetAttribute(k_ntt_pass<3, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
     EON_CUDA(ctx, cudaFuncSetAttribute(k_ntt_pass<2, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
-    g_attr_set = true;
+    ctx->ntt_attr_set = true;
   }
   if (p_shoup) {  // fixed-operand twiddles: radix-4 quartets only; 2 CTAs per SM unless EON_NTT_MINB asks for 3
     static int minb_sh = -1;
