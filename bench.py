@@ -173,10 +173,13 @@ def run_reference(args):
     srs = cport.srs_generate(ALPHA, rows)
     t_setup = time.perf_counter() - t_setup
     vals = []
-    steps = max(1, min(args.steps, 3))
-    for i in range(args.warmup_ref + steps):
+    # exactly --warmup untimed and --steps timed steps, like the eon arm; every step is the bounded sample above
+    # (about 3 s of CPU work at 2^20 x 16 on the GPU box's host), so the default run stays well under a few minutes
+    steps = max(1, args.steps)
+    warm = args.warmup_ref if args.warmup_ref > 0 else max(0, args.warmup)
+    for i in range(warm + steps):
         v, est, d = cpu_reference_sample(args.log_rows, args.cols, sample_cols, srs=srs)
-        if i >= args.warmup_ref:
+        if i >= warm:
             vals.append((v, est, d))
     v = float(np.median([x[0] for x in vals]))
     est = float(np.median([x[1] for x in vals]))
@@ -185,7 +188,7 @@ def run_reference(args):
               f"affine SRS normalised once (no per-call to_affine, bn254/src/curve.rs:170)")
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
-        "warmup": args.warmup_ref, "ms_per_step": est * 1e3, "higher_is_better": True, "scaling": "weak",
+        "warmup": warm, "ms_per_step": est * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u256 (4x64-bit Montgomery, BN254 Fr/Fq)", "data": "synthetic",
         "config": {"workload": f"KZG commit + blow-up-2 coset LDE, 2^{args.log_rows} rows x {args.cols} cols, "
                                "CPU port of the reference path (oracle/c, OpenMP)",
@@ -722,7 +725,8 @@ def main():
     ap.add_argument("--added-bits", type=int, default=1, help="log2 of the LDE blow-up (1: configs[1]; 2: configs[4])")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (large shapes: pinned LDE buffer)")
     ap.add_argument("--check-e2e", action="store_true", help="compare the fused and two-call LDE bytes (1 GiB copy)")
-    ap.add_argument("--warmup-ref", type=int, default=0)
+    ap.add_argument("--warmup-ref", type=int, default=0,
+                    help="reference arm: warm-up steps if they should differ from --warmup (0 = use --warmup)")
     ap.add_argument("--window-bits", type=int, default=-1,
                     help="MSM window tables: -1 library default, 0 none (plain c=16), 8..20 explicit")
     ap.add_argument("--slice-schedule", type=int, default=-1,

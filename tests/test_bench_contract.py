@@ -1,0 +1,38 @@
+"""bench.py contract, CPU side: the reference arm (`--impl reference`: the C port of the reference path on the host
+cores) prints exactly ONE JSON line on stdout with the keys the driver reads, at a tiny shape so that the test takes
+a second.  The eon arm needs a GPU and must refuse to run without one (no CPU fallback)."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def run(*args):
+    return subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), *args], cwd=ROOT, capture_output=True,
+                          text=True, timeout=600)
+
+
+def test_reference_arm_prints_one_json_line():
+    out = run("--impl", "reference", "--log-rows", "10", "--cols", "4", "--steps", "2", "--warmup", "1")
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, out.stdout
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "kzg_commit_lde_cols_rows_per_s" and d["unit"] == "cols*rows/s"
+    assert d["n_gpus"] == 1 and d["steps"] == 2 and d["warmup"] == 1 and d["higher_is_better"] is True
+    assert d["value"] > 0 and d["ms_per_step"] > 0 and d["vs_baseline"] is None and d["data"] == "synthetic"
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in d["config"]
+
+
+def test_eon_arm_refuses_to_run_without_a_gpu():
+    import pytest
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    out = run("--steps", "1", "--warmup", "1")
+    assert out.returncode != 0 and "no CPU fallback" in (out.stderr + out.stdout)
