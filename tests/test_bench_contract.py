@@ -36,3 +36,27 @@ def test_eon_arm_refuses_to_run_without_a_gpu():
         pytest.skip("GPU present")
     out = run("--steps", "1", "--warmup", "1")
     assert out.returncode != 0 and "no CPU fallback" in (out.stderr + out.stdout)
+
+
+def test_committed_bench_line_has_the_contract_keys():
+    """The newest eon-arm line kept under profiles/ (written by bench.py on a B200) carries every key of the
+    contract: the base line, e2e with its byte counts, gpu_launches, clocks, roofline and cpu_baseline."""
+    import glob
+    import re
+    files = [f for f in glob.glob(os.path.join(ROOT, "profiles", "r*_bench.json"))
+             if re.fullmatch(r"r\\d+[a-z]_bench\\.json", os.path.basename(f))]
+    assert files
+    newest = sorted(files)[-1]
+    d = json.loads(open(newest).read().strip().splitlines()[-1])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "clocks", "roofline", "cpu_baseline"):
+        assert k in d, (newest, k)
+    assert d["warmup"] >= 3 and d["gpu_launches"] > 0 and "workload" in d["config"]
+    assert {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} <= set(d["e2e"])
+    assert d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0
+    assert d["e2e"]["value"] < d["value"]                      # the host-buffer number is not the device number
+    assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(d["roofline"])
+    assert abs(d["roofline"]["frac"] - d["roofline"]["achieved"] / d["roofline"]["peak"]) < 1e-9
+    assert {"value", "unit", "cores", "kind", "sample"} <= set(d["cpu_baseline"])
+    assert {"sm_mhz", "sm_max_mhz", "reasons"} <= set(d["clocks"])
+    assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
