@@ -44,7 +44,7 @@ def test_committed_bench_line_has_the_contract_keys():
     import glob
     import re
     files = [f for f in glob.glob(os.path.join(ROOT, "profiles", "r*_bench.json"))
-             if re.fullmatch(r"r\\d+[a-z]_bench\\.json", os.path.basename(f))]
+             if re.fullmatch(r"r\d+[a-z]_bench\.json", os.path.basename(f))]
     assert files
     newest = sorted(files)[-1]
     d = json.loads(open(newest).read().strip().splitlines()[-1])
