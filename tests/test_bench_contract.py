@@ -60,3 +60,21 @@ def test_committed_bench_line_has_the_contract_keys():
     assert {"value", "unit", "cores", "kind", "sample"} <= set(d["cpu_baseline"])
     assert {"sm_mhz", "sm_max_mhz", "reasons"} <= set(d["clocks"])
     assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+
+
+def test_reference_arm_under_torchrun_prints_from_rank_0_only():
+    """N > 1: the driver launches the reference arm with torchrun like the eon arm; rank 0 alone runs the CPU port
+    and prints the line, the other ranks exit 0 without work."""
+    import socket
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "bench.py"),
+                          "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "1", "--log-rows", "10",
+                          "--cols", "4"], cwd=ROOT, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip().startswith("{")]
+    assert len(lines) == 1, out.stdout
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["n_gpus"] == 2 and d["steps"] == 1 and d["warmup"] == 1
