@@ -335,7 +335,7 @@ def run_eon(args):
     if args.no_e2e:
         ms_e2e = ms_e2e2 = None
     else:
-        for _ in range(max(1, min(args.warmup, 2))):
+        for _ in range(max(1, args.warmup)):                    # the same W untimed steps as the device leg
             step_e2e()
         ms_e2e = timed(step_e2e, args.steps)
         assert np.array_equal(commits, commits_device), "e2e and device-resident commitments differ"
