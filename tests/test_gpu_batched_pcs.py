@@ -6,7 +6,6 @@
 
 Bit-exact: affine G1 wire points and canonical Fr limbs are compared directly.
 """
-import ctypes as C
 
 import numpy as np
 import pytest

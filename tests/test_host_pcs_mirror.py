@@ -3,7 +3,6 @@ rounds / matrices / points, the slicing of the flat ABI outputs, chunk views of 
 
 The ABI calls are served by an oracle-backed stand-in that follows the contracts written in include/eon_kzg.h
 (this checks the Python side of the boundary, not the kernels: those are the -m gpu tests)."""
-import ctypes as C
 
 import numpy as np
 
