@@ -218,8 +218,8 @@ __global__ void __launch_bounds__(256) k_modmul_peak(Fp<PP>* out, u32 iters, u32
   Fp<PP> a = fp_from_u64<PP>(seed + threadIdx.x + 1);
   Fp<PP> b = fp_from_u64<PP>(seed * 3 + blockIdx.x + 7);
   Fp<PP> c = fp_from_u64<PP>(seed * 5 + threadIdx.x * 11 + 13);
-  if (VARIANT >= 4) {
-    // fixed-operand products as the NTT butterflies would use them: the multiplier (b, b2) never changes, the
+  if constexpr (VARIANT >= 4) {
+    // fixed-operand products as the NTT butterflies use them: the multiplier (b, b2) never changes, the
     // running values stay lazily reduced.  4 = Shoup form (fp_shoup.cuh; bq / b2q stand in for the precomputed
     // floor(w 2^256 / p): the instruction stream does not depend on their values), 5 = word-serial Montgomery
     // product without the final correction (fp_mul_lazy, what k_ntt_pass runs today).
@@ -242,13 +242,13 @@ __global__ void __launch_bounds__(256) k_modmul_peak(Fp<PP>* out, u32 iters, u32
       c.v[0] ^= a.v[7];  // the two chains stay in step, like a = f(a, b); c = f(c, a) below
     }
     out[blockIdx.x * blockDim.x + threadIdx.x] = fp_add(shoup::canon_3p<PP>(a.v), shoup::canon_3p<PP>(c.v));
-    return;
+  } else {
+    for (u32 it = 0; it < iters; it++) {
+      a = bench_product<PP, VARIANT>(a, b);
+      c = bench_product<PP, VARIANT>(c, a);
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = fp_add(a, c);
   }
-  for (u32 it = 0; it < iters; it++) {
-    a = bench_product<PP, VARIANT>(a, b);
-    c = bench_product<PP, VARIANT>(c, a);
-  }
-  out[blockIdx.x * blockDim.x + threadIdx.x] = fp_add(a, c);
 }
 
 template <class PP>
