@@ -52,7 +52,7 @@ enum {
 };
 
 /* ---- context ------------------------------------------------------------------------- */
-/* One context per GPU.  `stream` is a cudaStream_t (NULL = the legacy default stream); every
+/* One context per GPU (several GPUs behind one handle: eon_mctx below).  `stream` is a cudaStream_t (NULL = the legacy default stream); every
  * kernel of the context is launched on it, so callers can bracket calls with their own
  * events (e.g. torch.cuda.current_stream().cuda_stream).
  * Replaces the implicit "process-global Radix2Dit / KzgPcs state" of the reference
@@ -103,6 +103,12 @@ int eon_coset_idft_batch(eon_ctx* ctx, const uint64_t* h_in, uint64_t* h_out, un
                          const uint64_t shift[4]);
 int eon_coset_lde_batch(eon_ctx* ctx, const uint64_t* h_in, uint64_t* h_out, unsigned log_h, size_t width,
                         unsigned added_bits, const uint64_t shift[4]);
+
+/* coset_lde_batch on the columns [0, width) of a WIDER host matrix: ld_in / ld_out = row pitch of the host
+ * matrices in Fr elements (0 = dense).  A caller that shards the columns of one RowMajorMatrix over several
+ * contexts (one per GPU) passes (base + c0 * 4, ld = full width) to each: no host-side de-interleave. */
+int eon_coset_lde_batch_ld(eon_ctx* ctx, const uint64_t* h_in, size_t ld_in, uint64_t* h_out, size_t ld_out,
+                           unsigned log_h, size_t width, unsigned added_bits, const uint64_t shift[4]);
 
 /* ---- SRS (kzg/src/params.rs) ------------------------------------------------------------- */
 /* Upload g1_powers as n affine points (8 x u64 each).  Replaces the per-call `to_affine` of
@@ -166,6 +172,19 @@ int eon_msm_points(eon_ctx* ctx, const uint64_t* h_points_xy, const uint64_t* h_
 /* MSM over the SRS slice [first, first + n) — the index-range shard of a multi-GPU MSM. */
 int eon_msm_srs_range_dev(eon_ctx* ctx, const uint64_t* d_scalars, size_t first, size_t n, size_t ncols, size_t ld,
                           uint64_t* h_out_xy);
+/* The same shard with its ncols partial sums left ON THE DEVICE (d_out_xy: ncols affine wire points), queued on the
+ * context's stream without a host synchronisation: the shards' sums are then gathered over NVLink (peer copy or
+ * ncclAllGather on the same stream) and added by eon_g1_sum_cols_dev -- no host hop (EC addition is not an NCCL
+ * reduction op, so the "partial-sum reduction" of BASELINE configs[4] is all_gather + one add kernel). */
+int eon_msm_srs_range_partial_dev(eon_ctx* ctx, const uint64_t* d_scalars, size_t first, size_t n, size_t ncols,
+                                  size_t ld, uint64_t* d_out_xy);
+/* h_out_xy[c] = sum_p d_parts_xy[p * ncols + c]: nparts x ncols affine wire points on the device -> ncols on the host */
+int eon_g1_sum_cols_dev(eon_ctx* ctx, const uint64_t* d_parts_xy, size_t nparts, size_t ncols, uint64_t* h_out_xy);
+/* Window tables over the SRS index range [first, first + n) only, beside the whole-SRS tables: the shard one GPU
+ * owns in an index-range sharded MSM gets a window sized for ITS length (2^21 points of a 2^24-point SRS: c = 17-18
+ * instead of 20, an eighth of the buckets to reduce).  window_bits 0 = cost model; n = 0 drops them.  MSMs whose
+ * bases lie inside the range use these tables. */
+int eon_srs_set_range_tables(eon_ctx* ctx, size_t first, size_t n, unsigned window_bits);
 /* out = sum of n affine points (combining per-GPU partial sums). */
 int eon_g1_sum(eon_ctx* ctx, const uint64_t* h_points_xy, size_t n, uint64_t* h_out_xy);
 
@@ -192,6 +211,13 @@ int eon_kzg_commit_lde_dev(eon_ctx* ctx, const uint64_t* d_evals, unsigned log_h
 int eon_kzg_commit_lde(eon_ctx* ctx, const uint64_t* h_evals, unsigned log_h, size_t width, const uint64_t shift[4],
                        uint64_t* h_commit_xy, eon_handle* out_handle, unsigned lde_log_size,
                        const uint64_t lde_shift[4], uint64_t* h_lde_out);
+/* The two entry points above on the columns [0, width) of a wider host matrix (row pitch ld_in; ld_out for the LDE
+ * result), see eon_coset_lde_batch_ld. */
+int eon_kzg_commit_ld(eon_ctx* ctx, const uint64_t* h_evals, size_t ld_in, unsigned log_h, size_t width,
+                      const uint64_t shift[4], uint64_t* h_commit_xy, eon_handle* out_handle);
+int eon_kzg_commit_lde_ld(eon_ctx* ctx, const uint64_t* h_evals, size_t ld_in, unsigned log_h, size_t width,
+                          const uint64_t shift[4], uint64_t* h_commit_xy, eon_handle* out_handle, unsigned lde_log_size,
+                          const uint64_t lde_shift[4], uint64_t* h_lde_out, size_t ld_out);
 /* Pcs::commit_quotient (trait default, commit/src/pcs.rs:82-102) in one call.  `evals`: the quotient
  * evaluations on shift*<omega_{2^log_size}>, natural order, (1 << log_size) x width.  Chunk i (of
  * 2^log_chunks) is rows i, i + 2^log_chunks, ... (split_evals, commit/src/domain.rs:188-221) on the coset
@@ -220,9 +246,13 @@ int eon_kzg_commit_coeffs_dev(eon_ctx* ctx, const uint64_t* d_coeffs, size_t row
 int eon_kzg_read_coeffs(eon_ctx* ctx, eon_handle h, uint64_t* h_out);
 /* get_evaluations_on_domain (pcs.rs:267-287) on the coset shift*<omega_{2^log_size}>,
  * natural order, (1 << log_size) x width.  Computed as zero-pad + coset NTT, which is
- * bit-identical to the reference's Horner evaluation.  Requires 2^log_size >= h. */
+ * bit-identical to the reference's Horner evaluation; a coset smaller than h (the Horner loop accepts any)
+ * is served by first reducing the coefficients mod X^(2^log_size) - shift^(2^log_size). */
 int eon_kzg_evals_on_coset(eon_ctx* ctx, eon_handle h, unsigned log_size, const uint64_t shift[4], uint64_t* h_out);
 int eon_kzg_evals_on_coset_dev(eon_ctx* ctx, eon_handle h, unsigned log_size, const uint64_t shift[4], uint64_t* d_out);
+/* ... into the columns [0, width) of a wider host matrix with row pitch ld_out (0 = dense) */
+int eon_kzg_evals_on_coset_ld(eon_ctx* ctx, eon_handle h, unsigned log_size, const uint64_t shift[4], uint64_t* h_out,
+                              size_t ld_out);
 /* open (pcs.rs:289-335) of one matrix at `npoints` points: for point p and column c
  *   h_values[p*width + c]       = f_c(z_p)                         (Fr)
  *   h_witness_xy[(p*width+c)*8] = commit((f_c - f_c(z_p))/(X - z_p)) (G1 affine)
@@ -245,6 +275,64 @@ int eon_handle_free(eon_ctx* ctx, eon_handle h);
  * whose last row is zero; h_values gets the width evaluations f_c(z). */
 int eon_quotient_and_eval_dev(eon_ctx* ctx, const uint64_t* d_coeffs, size_t h, size_t width, const uint64_t z[4],
                               uint64_t* d_quot, uint64_t* h_values);
+
+/* ---- multi-device context: one process, several GPUs, the same host-matrix calls ---------------------------------
+ * The reference prover is ONE process that hands whole matrices to pcs.commit / get_evaluations_on_domain / open
+ * (eon-uni-stark/src/prover.rs:186-187,307-322,371-372,424-442); KzgPcs then walks the columns one by one
+ * (kzg/src/pcs.rs:244-249,311-318).  An eon_mctx takes the same whole host matrices and splits the COLUMNS over its
+ * devices (device g: a contiguous column range, copied straight out of / into the caller's row-major buffers with
+ * strided copies; the SRS is replicated), so a Rust `Pcs` / `TwoAdicSubgroupDft` shim reaches every GPU of the box
+ * without knowing about them.  Results are byte-identical to the single-device entry points of the same name.
+ * A single MSM with fewer columns than devices is sharded by point index instead (per-device range tables, partial
+ * sums pushed to the first device as NVLink peer copies, one add kernel there).
+ * `devices`: CUDA ordinals; the same ordinal may appear more than once (several shard contexts on one GPU: how the
+ * sharding logic is tested on a single-GPU box).  Handles returned by an eon_mctx are only valid with eon_mctx_*.
+ * The per-device contexts are reachable through eon_mctx_ctx for tuning / timing calls (eon_msm_set_*,
+ * eon_last_phase_ms, ...); do not run work on them while an eon_mctx_* call is in flight. */
+typedef struct eon_mctx eon_mctx;
+int eon_mctx_create(const int* devices, int n, eon_mctx** out);
+void eon_mctx_destroy(eon_mctx* m);
+const char* eon_mctx_last_error(const eon_mctx* m);
+int eon_mctx_device_count(const eon_mctx* m);
+eon_ctx* eon_mctx_ctx(eon_mctx* m, int i);
+uint64_t eon_mctx_launch_count(const eon_mctx* m);
+/* SRS, replicated on every device (init_srs_unsafe / deserialised g1_powers, kzg/src/params.rs:57-139) */
+int eon_mctx_srs_generate_unsafe(eon_mctx* m, const uint64_t alpha[4], size_t n);
+int eon_mctx_srs_load_affine(eon_mctx* m, const uint64_t* h_xy, size_t n);
+int eon_mctx_srs_load_compressed(eon_mctx* m, const uint8_t* h_in, size_t n, int enc, size_t* bad_index);
+size_t eon_mctx_srs_size(const eon_mctx* m);
+int eon_mctx_srs_read(eon_mctx* m, size_t first, size_t n, uint64_t* h_xy);
+/* TwoAdicSubgroupDft<Fr> (dft/src/traits.rs:61,83-91,111-122,144-153,226-249), whole host matrices */
+int eon_mctx_dft_batch(eon_mctx* m, const uint64_t* h_in, uint64_t* h_out, unsigned log_h, size_t width);
+int eon_mctx_coset_dft_batch(eon_mctx* m, const uint64_t* h_in, uint64_t* h_out, unsigned log_h, size_t width,
+                             const uint64_t shift[4]);
+int eon_mctx_idft_batch(eon_mctx* m, const uint64_t* h_in, uint64_t* h_out, unsigned log_h, size_t width);
+int eon_mctx_coset_idft_batch(eon_mctx* m, const uint64_t* h_in, uint64_t* h_out, unsigned log_h, size_t width,
+                              const uint64_t shift[4]);
+int eon_mctx_coset_lde_batch(eon_mctx* m, const uint64_t* h_in, uint64_t* h_out, unsigned log_h, size_t width,
+                             unsigned added_bits, const uint64_t shift[4]);
+/* KzgPcs (kzg/src/pcs.rs:223-335) and KzgMmcs::commit (kzg/src/mmcs.rs:155-190), arguments as the eon_kzg_* forms */
+int eon_mctx_kzg_commit(eon_mctx* m, const uint64_t* h_evals, unsigned log_h, size_t width, const uint64_t shift[4],
+                        uint64_t* h_commit_xy, eon_handle* out_handle);
+int eon_mctx_kzg_commit_lde(eon_mctx* m, const uint64_t* h_evals, unsigned log_h, size_t width, const uint64_t shift[4],
+                            uint64_t* h_commit_xy, eon_handle* out_handle, unsigned lde_log_size,
+                            const uint64_t lde_shift[4], uint64_t* h_lde_out);
+int eon_mctx_kzg_commit_coeffs(eon_mctx* m, const uint64_t* h_coeffs, size_t rows, size_t width, uint64_t* h_commit_xy,
+                               eon_handle* out_handle);
+int eon_mctx_kzg_commit_quotient(eon_mctx* m, const uint64_t* h_evals, unsigned log_size, size_t width,
+                                 unsigned log_chunks, const uint64_t shift[4], uint64_t* h_commit_xy,
+                                 eon_handle* out_handles);
+int eon_mctx_kzg_evals_on_coset(eon_mctx* m, eon_handle h, unsigned log_size, const uint64_t shift[4], uint64_t* h_out);
+int eon_mctx_kzg_open_batch(eon_mctx* m, size_t nmat, const eon_handle* handles, const size_t* npoints,
+                            const uint64_t* h_points, uint64_t* h_values, uint64_t* h_witness_xy);
+int eon_mctx_kzg_read_coeffs(eon_mctx* m, eon_handle h, uint64_t* h_out);
+int eon_mctx_handle_dims(eon_mctx* m, eon_handle h, unsigned* log_h, size_t* width);
+int eon_mctx_handle_free(eon_mctx* m, eon_handle h);
+/* G1::multi_exp (bn254/src/curve.rs:158-180): over the resident SRS (columns sharded when ncols >= devices, else the
+ * points by index range) and over explicit bases (index range) */
+int eon_mctx_msm_srs(eon_mctx* m, const uint64_t* h_scalars, size_t n, size_t ncols, size_t ld, uint64_t* h_out_xy);
+int eon_mctx_msm_points(eon_mctx* m, const uint64_t* h_points_xy, const uint64_t* h_scalars, size_t n,
+                        uint64_t* h_out_xy);
 
 /* ---- measurement helpers ------------------------------------------------------------------- */
 /* Dependency-free integer-multiply microbenchmark: launches `iters` rounds on all SMs and

@@ -5,8 +5,8 @@ All compute happens in libeon_kzg.so (hand-written CUDA, sm_100a) through the C 
 include/eon_kzg.h.  This package is only the host-side mirror of the reference interface.
 Importing it does not require a GPU; creating a Context / running anything does.
 """
-from .lib import (Context, DegreeTooLarge, EonError, InvalidG1Point, default_context, load,  # noqa: F401
-                  pinned_empty)
+from .lib import (Context, DegreeTooLarge, EonError, InvalidG1Point, MultiContext, default_context,  # noqa: F401
+                  load, pinned_empty)
 from .dft import GpuDft  # noqa: F401
 from .pcs import GpuKzgPcs, TwoAdicMultiplicativeCoset, observe_commitment  # noqa: F401
 from .mmcs import GpuKzgMmcs  # noqa: F401

@@ -31,16 +31,32 @@ int set_device(eon_ctx* ctx) {
 
 size_t mat_bytes(unsigned log_h, size_t width) { return (((size_t)1) << log_h) * width * sizeof(Fr); }
 
-// host-buffer wrapper: H2D into scratch A, run f(d_in, d_out), D2H from scratch B
+// host-buffer wrapper: H2D into scratch A, run f(d_in, d_out), D2H from scratch B.  The device copies are dense
+// (row pitch = width); ld_in / ld_out are the host row pitches in elements (0 = dense): a column range of a wider
+// host matrix goes through strided copies (the multi-device context hands every GPU its columns that way).
 template <class F>
-int host_io(eon_ctx* ctx, const uint64_t* h_in, size_t in_bytes, uint64_t* h_out, size_t out_bytes, F f) {
+int host_io(eon_ctx* ctx, const uint64_t* h_in, size_t rows_in, size_t ld_in, uint64_t* h_out, size_t rows_out,
+            size_t ld_out, size_t width, F f) {
+  const size_t in_bytes = rows_in * width * sizeof(Fr), out_bytes = rows_out * width * sizeof(Fr);
   if ((in_bytes && !h_in) || (out_bytes && !h_out)) return fail(ctx, EON_ERR_BAD_ARG, "null host buffer");
+  if ((ld_in && ld_in < width) || (ld_out && ld_out < width)) return fail(ctx, EON_ERR_BAD_ARG, "row pitch < width");
   void *d_in = nullptr, *d_out = nullptr;
   EON_TRY(scratch_get(ctx, SC_IO_A, in_bytes + 32, &d_in));
   EON_TRY(scratch_get(ctx, SC_IO_B, out_bytes + 32, &d_out));
-  if (in_bytes) EON_CUDA(ctx, cudaMemcpyAsync(d_in, h_in, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
+  const size_t wb = width * sizeof(Fr);
+  if (in_bytes) {
+    if (ld_in == 0 || ld_in == width)
+      EON_CUDA(ctx, cudaMemcpyAsync(d_in, h_in, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    else
+      EON_CUDA(ctx, cudaMemcpy2DAsync(d_in, wb, h_in, ld_in * sizeof(Fr), wb, rows_in, cudaMemcpyHostToDevice, ctx->stream));
+  }
   EON_TRY(f((const Fr*)d_in, (Fr*)d_out));
-  if (out_bytes) EON_CUDA(ctx, cudaMemcpyAsync(h_out, d_out, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  if (out_bytes) {
+    if (ld_out == 0 || ld_out == width)
+      EON_CUDA(ctx, cudaMemcpyAsync(h_out, d_out, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    else
+      EON_CUDA(ctx, cudaMemcpy2DAsync(h_out, ld_out * sizeof(Fr), d_out, wb, wb, rows_out, cudaMemcpyDeviceToHost, ctx->stream));
+  }
   EON_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return EON_OK;
 }
@@ -92,6 +108,7 @@ void eon_ctx_destroy(eon_ctx* ctx) {
   for (auto& kv : ctx->coeff_pool) cudaFree(kv.second);
   if (ctx->d_srs) cudaFree(ctx->d_srs);
   if (ctx->d_srs_tab) cudaFree(ctx->d_srs_tab);
+  if (ctx->d_rng_tab) cudaFree(ctx->d_rng_tab);
   for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
   for (cudaEvent_t e : ctx->ev_pipe)
     if (e) cudaEventDestroy(e);
@@ -222,62 +239,69 @@ int eon_coset_lde_batch_dev(eon_ctx* ctx, const uint64_t* d_in, uint64_t* d_out,
   return lde_dev(ctx, d_in, d_out, log_h, width, added_bits, s);
 }
 
+}  // extern "C"
+
+namespace eon {
+// Host-buffer transform of one matrix (or of a column range of a wider host matrix: ld_in / ld_out = host row
+// pitch in elements, 0 = dense), ctx->mu held.  kind: DFT_* below; shift ignored for the plain kinds.
+int dft_host_locked(eon_ctx* ctx, int kind, const uint64_t* h_in, size_t ld_in, uint64_t* h_out, size_t ld_out,
+                    unsigned log_h, size_t width, unsigned added_bits, const uint64_t shift[4]) {
+  EON_TRY(set_device(ctx));
+  if (kind != DFT_COSET_LDE) added_bits = 0;
+  EON_TRY(check_dims(ctx, log_h, width, added_bits));
+  Fr s = Fr::one();
+  if (kind == DFT_COSET || kind == DFT_COSET_INV || kind == DFT_COSET_LDE) EON_TRY(check_shift(ctx, shift, &s));
+  const size_t rows = (size_t)1 << log_h;
+  return host_io(ctx, h_in, rows, ld_in, h_out, rows << added_bits, ld_out, width, [&](const Fr* i, Fr* o) {
+    const uint64_t* di = (const uint64_t*)i;
+    uint64_t* dout = (uint64_t*)o;
+    switch (kind) {
+      case DFT_PLAIN:
+      case DFT_COSET: return dft_dev(ctx, di, dout, log_h, width, s);
+      case DFT_INV:
+      case DFT_COSET_INV: return idft_dev(ctx, di, dout, log_h, width, s);
+      case DFT_COSET_LDE: return lde_dev(ctx, di, dout, log_h, width, added_bits, s);
+    }
+    return fail(ctx, EON_ERR_BAD_ARG, "unknown transform kind");
+  });
+}
+}  // namespace eon
+
+extern "C" {
+
 int eon_dft_batch(eon_ctx* ctx, const uint64_t* h_in, uint64_t* h_out, unsigned log_h, size_t width) {
   if (!ctx) return EON_ERR_BAD_ARG;
   Lock lk(ctx);
-  EON_TRY(set_device(ctx));
-  EON_TRY(check_dims(ctx, log_h, width));
-  size_t b = mat_bytes(log_h, width);
-  return host_io(ctx, h_in, b, h_out, b, [&](const Fr* i, Fr* o) {
-    return dft_dev(ctx, (const uint64_t*)i, (uint64_t*)o, log_h, width, Fr::one());
-  });
+  return dft_host_locked(ctx, DFT_PLAIN, h_in, 0, h_out, 0, log_h, width, 0, nullptr);
 }
 int eon_coset_dft_batch(eon_ctx* ctx, const uint64_t* h_in, uint64_t* h_out, unsigned log_h, size_t width,
                         const uint64_t shift[4]) {
   if (!ctx) return EON_ERR_BAD_ARG;
   Lock lk(ctx);
-  EON_TRY(set_device(ctx));
-  EON_TRY(check_dims(ctx, log_h, width));
-  Fr s;
-  EON_TRY(check_shift(ctx, shift, &s));
-  size_t b = mat_bytes(log_h, width);
-  return host_io(ctx, h_in, b, h_out, b,
-                 [&](const Fr* i, Fr* o) { return dft_dev(ctx, (const uint64_t*)i, (uint64_t*)o, log_h, width, s); });
+  return dft_host_locked(ctx, DFT_COSET, h_in, 0, h_out, 0, log_h, width, 0, shift);
 }
 int eon_idft_batch(eon_ctx* ctx, const uint64_t* h_in, uint64_t* h_out, unsigned log_h, size_t width) {
   if (!ctx) return EON_ERR_BAD_ARG;
   Lock lk(ctx);
-  EON_TRY(set_device(ctx));
-  EON_TRY(check_dims(ctx, log_h, width));
-  size_t b = mat_bytes(log_h, width);
-  return host_io(ctx, h_in, b, h_out, b, [&](const Fr* i, Fr* o) {
-    return idft_dev(ctx, (const uint64_t*)i, (uint64_t*)o, log_h, width, Fr::one());
-  });
+  return dft_host_locked(ctx, DFT_INV, h_in, 0, h_out, 0, log_h, width, 0, nullptr);
 }
 int eon_coset_idft_batch(eon_ctx* ctx, const uint64_t* h_in, uint64_t* h_out, unsigned log_h, size_t width,
                          const uint64_t shift[4]) {
   if (!ctx) return EON_ERR_BAD_ARG;
   Lock lk(ctx);
-  EON_TRY(set_device(ctx));
-  EON_TRY(check_dims(ctx, log_h, width));
-  Fr s;
-  EON_TRY(check_shift(ctx, shift, &s));
-  size_t b = mat_bytes(log_h, width);
-  return host_io(ctx, h_in, b, h_out, b,
-                 [&](const Fr* i, Fr* o) { return idft_dev(ctx, (const uint64_t*)i, (uint64_t*)o, log_h, width, s); });
+  return dft_host_locked(ctx, DFT_COSET_INV, h_in, 0, h_out, 0, log_h, width, 0, shift);
 }
 int eon_coset_lde_batch(eon_ctx* ctx, const uint64_t* h_in, uint64_t* h_out, unsigned log_h, size_t width,
                         unsigned added_bits, const uint64_t shift[4]) {
   if (!ctx) return EON_ERR_BAD_ARG;
   Lock lk(ctx);
-  EON_TRY(set_device(ctx));
-  EON_TRY(check_dims(ctx, log_h, width, added_bits));
-  Fr s;
-  EON_TRY(check_shift(ctx, shift, &s));
-  return host_io(ctx, h_in, mat_bytes(log_h, width), h_out, mat_bytes(log_h + added_bits, width),
-                 [&](const Fr* i, Fr* o) {
-                   return lde_dev(ctx, (const uint64_t*)i, (uint64_t*)o, log_h, width, added_bits, s);
-                 });
+  return dft_host_locked(ctx, DFT_COSET_LDE, h_in, 0, h_out, 0, log_h, width, added_bits, shift);
+}
+int eon_coset_lde_batch_ld(eon_ctx* ctx, const uint64_t* h_in, size_t ld_in, uint64_t* h_out, size_t ld_out,
+                           unsigned log_h, size_t width, unsigned added_bits, const uint64_t shift[4]) {
+  if (!ctx) return EON_ERR_BAD_ARG;
+  Lock lk(ctx);
+  return dft_host_locked(ctx, DFT_COSET_LDE, h_in, ld_in, h_out, ld_out, log_h, width, added_bits, shift);
 }
 
 // ---- SRS ---------------------------------------------------------------------------------------
@@ -288,6 +312,7 @@ static int srs_drop(eon_ctx* ctx) {
     ctx->d_srs = nullptr;
     ctx->srs_n = 0;
     EON_TRY(srs_build_tables(ctx, 0));
+    EON_TRY(srs_build_range_tables(ctx, 0, 0, 0));
   }
   return EON_OK;
 }
@@ -404,7 +429,7 @@ int eon_srs_read(eon_ctx* ctx, size_t first, size_t n, uint64_t* h_xy) {
   if (!ctx) return EON_ERR_BAD_ARG;
   Lock lk(ctx);
   EON_TRY(set_device(ctx));
-  if (first + n > ctx->srs_n) return fail(ctx, EON_ERR_BAD_ARG, "SRS range out of bounds");
+  if (first > ctx->srs_n || n > ctx->srs_n - first) return fail(ctx, EON_ERR_BAD_ARG, "SRS range out of bounds");
   if (n == 0) return EON_OK;
   EON_CUDA(ctx, cudaMemcpyAsync(h_xy, ctx->d_srs + first, n * sizeof(G1Affine), cudaMemcpyDeviceToHost, ctx->stream));
   EON_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -430,7 +455,7 @@ int eon_msm_srs_range_dev(eon_ctx* ctx, const uint64_t* d_scalars, size_t first,
   if (!ctx) return EON_ERR_BAD_ARG;
   Lock lk(ctx);
   EON_TRY(set_device(ctx));
-  if (first + n > ctx->srs_n) {
+  if (first > ctx->srs_n || n > ctx->srs_n - first) {
     // commit_column's degree guard (kzg/src/util.rs:38, params.rs:164-173)
     char b[128];
     snprintf(b, sizeof(b), "DegreeTooLarge: need %zu SRS points, have %zu", first + n, ctx->srs_n);
@@ -438,6 +463,48 @@ int eon_msm_srs_range_dev(eon_ctx* ctx, const uint64_t* d_scalars, size_t first,
   }
   if (n && ncols && !d_scalars) return fail(ctx, EON_ERR_BAD_ARG, "null scalars");
   return msm_to_host(ctx, ctx->d_srs + first, (const Fr*)d_scalars, n, ncols, ld, h_out_xy);
+}
+
+// index-range shard with the partial sums left on the device (ncols affine points at d_out_xy), queued on the
+// context's stream without a host synchronisation: the caller gathers the shards' partial sums over NVLink
+// (peer copy or ncclAllGather) and adds them with eon_g1_sum_cols_dev -- no host hop in between.
+int eon_msm_srs_range_partial_dev(eon_ctx* ctx, const uint64_t* d_scalars, size_t first, size_t n, size_t ncols,
+                                  size_t ld, uint64_t* d_out_xy) {
+  if (!ctx) return EON_ERR_BAD_ARG;
+  Lock lk(ctx);
+  EON_TRY(set_device(ctx));
+  if (first > ctx->srs_n || n > ctx->srs_n - first) {
+    char b[128];
+    snprintf(b, sizeof(b), "DegreeTooLarge: need %zu SRS points, have %zu", first + n, ctx->srs_n);
+    return fail(ctx, EON_ERR_SRS_TOO_SHORT, b);
+  }
+  if (ncols == 0) return EON_OK;
+  if ((n && !d_scalars) || !d_out_xy) return fail(ctx, EON_ERR_BAD_ARG, "null buffer");
+  if (ld < ncols) return fail(ctx, EON_ERR_BAD_ARG, "ld < ncols");
+  return msm_run(ctx, ctx->d_srs + first, (const Fr*)d_scalars, n, ncols, ld, (G1Affine*)d_out_xy);
+}
+
+int eon_g1_sum_cols_dev(eon_ctx* ctx, const uint64_t* d_parts_xy, size_t nparts, size_t ncols, uint64_t* h_out_xy) {
+  if (!ctx) return EON_ERR_BAD_ARG;
+  Lock lk(ctx);
+  EON_TRY(set_device(ctx));
+  if (ncols == 0) return EON_OK;
+  if ((nparts && !d_parts_xy) || !h_out_xy) return fail(ctx, EON_ERR_BAD_ARG, "null buffer");
+  void* d_res = nullptr;
+  EON_TRY(scratch_get(ctx, SC_MSM_RESULT, ncols * sizeof(G1Affine) + 64, &d_res));
+  EON_TRY(g1_sum_cols_run(ctx, (const G1Affine*)d_parts_xy, nparts, ncols, (G1Affine*)d_res));
+  EON_CUDA(ctx, cudaMemcpyAsync(h_out_xy, d_res, ncols * sizeof(G1Affine), cudaMemcpyDeviceToHost, ctx->stream));
+  EON_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return EON_OK;
+}
+
+int eon_srs_set_range_tables(eon_ctx* ctx, size_t first, size_t n, unsigned window_bits) {
+  if (!ctx) return EON_ERR_BAD_ARG;
+  Lock lk(ctx);
+  EON_TRY(set_device(ctx));
+  EON_TRY(srs_build_range_tables(ctx, first, n, window_bits));
+  EON_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return EON_OK;
 }
 
 int eon_msm_srs_dev(eon_ctx* ctx, const uint64_t* d_scalars, size_t n, size_t ncols, size_t ld, uint64_t* h_out_xy) {
@@ -580,7 +647,7 @@ static int kzg_commit_locked(eon_ctx* ctx, const uint64_t* d_evals, unsigned log
 // KzgMmcs::commit (kzg/src/mmcs.rs:155-190): the matrix columns ARE the coefficient vectors (no
 // iDFT), any height.  d_coeffs_in is copied into a pooled buffer that the handle owns.
 static int kzg_commit_coeffs_locked(eon_ctx* ctx, const uint64_t* src, bool src_is_host, size_t rows, size_t width,
-                                    uint64_t* h_commit_xy, eon_handle* out_handle) {
+                                    uint64_t* h_commit_xy, eon_handle* out_handle, size_t src_ld = 0) {
   if (!out_handle) return fail(ctx, EON_ERR_BAD_ARG, "null handle pointer");
   *out_handle = 0;
   if (width > 0xffffffffull || (width && rows > (~(size_t)0) / (width * sizeof(Fr))))
@@ -597,9 +664,16 @@ static int kzg_commit_coeffs_locked(eon_ctx* ctx, const uint64_t* src, bool src_
   size_t cap = 0;
   EON_TRY(coeff_buffer_get(ctx, bytes + 32, &d_coeffs, &cap));
   int rc = EON_OK;
+  if (src_ld && src_ld < width) {
+    cudaFree(d_coeffs);
+    return fail(ctx, EON_ERR_BAD_ARG, "row pitch < width");
+  }
   if (bytes) {
-    cudaError_t e = cudaMemcpyAsync(d_coeffs, src, bytes, src_is_host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice,
-                                    ctx->stream);
+    const cudaMemcpyKind kind = src_is_host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
+    cudaError_t e = (src_ld == 0 || src_ld == width)
+                        ? cudaMemcpyAsync(d_coeffs, src, bytes, kind, ctx->stream)
+                        : cudaMemcpy2DAsync(d_coeffs, width * sizeof(Fr), src, src_ld * sizeof(Fr), width * sizeof(Fr), rows,
+                                            kind, ctx->stream);
     if (e != cudaSuccess) rc = fail(ctx, EON_ERR_CUDA, std::string("copy of the coefficient matrix failed: ") + cudaGetErrorString(e));
   }
   if (rc == EON_OK) rc = msm_to_host(ctx, ctx->d_srs, d_coeffs, rows, width, width, h_commit_xy);
@@ -679,10 +753,16 @@ static int pipe_init(eon_ctx* ctx) {
 
 // commit from host buffers, optionally with the evaluations on a second coset (the LDE the prover asks
 // for next, eon-uni-stark/src/prover.rs:307-322) produced in the same call: lde_log_size == 0 -> none.
-static int kzg_commit_host(eon_ctx* ctx, const uint64_t* h_evals, unsigned log_h, size_t width, const uint64_t shift[4],
-                           uint64_t* h_commit_xy, eon_handle* out_handle, unsigned lde_log_size,
-                           const uint64_t lde_shift[4], uint64_t* h_lde_out) {
+// h_ld_in / h_ld_out: row pitch of the host matrices in elements (0 = dense, i.e. width): the columns
+// [c0, c0 + width) of a wider host matrix are passed as (base + c0, ld = full width).
+static int kzg_commit_host(eon_ctx* ctx, const uint64_t* h_evals, size_t h_ld_in, unsigned log_h, size_t width,
+                           const uint64_t shift[4], uint64_t* h_commit_xy, eon_handle* out_handle, unsigned lde_log_size,
+                           const uint64_t lde_shift[4], uint64_t* h_lde_out, size_t h_ld_out) {
   EON_TRY(check_dims(ctx, log_h, width));
+  if (h_ld_in == 0) h_ld_in = width;
+  if (h_ld_out == 0) h_ld_out = width;
+  if (h_ld_in < width || h_ld_out < width) return fail(ctx, EON_ERR_BAD_ARG, "row pitch < width");
+  const size_t hpitch_in = h_ld_in * sizeof(Fr), hpitch_out = h_ld_out * sizeof(Fr);
   const bool want_lde = lde_log_size != 0;
   Fr ls = Fr::one();
   if (want_lde) {
@@ -697,7 +777,10 @@ static int kzg_commit_host(eon_ctx* ctx, const uint64_t* h_evals, unsigned log_h
   EON_TRY(scratch_get(ctx, SC_IO_A, b + 32, &d_in));
   auto groups = column_groups(width, b, true);
   if (groups.size() == 1 && !want_lde) {
-    if (b) EON_CUDA(ctx, cudaMemcpyAsync(d_in, h_evals, b, cudaMemcpyHostToDevice, ctx->stream));
+    if (b && h_ld_in == width) EON_CUDA(ctx, cudaMemcpyAsync(d_in, h_evals, b, cudaMemcpyHostToDevice, ctx->stream));
+    else if (b)
+      EON_CUDA(ctx, cudaMemcpy2DAsync(d_in, width * sizeof(Fr), h_evals, hpitch_in, width * sizeof(Fr), (size_t)1 << log_h,
+                                      cudaMemcpyHostToDevice, ctx->stream));
     return kzg_commit_locked(ctx, (const uint64_t*)d_in, log_h, width, shift, h_commit_xy, out_handle);
   }
   if (width == 0) {
@@ -731,7 +814,7 @@ static int kzg_commit_host(eon_ctx* ctx, const uint64_t* h_evals, unsigned log_h
   if (rc == EON_OK) cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_pipe[7], 0);
   for (size_t g = 0; rc == EON_OK && g < groups.size(); g++) {
     const size_t c0 = groups[g].first, gw = groups[g].second;
-    cudaError_t e = cudaMemcpy2DAsync((Fr*)d_in + c0, pitch, (const Fr*)h_evals + c0, pitch, gw * sizeof(Fr), h,
+    cudaError_t e = cudaMemcpy2DAsync((Fr*)d_in + c0, pitch, (const Fr*)h_evals + c0, hpitch_in, gw * sizeof(Fr), h,
                                       cudaMemcpyHostToDevice, ctx->copy_stream);
     if (e == cudaSuccess) e = cudaEventRecord(ctx->ev_pipe[g], ctx->copy_stream);
     if (e != cudaSuccess) rc = fail(ctx, EON_ERR_CUDA, std::string("group upload failed: ") + cudaGetErrorString(e));
@@ -747,7 +830,7 @@ static int kzg_commit_host(eon_ctx* ctx, const uint64_t* h_evals, unsigned log_h
       if (rc == EON_OK) {
         cudaError_t e = cudaStreamWaitEvent(ctx->copy_stream2, ctx->ev_pipe[8 + g], 0);
         if (e == cudaSuccess)
-          e = cudaMemcpy2DAsync((Fr*)h_lde_out + c0, pitch, (const Fr*)d_lde + c0, pitch, gw * sizeof(Fr), lde_rows,
+          e = cudaMemcpy2DAsync((Fr*)h_lde_out + c0, hpitch_out, (const Fr*)d_lde + c0, pitch, gw * sizeof(Fr), lde_rows,
                                 cudaMemcpyDeviceToHost, ctx->copy_stream2);
         if (e != cudaSuccess) rc = fail(ctx, EON_ERR_CUDA, std::string("LDE download failed: ") + cudaGetErrorString(e));
       }
@@ -777,7 +860,15 @@ int eon_kzg_commit(eon_ctx* ctx, const uint64_t* h_evals, unsigned log_h, size_t
   if (!ctx) return EON_ERR_BAD_ARG;
   Lock lk(ctx);
   EON_TRY(set_device(ctx));
-  return kzg_commit_host(ctx, h_evals, log_h, width, shift, h_commit_xy, out_handle, 0, nullptr, nullptr);
+  return kzg_commit_host(ctx, h_evals, 0, log_h, width, shift, h_commit_xy, out_handle, 0, nullptr, nullptr, 0);
+}
+
+int eon_kzg_commit_ld(eon_ctx* ctx, const uint64_t* h_evals, size_t ld_in, unsigned log_h, size_t width,
+                      const uint64_t shift[4], uint64_t* h_commit_xy, eon_handle* out_handle) {
+  if (!ctx) return EON_ERR_BAD_ARG;
+  Lock lk(ctx);
+  EON_TRY(set_device(ctx));
+  return kzg_commit_host(ctx, h_evals, ld_in, log_h, width, shift, h_commit_xy, out_handle, 0, nullptr, nullptr, 0);
 }
 
 int eon_kzg_commit_lde(eon_ctx* ctx, const uint64_t* h_evals, unsigned log_h, size_t width, const uint64_t shift[4],
@@ -787,8 +878,19 @@ int eon_kzg_commit_lde(eon_ctx* ctx, const uint64_t* h_evals, unsigned log_h, si
   if (lde_log_size == 0) return EON_ERR_BAD_ARG;
   Lock lk(ctx);
   EON_TRY(set_device(ctx));
-  return kzg_commit_host(ctx, h_evals, log_h, width, shift, h_commit_xy, out_handle, lde_log_size, lde_shift,
-                         h_lde_out);
+  return kzg_commit_host(ctx, h_evals, 0, log_h, width, shift, h_commit_xy, out_handle, lde_log_size, lde_shift,
+                         h_lde_out, 0);
+}
+
+int eon_kzg_commit_lde_ld(eon_ctx* ctx, const uint64_t* h_evals, size_t ld_in, unsigned log_h, size_t width,
+                          const uint64_t shift[4], uint64_t* h_commit_xy, eon_handle* out_handle, unsigned lde_log_size,
+                          const uint64_t lde_shift[4], uint64_t* h_lde_out, size_t ld_out) {
+  if (!ctx) return EON_ERR_BAD_ARG;
+  if (lde_log_size == 0) return EON_ERR_BAD_ARG;
+  Lock lk(ctx);
+  EON_TRY(set_device(ctx));
+  return kzg_commit_host(ctx, h_evals, ld_in, log_h, width, shift, h_commit_xy, out_handle, lde_log_size, lde_shift,
+                         h_lde_out, ld_out);
 }
 
 // ---- Pcs::commit_quotient (commit/src/pcs.rs:82-102) ---------------------------------------------
@@ -798,16 +900,20 @@ int eon_kzg_commit_lde(eon_ctx* ctx, const uint64_t* h_evals, unsigned log_h, si
 // Here nothing is de-interleaved: chunk i IS the column group [i*width, (i+1)*width) of the same buffer
 // read with a row pitch of 2^log_chunks * width, the coset iDFTs write side by side into one
 // h x (chunks*width) coefficient matrix, and ONE batched MSM commits every column of every chunk.
+// chunk_first / chunk_count: the contiguous chunk range [chunk_first, chunk_first + chunk_count) this call commits
+// (everything for the single-device entry points; the multi-device context gives every GPU a range).  d_evals
+// holds ONLY those chunks: 2^(log_size - log_chunks) rows of chunk_count * width elements.
 static int kzg_commit_quotient_locked(eon_ctx* ctx, const Fr* d_evals, unsigned log_size, size_t width,
-                                      unsigned log_chunks, const uint64_t shift[4], uint64_t* h_commit_xy,
-                                      eon_handle* out_handles) {
+                                      unsigned log_chunks, size_t chunk_first, size_t chunk_count,
+                                      const uint64_t shift[4], uint64_t* h_commit_xy, eon_handle* out_handles) {
   if (log_chunks > log_size) return fail(ctx, EON_ERR_BAD_ARG, "more chunks than quotient rows");
   if (log_chunks > 16) return fail(ctx, EON_ERR_BAD_ARG, "too many quotient chunks");
   EON_TRY(check_dims(ctx, log_size, width));
   Fr s;
   EON_TRY(check_shift(ctx, shift, &s));
   if (!out_handles) return fail(ctx, EON_ERR_BAD_ARG, "null handle pointer");
-  const size_t nchunks = (size_t)1 << log_chunks;
+  const size_t nchunks = chunk_count;
+  if (chunk_first + chunk_count > ((size_t)1 << log_chunks)) return fail(ctx, EON_ERR_BAD_ARG, "chunk range out of bounds");
   for (size_t i = 0; i < nchunks; i++) out_handles[i] = 0;
   const unsigned log_h = log_size - log_chunks;
   const size_t h = (size_t)1 << log_h;
@@ -818,12 +924,13 @@ static int kzg_commit_quotient_locked(eon_ctx* ctx, const Fr* d_evals, unsigned 
     snprintf(b, sizeof(b), "DegreeTooLarge: degree %zu > max %zu", h - 1, ctx->srs_n ? ctx->srs_n - 1 : 0);
     return fail(ctx, EON_ERR_SRS_TOO_SHORT, b);
   }
-  if (width && (!d_evals || !h_commit_xy)) return fail(ctx, EON_ERR_BAD_ARG, "null buffer");
+  if (cw && (!d_evals || !h_commit_xy)) return fail(ctx, EON_ERR_BAD_ARG, "null buffer");
   void *d_comb = nullptr, *d_res = nullptr;
   EON_TRY(scratch_get(ctx, SC_QUOT, h * cw * sizeof(Fr) + 32, &d_comb));
   EON_TRY(scratch_get(ctx, SC_MSM_RESULT, cw * sizeof(G1Affine) + 64, &d_res));
   const Fr g = fr_two_adic_generator(log_size);
   Fr si = s;
+  for (size_t i = 0; i < chunk_first; i++) si = fp_mul(si, g);
   for (size_t i = 0; i < nchunks; i++) {
     EON_TRY(ntt_inverse(ctx, d_evals + i * width, (Fr*)d_comb + i * width, log_h, width, si, LAYOUT_NATURAL, cw, cw));
     si = fp_mul(si, g);
@@ -856,14 +963,40 @@ static int kzg_commit_quotient_locked(eon_ctx* ctx, const Fr* d_evals, unsigned 
   return EON_OK;
 }
 
+// host evaluations (the WHOLE quotient matrix, 2^log_size x width) -> the chunk range of this device
+static int kzg_commit_quotient_host(eon_ctx* ctx, const uint64_t* h_evals, unsigned log_size, size_t width,
+                                    unsigned log_chunks, size_t chunk_first, size_t chunk_count, const uint64_t shift[4],
+                                    uint64_t* h_commit_xy, eon_handle* out_handles) {
+  EON_TRY(check_dims(ctx, log_size, width));
+  if (log_chunks > log_size || log_chunks > 16) return fail(ctx, EON_ERR_BAD_ARG, "bad chunk count");
+  const size_t nchunks = (size_t)1 << log_chunks;
+  if (chunk_first + chunk_count > nchunks) return fail(ctx, EON_ERR_BAD_ARG, "chunk range out of bounds");
+  const size_t h = (size_t)1 << (log_size - log_chunks);
+  const size_t b = h * chunk_count * width * sizeof(Fr);
+  if (b && !h_evals) return fail(ctx, EON_ERR_BAD_ARG, "null evals");
+  void* d_in = nullptr;
+  EON_TRY(scratch_get(ctx, SC_IO_A, b + 32, &d_in));
+  if (b) {
+    if (chunk_count == nchunks)
+      EON_CUDA(ctx, cudaMemcpyAsync(d_in, h_evals, b, cudaMemcpyHostToDevice, ctx->stream));
+    else
+      EON_CUDA(ctx, cudaMemcpy2DAsync(d_in, chunk_count * width * sizeof(Fr), (const Fr*)h_evals + chunk_first * width,
+                                      nchunks * width * sizeof(Fr), chunk_count * width * sizeof(Fr), h,
+                                      cudaMemcpyHostToDevice, ctx->stream));
+  }
+  return kzg_commit_quotient_locked(ctx, (const Fr*)d_in, log_size, width, log_chunks, chunk_first, chunk_count, shift,
+                                    h_commit_xy, out_handles);
+}
+
 int eon_kzg_commit_quotient_dev(eon_ctx* ctx, const uint64_t* d_evals, unsigned log_size, size_t width,
                                 unsigned log_chunks, const uint64_t shift[4], uint64_t* h_commit_xy,
                                 eon_handle* out_handles) {
   if (!ctx) return EON_ERR_BAD_ARG;
   Lock lk(ctx);
   EON_TRY(set_device(ctx));
-  return kzg_commit_quotient_locked(ctx, (const Fr*)d_evals, log_size, width, log_chunks, shift, h_commit_xy,
-                                    out_handles);
+  if (log_chunks > 16) return fail(ctx, EON_ERR_BAD_ARG, "too many quotient chunks");
+  return kzg_commit_quotient_locked(ctx, (const Fr*)d_evals, log_size, width, log_chunks, 0, (size_t)1 << log_chunks,
+                                    shift, h_commit_xy, out_handles);
 }
 
 int eon_kzg_commit_quotient(eon_ctx* ctx, const uint64_t* h_evals, unsigned log_size, size_t width, unsigned log_chunks,
@@ -871,13 +1004,9 @@ int eon_kzg_commit_quotient(eon_ctx* ctx, const uint64_t* h_evals, unsigned log_
   if (!ctx) return EON_ERR_BAD_ARG;
   Lock lk(ctx);
   EON_TRY(set_device(ctx));
-  EON_TRY(check_dims(ctx, log_size, width));
-  const size_t b = mat_bytes(log_size, width);
-  if (b && !h_evals) return fail(ctx, EON_ERR_BAD_ARG, "null evals");
-  void* d_in = nullptr;
-  EON_TRY(scratch_get(ctx, SC_IO_A, b + 32, &d_in));
-  if (b) EON_CUDA(ctx, cudaMemcpyAsync(d_in, h_evals, b, cudaMemcpyHostToDevice, ctx->stream));
-  return kzg_commit_quotient_locked(ctx, (const Fr*)d_in, log_size, width, log_chunks, shift, h_commit_xy, out_handles);
+  if (log_chunks > 16) return fail(ctx, EON_ERR_BAD_ARG, "too many quotient chunks");
+  return kzg_commit_quotient_host(ctx, h_evals, log_size, width, log_chunks, 0, (size_t)1 << log_chunks, shift,
+                                  h_commit_xy, out_handles);
 }
 
 static int find_handle(eon_ctx* ctx, eon_handle h, ProverMatrix* pm) {
@@ -935,11 +1064,17 @@ static int evals_on_coset_locked(eon_ctx* ctx, eon_handle h, unsigned log_size, 
   EON_TRY(check_shift(ctx, shift, &s));
   if (pm.log_h == NOT_POW2)
     return fail(ctx, EON_ERR_BAD_ARG, "prover data has a non-power-of-two height (KzgMmcs matrix): no coset evaluation");
-  if (log_size < pm.log_h)
-    return fail(ctx, EON_ERR_BAD_ARG, "evaluation domain smaller than the committed polynomial length");
   EON_TRY(check_dims(ctx, log_size, pm.width));
   if (pm.width == 0) return EON_OK;
   if (!d_out) return fail(ctx, EON_ERR_BAD_ARG, "null output");
+  if (log_size < pm.log_h) {
+    // a coset smaller than the polynomial (allowed by the Horner loop of kzg/src/pcs.rs:278-286): reduce the
+    // coefficients mod X^n - shift^n first, then the size-n coset NTT
+    void* folded = nullptr;
+    EON_TRY(scratch_get(ctx, SC_QUOT_AUX, mat_bytes(log_size, pm.width) + 32, &folded));
+    EON_TRY(fold_coeffs_run(ctx, pm.d_coeffs, pm.rows, pm.width, log_size, s, (Fr*)folded));
+    return ntt_forward(ctx, (const Fr*)folded, d_out, log_size, 0, pm.width, s, LAYOUT_NATURAL);
+  }
   return ntt_forward(ctx, pm.d_coeffs, d_out, log_size, log_size - pm.log_h, pm.width, s, LAYOUT_NATURAL);
 }
 
@@ -951,22 +1086,25 @@ int eon_kzg_evals_on_coset_dev(eon_ctx* ctx, eon_handle h, unsigned log_size, co
   return evals_on_coset_locked(ctx, h, log_size, shift, (Fr*)d_out);
 }
 
-int eon_kzg_evals_on_coset(eon_ctx* ctx, eon_handle h, unsigned log_size, const uint64_t shift[4], uint64_t* h_out) {
-  if (!ctx) return EON_ERR_BAD_ARG;
-  Lock lk(ctx);
-  EON_TRY(set_device(ctx));
+static int evals_on_coset_host(eon_ctx* ctx, eon_handle h, unsigned log_size, const uint64_t shift[4], uint64_t* h_out,
+                               size_t h_ld_out) {
   ProverMatrix pm;
   EON_TRY(find_handle(ctx, h, &pm));
   if (log_size > 28) return fail(ctx, EON_ERR_TWO_ADICITY, "domain exceeds 2^28");
+  if (h_ld_out == 0) h_ld_out = pm.width;
+  if (h_ld_out < pm.width) return fail(ctx, EON_ERR_BAD_ARG, "row pitch < width");
+  const size_t hpitch = h_ld_out * sizeof(Fr);
   size_t b = mat_bytes(log_size, pm.width);
   void* d_out = nullptr;
   EON_TRY(scratch_get(ctx, SC_IO_B, b + 32, &d_out));
   auto groups = column_groups(pm.width, b, false);
+  const size_t w = pm.width, rows = (size_t)1 << log_size, pitch = w * sizeof(Fr);
   if (groups.size() == 1 || pm.log_h == NOT_POW2 || log_size < pm.log_h) {
     EON_TRY(evals_on_coset_locked(ctx, h, log_size, shift, (Fr*)d_out));
     if (b) {
       if (!h_out) return fail(ctx, EON_ERR_BAD_ARG, "null output");
-      EON_CUDA(ctx, cudaMemcpyAsync(h_out, d_out, b, cudaMemcpyDeviceToHost, ctx->stream));
+      if (h_ld_out == w) EON_CUDA(ctx, cudaMemcpyAsync(h_out, d_out, b, cudaMemcpyDeviceToHost, ctx->stream));
+      else EON_CUDA(ctx, cudaMemcpy2DAsync(h_out, hpitch, d_out, pitch, pitch, rows, cudaMemcpyDeviceToHost, ctx->stream));
     }
     EON_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return EON_OK;
@@ -977,7 +1115,6 @@ int eon_kzg_evals_on_coset(eon_ctx* ctx, eon_handle h, unsigned log_size, const 
   EON_TRY(check_dims(ctx, log_size, pm.width));
   if (!h_out) return fail(ctx, EON_ERR_BAD_ARG, "null output");
   EON_TRY(pipe_init(ctx));
-  const size_t w = pm.width, rows = (size_t)1 << log_size, pitch = w * sizeof(Fr);
   int rc = EON_OK;
   for (size_t g = 0; rc == EON_OK && g < groups.size(); g++) {
     const size_t c0 = groups[g].first, gw = groups[g].second;
@@ -986,7 +1123,7 @@ int eon_kzg_evals_on_coset(eon_ctx* ctx, eon_handle h, unsigned log_size, const 
     cudaError_t e = cudaEventRecord(ctx->ev_pipe[g], ctx->stream);
     if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_pipe[g], 0);
     if (e == cudaSuccess)
-      e = cudaMemcpy2DAsync((Fr*)h_out + c0, pitch, (const Fr*)d_out + c0, pitch, gw * sizeof(Fr), rows,
+      e = cudaMemcpy2DAsync((Fr*)h_out + c0, hpitch, (const Fr*)d_out + c0, pitch, gw * sizeof(Fr), rows,
                             cudaMemcpyDeviceToHost, ctx->copy_stream);
     if (e != cudaSuccess) rc = fail(ctx, EON_ERR_CUDA, std::string("group download failed: ") + cudaGetErrorString(e));
   }
@@ -994,6 +1131,21 @@ int eon_kzg_evals_on_coset(eon_ctx* ctx, eon_handle h, unsigned log_size, const 
   if (rc == EON_OK && (e1 != cudaSuccess || e2 != cudaSuccess))
     rc = fail(ctx, EON_ERR_CUDA, std::string("download failed: ") + cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
   return rc;
+}
+
+int eon_kzg_evals_on_coset(eon_ctx* ctx, eon_handle h, unsigned log_size, const uint64_t shift[4], uint64_t* h_out) {
+  if (!ctx) return EON_ERR_BAD_ARG;
+  Lock lk(ctx);
+  EON_TRY(set_device(ctx));
+  return evals_on_coset_host(ctx, h, log_size, shift, h_out, 0);
+}
+
+int eon_kzg_evals_on_coset_ld(eon_ctx* ctx, eon_handle h, unsigned log_size, const uint64_t shift[4], uint64_t* h_out,
+                              size_t ld_out) {
+  if (!ctx) return EON_ERR_BAD_ARG;
+  Lock lk(ctx);
+  EON_TRY(set_device(ctx));
+  return evals_on_coset_host(ctx, h, log_size, shift, h_out, ld_out);
 }
 
 int eon_quotient_and_eval_dev(eon_ctx* ctx, const uint64_t* d_coeffs, size_t h, size_t width, const uint64_t z[4],
@@ -1100,6 +1252,68 @@ int eon_kzg_open_batch(eon_ctx* ctx, size_t nmat, const eon_handle* handles, con
   EON_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return EON_OK;
 }
+
+}  // extern "C"
+
+namespace eon {
+int dft_host(eon_ctx* ctx, int kind, const uint64_t* h_in, size_t ld_in, uint64_t* h_out, size_t ld_out, unsigned log_h,
+             size_t width, unsigned added_bits, const uint64_t shift[4]) {
+  Lock lk(ctx);
+  return dft_host_locked(ctx, kind, h_in, ld_in, h_out, ld_out, log_h, width, added_bits, shift);
+}
+int kzg_commit_quotient_range_host(eon_ctx* ctx, const uint64_t* h_evals, unsigned log_size, size_t width,
+                                   unsigned log_chunks, size_t chunk_first, size_t chunk_count, const uint64_t shift[4],
+                                   uint64_t* h_commit_xy, eon_handle* out_handles) {
+  Lock lk(ctx);
+  EON_TRY(set_device(ctx));
+  if (log_chunks > 16) return fail(ctx, EON_ERR_BAD_ARG, "too many quotient chunks");
+  return kzg_commit_quotient_host(ctx, h_evals, log_size, width, log_chunks, chunk_first, chunk_count, shift, h_commit_xy,
+                                  out_handles);
+}
+int kzg_commit_coeffs_host_ld(eon_ctx* ctx, const uint64_t* h_coeffs, size_t ld, size_t rows, size_t width,
+                              uint64_t* h_commit_xy, eon_handle* out_handle) {
+  Lock lk(ctx);
+  EON_TRY(set_device(ctx));
+  return kzg_commit_coeffs_locked(ctx, h_coeffs, true, rows, width, h_commit_xy, out_handle, ld);
+}
+int msm_srs_range_host_partial(eon_ctx* ctx, const uint64_t* h_scalars_rows, size_t first, size_t n, size_t ncols,
+                               size_t ld, const G1Affine** d_partial) {
+  Lock lk(ctx);
+  EON_TRY(set_device(ctx));
+  if (first > ctx->srs_n || n > ctx->srs_n - first)
+    return fail(ctx, EON_ERR_SRS_TOO_SHORT, "DegreeTooLarge: polynomial longer than the SRS");
+  if (ld < ncols) return fail(ctx, EON_ERR_BAD_ARG, "ld < ncols");
+  if (n && ncols && !h_scalars_rows) return fail(ctx, EON_ERR_BAD_ARG, "null scalars");
+  void *d_sc = nullptr, *d_res = nullptr;
+  const size_t wb = ncols * sizeof(Fr);
+  EON_TRY(scratch_get(ctx, SC_IO_A, n * wb + 32, &d_sc));
+  EON_TRY(scratch_get(ctx, SC_MSM_RESULT, ncols * sizeof(G1Affine) + 64, &d_res));
+  if (n && ncols) {
+    if (ld == ncols) EON_CUDA(ctx, cudaMemcpyAsync(d_sc, h_scalars_rows, n * wb, cudaMemcpyHostToDevice, ctx->stream));
+    else EON_CUDA(ctx, cudaMemcpy2DAsync(d_sc, wb, h_scalars_rows, ld * sizeof(Fr), wb, n, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  EON_TRY(msm_run(ctx, ctx->d_srs + first, (const Fr*)d_sc, n, ncols, ncols, (G1Affine*)d_res));
+  *d_partial = (const G1Affine*)d_res;
+  return EON_OK;
+}
+int msm_srs_host_ld(eon_ctx* ctx, const uint64_t* h_scalars, size_t n, size_t ncols, size_t ld, uint64_t* h_out_xy) {
+  Lock lk(ctx);
+  EON_TRY(set_device(ctx));
+  if (n > ctx->srs_n) return fail(ctx, EON_ERR_SRS_TOO_SHORT, "DegreeTooLarge: polynomial longer than the SRS");
+  if (n && ncols && !h_scalars) return fail(ctx, EON_ERR_BAD_ARG, "null scalars");
+  if (ld < ncols) return fail(ctx, EON_ERR_BAD_ARG, "ld < ncols");
+  void* d_sc = nullptr;
+  const size_t wb = ncols * sizeof(Fr);
+  EON_TRY(scratch_get(ctx, SC_IO_A, n * wb + 32, &d_sc));
+  if (n && ncols) {
+    if (ld == ncols) EON_CUDA(ctx, cudaMemcpyAsync(d_sc, h_scalars, n * wb, cudaMemcpyHostToDevice, ctx->stream));
+    else EON_CUDA(ctx, cudaMemcpy2DAsync(d_sc, wb, h_scalars, ld * sizeof(Fr), wb, n, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  return msm_to_host(ctx, ctx->d_srs, (const Fr*)d_sc, n, ncols, ncols, h_out_xy);
+}
+}  // namespace eon
+
+extern "C" {
 
 // ---- measurement ---------------------------------------------------------------------------------
 int eon_bench_imad_peak(eon_ctx* ctx, int kind, double* out_tops) {

@@ -110,6 +110,11 @@ struct eon_ctx {
   // window tables tab[t][i] = 2^(c t) * srs[i] (t < ceil(256/c)), built once per SRS; null = none
   eon::G1Affine* d_srs_tab = nullptr;
   unsigned srs_tab_c = 0;
+  // a second table set over the SRS index range [rng_first, rng_first + rng_n) only, with a window sized for that
+  // range: the shard this GPU owns in an index-range sharded MSM (eon_srs_set_range_tables)
+  eon::G1Affine* d_rng_tab = nullptr;
+  size_t rng_first = 0, rng_n = 0;
+  unsigned rng_c = 0;
   // batched-affine pairwise rounds before the XYZZ finisher: -1 = automatic (msm_pick_rounds)
   int msm_rounds = -1;
   int msm_sort_mode = -1;        // -1 automatic, 0 one-pass atomic scatter, 1 two-pass coalesced sort
@@ -253,6 +258,9 @@ bool ntt_twiddles_are_fixed_operand();
 int msm_run(eon_ctx* ctx, const G1Affine* d_bases, const Fr* d_scalars, size_t n, size_t ncols, size_t ld,
             G1Affine* d_out);
 int g1_sum_run(eon_ctx* ctx, const G1Affine* d_points, size_t n, G1Affine* d_out);
+// d_out[c] = sum_p d_parts[p * ncols + c]
+int g1_sum_cols_run(eon_ctx* ctx, const G1Affine* d_parts, size_t nparts, size_t ncols, G1Affine* d_out);
+int srs_build_range_tables(eon_ctx* ctx, size_t first, size_t n, unsigned window_bits);
 int srs_generate(eon_ctx* ctx, const Fr& alpha, size_t n);
 int srs_build_tables(eon_ctx* ctx, unsigned window_bits);
 int srs_build_default_tables(eon_ctx* ctx);
@@ -262,6 +270,32 @@ int g1_decompress_run(eon_ctx* ctx, const uint8_t* h_in, size_t n, G1Affine* d_o
 
 int quotient_run(eon_ctx* ctx, const Fr* d_coeffs, size_t h, size_t width, size_t ld_out, const Fr& z, Fr* d_quot,
                  Fr* d_values);
+
+// d_out[i][c] = sum_j d_coeffs[i + j 2^log_n][c] * (shift^(2^log_n))^j, i < 2^log_n (2^log_n <= h)
+int fold_coeffs_run(eon_ctx* ctx, const Fr* d_coeffs, size_t h, size_t width, unsigned log_n, const Fr& shift,
+                    Fr* d_out);
+
+// ---- host-buffer entry points shared with the multi-device context (multi.cu); every one takes ctx->mu ----------
+enum DftKind { DFT_PLAIN = 0, DFT_COSET, DFT_INV, DFT_COSET_INV, DFT_COSET_LDE };
+// transform of the columns [0, width) of a host matrix with row pitch ld_in (ld_out for the result), 0 = dense
+int dft_host_locked(eon_ctx* ctx, int kind, const uint64_t* h_in, size_t ld_in, uint64_t* h_out, size_t ld_out,
+                    unsigned log_h, size_t width, unsigned added_bits, const uint64_t shift[4]);
+int dft_host(eon_ctx* ctx, int kind, const uint64_t* h_in, size_t ld_in, uint64_t* h_out, size_t ld_out, unsigned log_h,
+             size_t width, unsigned added_bits, const uint64_t shift[4]);
+// Pcs::commit_quotient of the chunk range [chunk_first, chunk_first + chunk_count) from the WHOLE host quotient matrix
+int kzg_commit_quotient_range_host(eon_ctx* ctx, const uint64_t* h_evals, unsigned log_size, size_t width,
+                                   unsigned log_chunks, size_t chunk_first, size_t chunk_count, const uint64_t shift[4],
+                                   uint64_t* h_commit_xy, eon_handle* out_handles);
+// KzgMmcs::commit of the columns [0, width) of a host coefficient matrix with row pitch ld (0 = dense)
+int kzg_commit_coeffs_host_ld(eon_ctx* ctx, const uint64_t* h_coeffs, size_t ld, size_t rows, size_t width,
+                              uint64_t* h_commit_xy, eon_handle* out_handle);
+// rows [first, first + n) of a host scalar matrix (row pitch ld, ncols used) against SRS[first, first + n): the
+// partial sums stay on the device (*d_partial: ncols affine points, valid until the next MSM on this context);
+// queued on ctx->stream, not synchronised
+int msm_srs_range_host_partial(eon_ctx* ctx, const uint64_t* h_scalars_rows, size_t first, size_t n, size_t ncols,
+                               size_t ld, const G1Affine** d_partial);
+// columns [0, ncols) of a host scalar matrix with row pitch ld over SRS[0, n) -> ncols affine points on the host
+int msm_srs_host_ld(eon_ctx* ctx, const uint64_t* h_scalars, size_t n, size_t ncols, size_t ld, uint64_t* h_out_xy);
 
 int bench_imad(eon_ctx* ctx, int kind, double* out_tops);
 int bench_modmul(eon_ctx* ctx, int field, int variant, double* out_gmuls);

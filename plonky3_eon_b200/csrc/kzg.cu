@@ -139,6 +139,36 @@ int quotient_run(eon_ctx* ctx, const Fr* d_coeffs, size_t h, size_t width, size_
   return EON_OK;
 }
 
+// ---- coefficient folding: p mod (X^n - m) ---------------------------------------------------------
+// get_evaluations_on_domain (kzg/src/pcs.rs:278-286) evaluates the committed polynomial by Horner on ANY coset,
+// including one smaller than the polynomial: on x = s*omega_n^k every x^n equals m = s^n, so
+//     p(x) = sum_{i<n} ( sum_j c[i + j n] m^j ) x^i
+// and the size-n coset NTT of the folded coefficients gives exactly the values the Horner loop gives.
+__global__ void __launch_bounds__(256)
+k_fold_coeffs(const Fr* __restrict__ coeffs, size_t h, size_t width, size_t n, Fr m, Fr* __restrict__ out) {
+  size_t g = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (g >= n * width) return;
+  size_t i = g / width, col = g % width;
+  size_t top = i + ((h - 1 - i) / n) * n;  // last row congruent to i (h > i because n <= h)
+  Fr acc = ld_fr(coeffs + top * width + col);
+  for (size_t j = top; j >= n + i; ) {
+    j -= n;
+    acc = fp_add(fp_mul(acc, m), ld_fr(coeffs + j * width + col));
+  }
+  st_fr(out + g, acc);
+}
+
+int fold_coeffs_run(eon_ctx* ctx, const Fr* d_coeffs, size_t h, size_t width, unsigned log_n, const Fr& shift,
+                    Fr* d_out) {
+  if (width == 0 || h == 0) return EON_OK;
+  const size_t n = (size_t)1 << log_n;
+  Fr m = shift;
+  for (unsigned i = 0; i < log_n; i++) m = fp_sqr(m);  // shift^n
+  k_fold_coeffs<<<(unsigned)((n * width + 255) / 256), 256, 0, ctx->stream>>>(d_coeffs, h, width, n, m, d_out);
+  EON_LAUNCHED(ctx);
+  return EON_OK;
+}
+
 // ---- integer-pipe microbenchmarks (roofline denominators) ----------------------------------------
 template <int KIND>
 __global__ void __launch_bounds__(256) k_imad_peak(u32* out, u32 iters, u32 seed) {

@@ -404,6 +404,22 @@ __global__ void k_g1_sum(const G1Affine* __restrict__ pts, size_t n, G1Affine* _
   }
 }
 
+// out[c] = sum_p pts[p * ncols + c]: the per-GPU partial sums of an index-range sharded MSM, all columns in one launch
+__global__ void k_g1_sum_cols(const G1Affine* __restrict__ pts, size_t nparts, size_t ncols, G1Affine* __restrict__ out) {
+  size_t c = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (c >= ncols) return;
+  G1Xyzz acc = G1Xyzz::identity();
+  for (size_t p = 0; p < nparts; p++) g1_add_mixed(acc, pts[p * ncols + c]);
+  out[c] = g1_to_affine(acc);
+}
+
+int g1_sum_cols_run(eon_ctx* ctx, const G1Affine* d_parts, size_t nparts, size_t ncols, G1Affine* d_out) {
+  if (ncols == 0) return EON_OK;
+  k_g1_sum_cols<<<(unsigned)((ncols + 31) / 32), 32, 0, ctx->stream>>>(d_parts, nparts, ncols, d_out);
+  EON_LAUNCHED(ctx);
+  return EON_OK;
+}
+
 int g1_sum_run(eon_ctx* ctx, const G1Affine* d_points, size_t n, G1Affine* d_out) {
   k_g1_sum<<<1, 32, 0, ctx->stream>>>(d_points, n, d_out);
   EON_LAUNCHED(ctx);
@@ -567,7 +583,17 @@ int msm_run(eon_ctx* ctx, const G1Affine* d_bases, const Fr* d_scalars, size_t n
   MsmShape sh = msm_shape_plain(n);
   const G1Affine* bases = d_bases;
   // bases inside the resident SRS and window tables available: all windows share one bucket set
-  if (ctx->d_srs_tab && d_bases >= ctx->d_srs && d_bases + n <= ctx->d_srs + ctx->srs_n) {
+  bool have_tables = false;
+  if (ctx->d_rng_tab && d_bases >= ctx->d_srs + ctx->rng_first && d_bases + n <= ctx->d_srs + ctx->rng_first + ctx->rng_n) {
+    // tables built for exactly this index range (the shard of a multi-GPU MSM): their window size fits the shard
+    MsmShape m = msm_shape_merged(n, ctx->rng_c, ctx->rng_n, (u64)(d_bases - (ctx->d_srs + ctx->rng_first)));
+    if ((u64)n * m.W >= 4ull * m.NB) {
+      sh = m;
+      bases = ctx->d_rng_tab;
+      have_tables = true;
+    }
+  }
+  if (!have_tables && ctx->d_srs_tab && d_bases >= ctx->d_srs && d_bases + n <= ctx->d_srs + ctx->srs_n) {
     MsmShape m = msm_shape_merged(n, ctx->srs_tab_c, ctx->srs_n, (u64)(d_bases - ctx->d_srs));
     if ((u64)n * m.W >= 4ull * m.NB) {  // enough entries per bucket for the larger window to pay off
       sh = m;
@@ -627,12 +653,8 @@ int srs_build_tables(eon_ctx* ctx, unsigned window_bits) {
   return EON_OK;
 }
 
-// default table policy after an SRS load (n >= 2^14 points, tables within 64 GiB): the c in [10, 20]
-// that minimises  n * W(c) mixed additions (10 modmul)  +  2^(c-1) bucket-reduction steps (~60 modmul
-// with the chunk offsets); 2^20 points -> c = 17 (15 windows).  Otherwise plain per-window buckets.
-int srs_build_default_tables(eon_ctx* ctx) {
-  const size_t n = ctx->srs_n;
-  if (n < ((size_t)1 << 14)) return srs_build_tables(ctx, 0);
+// cost model shared by the table policies: n * W(c) mixed additions (10 modmul) + 2^(c-1) bucket-reduction steps
+static u32 msm_best_window(size_t n) {
   u32 best_c = 0;
   double best = 0;
   for (u32 c = 10; c <= 20; c++) {
@@ -642,6 +664,41 @@ int srs_build_default_tables(eon_ctx* ctx) {
       best = cost;
     }
   }
+  return best_c;
+}
+
+// Window tables for the SRS index range [first, first + n) only: the shard one GPU owns in an index-range sharded
+// MSM.  window_bits 0 = chosen for n points by the cost model; n = 0 drops them.
+int srs_build_range_tables(eon_ctx* ctx, size_t first, size_t n, unsigned window_bits) {
+  if (ctx->d_rng_tab) {
+    EON_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    EON_CUDA(ctx, cudaFree(ctx->d_rng_tab));
+    ctx->d_rng_tab = nullptr;
+    ctx->rng_first = ctx->rng_n = 0;
+    ctx->rng_c = 0;
+  }
+  if (n == 0) return EON_OK;
+  if (first > ctx->srs_n || n > ctx->srs_n - first) return fail(ctx, EON_ERR_BAD_ARG, "SRS range out of bounds");
+  if (window_bits == 0) window_bits = msm_best_window(n);
+  if (window_bits < 8 || window_bits > 20) return fail(ctx, EON_ERR_BAD_ARG, "window bits must be in [8, 20]");
+  const u32 c = window_bits, W = msm_windows(c);
+  if ((u64)W * n >= 0x7fffffffull) return fail(ctx, EON_ERR_BAD_ARG, "range too large for window tables");
+  EON_CUDA(ctx, cudaMalloc(&ctx->d_rng_tab, (size_t)W * n * sizeof(G1Affine)));
+  k_srs_tables<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(ctx->d_srs + first, n, c, W, ctx->d_rng_tab);
+  EON_LAUNCHED(ctx);
+  ctx->rng_first = first;
+  ctx->rng_n = n;
+  ctx->rng_c = c;
+  return EON_OK;
+}
+
+// default table policy after an SRS load (n >= 2^14 points, tables within 64 GiB): the c in [10, 20]
+// that minimises  n * W(c) mixed additions (10 modmul)  +  2^(c-1) bucket-reduction steps (~60 modmul
+// with the chunk offsets); 2^20 points -> c = 17 (15 windows).  Otherwise plain per-window buckets.
+int srs_build_default_tables(eon_ctx* ctx) {
+  const size_t n = ctx->srs_n;
+  if (n < ((size_t)1 << 14)) return srs_build_tables(ctx, 0);
+  const u32 best_c = msm_best_window(n);
   u32 W = msm_windows(best_c);
   if ((size_t)W * n * sizeof(G1Affine) > ((size_t)64 << 30)) return srs_build_tables(ctx, 0);
   return srs_build_tables(ctx, best_c);
@@ -665,6 +722,7 @@ int srs_generate(eon_ctx* ctx, const Fr& alpha, size_t n) {
     ctx->d_srs = nullptr;
     ctx->srs_n = 0;
     EON_TRY(srs_build_tables(ctx, 0));
+    EON_TRY(srs_build_range_tables(ctx, 0, 0, 0));
   }
   if (n == 0) return EON_OK;
   EON_CUDA(ctx, cudaMalloc(&ctx->d_srs, n * sizeof(G1Affine)));

@@ -84,6 +84,45 @@ _SIGS = {
     "eon_handle_dims": (C.c_int, [C.c_void_p, C.c_uint64, C.POINTER(C.c_uint), C.POINTER(C.c_size_t)]),
     "eon_handle_free": (C.c_int, [C.c_void_p, C.c_uint64]),
     "eon_quotient_and_eval_dev": (C.c_int, [C.c_void_p, _u64p, C.c_size_t, C.c_size_t, _u64p, _u64p, _u64p]),
+    "eon_coset_lde_batch_ld": (C.c_int, [C.c_void_p, _u64p, C.c_size_t, _u64p, C.c_size_t, C.c_uint, C.c_size_t, C.c_uint,
+                                         _u64p]),
+    "eon_kzg_commit_ld": (C.c_int, [C.c_void_p, _u64p, C.c_size_t, C.c_uint, C.c_size_t, _u64p, _u64p,
+                                    C.POINTER(C.c_uint64)]),
+    "eon_kzg_commit_lde_ld": (C.c_int, [C.c_void_p, _u64p, C.c_size_t, C.c_uint, C.c_size_t, _u64p, _u64p,
+                                        C.POINTER(C.c_uint64), C.c_uint, _u64p, _u64p, C.c_size_t]),
+    "eon_kzg_evals_on_coset_ld": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint, _u64p, _u64p, C.c_size_t]),
+    "eon_msm_srs_range_partial_dev": (C.c_int, [C.c_void_p, _u64p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t, _u64p]),
+    "eon_g1_sum_cols_dev": (C.c_int, [C.c_void_p, _u64p, C.c_size_t, C.c_size_t, _u64p]),
+    "eon_srs_set_range_tables": (C.c_int, [C.c_void_p, C.c_size_t, C.c_size_t, C.c_uint]),
+    # multi-device context (one process, several GPUs): same argument lists as the eon_* forms
+    "eon_mctx_create": (C.c_int, [C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_void_p)]),
+    "eon_mctx_destroy": (None, [C.c_void_p]),
+    "eon_mctx_last_error": (C.c_char_p, [C.c_void_p]),
+    "eon_mctx_device_count": (C.c_int, [C.c_void_p]),
+    "eon_mctx_ctx": (C.c_void_p, [C.c_void_p, C.c_int]),
+    "eon_mctx_launch_count": (C.c_uint64, [C.c_void_p]),
+    "eon_mctx_srs_generate_unsafe": (C.c_int, [C.c_void_p, _u64p, C.c_size_t]),
+    "eon_mctx_srs_load_affine": (C.c_int, [C.c_void_p, _u64p, C.c_size_t]),
+    "eon_mctx_srs_load_compressed": (C.c_int, [C.c_void_p, _u64p, C.c_size_t, C.c_int, C.POINTER(C.c_size_t)]),
+    "eon_mctx_srs_size": (C.c_size_t, [C.c_void_p]),
+    "eon_mctx_srs_read": (C.c_int, [C.c_void_p, C.c_size_t, C.c_size_t, _u64p]),
+    "eon_mctx_dft_batch": (C.c_int, [C.c_void_p, _u64p, _u64p, C.c_uint, C.c_size_t]),
+    "eon_mctx_coset_dft_batch": (C.c_int, [C.c_void_p, _u64p, _u64p, C.c_uint, C.c_size_t, _u64p]),
+    "eon_mctx_idft_batch": (C.c_int, [C.c_void_p, _u64p, _u64p, C.c_uint, C.c_size_t]),
+    "eon_mctx_coset_idft_batch": (C.c_int, [C.c_void_p, _u64p, _u64p, C.c_uint, C.c_size_t, _u64p]),
+    "eon_mctx_coset_lde_batch": (C.c_int, [C.c_void_p, _u64p, _u64p, C.c_uint, C.c_size_t, C.c_uint, _u64p]),
+    "eon_mctx_kzg_commit": (C.c_int, [C.c_void_p, _u64p, C.c_uint, C.c_size_t, _u64p, _u64p, C.POINTER(C.c_uint64)]),
+    "eon_mctx_kzg_commit_lde": (C.c_int, [C.c_void_p, _u64p, C.c_uint, C.c_size_t, _u64p, _u64p, C.POINTER(C.c_uint64),
+                                          C.c_uint, _u64p, _u64p]),
+    "eon_mctx_kzg_commit_coeffs": (C.c_int, [C.c_void_p, _u64p, C.c_size_t, C.c_size_t, _u64p, C.POINTER(C.c_uint64)]),
+    "eon_mctx_kzg_commit_quotient": (C.c_int, [C.c_void_p, _u64p, C.c_uint, C.c_size_t, C.c_uint, _u64p, _u64p, _u64p]),
+    "eon_mctx_kzg_evals_on_coset": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint, _u64p, _u64p]),
+    "eon_mctx_kzg_open_batch": (C.c_int, [C.c_void_p, C.c_size_t, _u64p, _u64p, _u64p, _u64p, _u64p]),
+    "eon_mctx_kzg_read_coeffs": (C.c_int, [C.c_void_p, C.c_uint64, _u64p]),
+    "eon_mctx_handle_dims": (C.c_int, [C.c_void_p, C.c_uint64, C.POINTER(C.c_uint), C.POINTER(C.c_size_t)]),
+    "eon_mctx_handle_free": (C.c_int, [C.c_void_p, C.c_uint64]),
+    "eon_mctx_msm_srs": (C.c_int, [C.c_void_p, _u64p, C.c_size_t, C.c_size_t, C.c_size_t, _u64p]),
+    "eon_mctx_msm_points": (C.c_int, [C.c_void_p, _u64p, _u64p, C.c_size_t, _u64p]),
     "eon_bench_imad_peak": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_double)]),
     "eon_bench_modmul": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_double)]),
     "eon_bench_modmul_variant": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_double)]),
@@ -306,6 +345,110 @@ class Context:
         v = C.c_double()
         self.call("eon_bench_modmul_variant", field, variant, C.byref(v))
         return float(v.value)
+
+
+class _ShardContext(Context):
+    """Non-owning view of one device context of a MultiContext (tuning / timing calls)."""
+
+    def __init__(self, lib, handle, device):  # noqa: D401 - no eon_ctx_create here
+        self.lib = lib
+        self.h = C.c_void_p(handle)
+        self.device = device
+
+    def close(self):
+        self.h = C.c_void_p()
+
+
+class MultiContext:
+    """One eon_mctx: several GPUs behind the whole-matrix calls of one process (include/eon_kzg.h).  Quacks like
+    Context for the host mirrors (GpuDft, GpuKzgPcs, KzgMmcs): `call("eon_X", ...)` goes to `eon_mctx_X` when that
+    exists; calls without per-device state (point compression, sums) go to the first device."""
+
+    _FIRST_DEVICE = {"eon_g1_compress", "eon_g1_decompress", "eon_g1_sum", "eon_bench_imad_peak",
+                     "eon_bench_modmul", "eon_bench_modmul_variant"}
+
+    def __init__(self, devices):
+        self.lib = load()
+        devs = (C.c_int * len(devices))(*[int(d) for d in devices])
+        h = C.c_void_p()
+        rc = self.lib.eon_mctx_create(devs, len(devices), C.byref(h))
+        if rc != EON_OK or not h.value:
+            raise EonError(rc, "eon_mctx_create failed: no usable sm_100 CUDA device (there is no CPU fallback)")
+        self.h = h
+        self.devices = list(devices)
+        self.device = devices[0]
+
+    def close(self):
+        if getattr(self, "h", None) is not None and self.h.value:
+            self.lib.eon_mctx_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def shard(self, i):
+        p = self.lib.eon_mctx_ctx(self.h, int(i))
+        if not p:
+            raise IndexError(i)
+        return _ShardContext(self.lib, p, self.devices[i])
+
+    def _raise(self, rc, msg):
+        if rc == EON_ERR_SRS_TOO_SHORT:
+            raise DegreeTooLarge(rc, msg)
+        if rc == EON_ERR_BAD_POINT:
+            raise InvalidG1Point(rc, msg)
+        raise EonError(rc, msg)
+
+    def call(self, name, *args):
+        conv = []
+        for a in args:
+            if isinstance(a, np.ndarray):
+                assert a.flags["C_CONTIGUOUS"], "buffer must be C-contiguous"
+                conv.append(C.c_void_p(a.ctypes.data))
+            else:
+                conv.append(a)
+        mname = "eon_mctx_" + name[4:]
+        if mname in _SIGS:
+            rc = getattr(self.lib, mname)(self.h, *conv)
+            if rc != EON_OK:
+                self._raise(rc, self.lib.eon_mctx_last_error(self.h).decode())
+            return
+        if name == "eon_kzg_open":  # one matrix = a batch of one
+            handle, pts, npoints, vals, wits = conv
+            hs = np.array([handle.value if hasattr(handle, "value") else int(handle)], dtype=np.uint64)
+            npts = np.array([int(npoints)], dtype=np.uint64)
+            return self.call("eon_kzg_open_batch", 1, hs, npts, pts, vals, wits)
+        if name in self._FIRST_DEVICE:
+            return self.shard(0).call(name, *args)
+        raise EonError(EON_ERR_BAD_ARG, f"{name} has no multi-device form (use MultiContext.shard(i))")
+
+    def sync(self):
+        for i in range(len(self.devices)):
+            self.shard(i).sync()
+
+    def launch_count(self):
+        return int(self.lib.eon_mctx_launch_count(self.h))
+
+    def srs_size(self):
+        return int(self.lib.eon_mctx_srs_size(self.h))
+
+    def g1_to_bytes(self, points_wire, enc=G1_ENC_HALO2):
+        return self.shard(0).g1_to_bytes(points_wire, enc)
+
+    def g1_from_bytes(self, data, enc=G1_ENC_HALO2):
+        return self.shard(0).g1_from_bytes(data, enc)
+
+    def srs_load_compressed(self, data, enc=G1_ENC_HALO2):
+        b = np.ascontiguousarray(data, dtype=np.uint8).reshape(-1, 32)
+        bad = C.c_size_t(0)
+        try:
+            self.call("eon_srs_load_compressed", b, b.shape[0], int(enc), C.byref(bad))
+        except InvalidG1Point as e:
+            e.index = int(bad.value)
+            raise
 
 
 _default_ctx = {}

@@ -8,13 +8,14 @@ open_batch  row `index` (scaled to each matrix's height, mmcs.rs:192-237): value
 verify_batch (pairings, mmcs.rs:243-295) stays on the CPU side, like KzgPcs::verify.
 """
 import ctypes as C
+import weakref
 from dataclasses import dataclass, field as dc_field
 
 import numpy as np
 
 from . import field
 from .lib import default_context
-from .pcs import _as_matrix, _shift_wire
+from .pcs import _as_matrix, _shift_wire, release_handle
 
 
 @dataclass
@@ -25,7 +26,14 @@ class KzgMmcsProverData:
     handles: list
     _ctx: object = dc_field(default=None, repr=False)
 
+    def __post_init__(self):
+        # dropped like the reference's ProverData: the device buffers go back when this object is collected
+        self._fins = [weakref.finalize(self, release_handle, self._ctx, h) for h in self.handles if h and self._ctx]
+
     def free(self):
+        for f in self._fins:
+            f.detach()
+        self._fins = []
         for h in self.handles:
             if h:
                 self._ctx.call("eon_handle_free", C.c_uint64(h))

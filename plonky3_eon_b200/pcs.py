@@ -14,6 +14,7 @@ Prover-side failures raise (the reference panics): AssertionError for a height/d
 (pcs.rs:233-237), DegreeTooLarge for a short SRS (pcs.rs:238-240).
 """
 import ctypes as C
+import weakref
 from dataclasses import dataclass, field as dc_field
 
 import numpy as np
@@ -65,6 +66,15 @@ class TwoAdicMultiplicativeCoset:
         return [np.ascontiguousarray(a[i::num_chunks]) for i in range(num_chunks)]
 
 
+def release_handle(ctx, handle):
+    """Finalizer of the prover-data classes: give a device coefficient buffer back, unless its context is gone."""
+    try:
+        if handle and getattr(ctx, "h", None) is not None and ctx.h.value:
+            ctx.call("eon_handle_free", C.c_uint64(handle))
+    except Exception:
+        pass
+
+
 @dataclass
 class MatrixProverData:
     """kzg/src/pcs.rs:52-61 — evals stay on the host (the prover reads them back for the
@@ -76,6 +86,11 @@ class MatrixProverData:
     # (log_size, shift, evaluations) produced ahead of time by commit() under an LDE hint
     lde: tuple = dc_field(default=None, repr=False)
 
+    def __post_init__(self):
+        # the reference's ProverData is dropped with its scope; here the coefficients live in HBM behind `handle`,
+        # so the handle goes back to the context when this object is collected (free() is the eager path)
+        self._fin = weakref.finalize(self, release_handle, self._ctx, self.handle) if self.handle and self._ctx else None
+
     def coeffs(self):
         h, w = self.evals.shape[0], self.evals.shape[1]
         out = np.empty((h, w, 4), dtype=np.uint64)
@@ -84,6 +99,8 @@ class MatrixProverData:
 
     def free(self):
         if self.handle:
+            if self._fin is not None:
+                self._fin.detach()
             self._ctx.call("eon_handle_free", C.c_uint64(self.handle))
             self.handle = 0
 

@@ -219,6 +219,27 @@ def test_golden_fixture(ctx):
     assert np.array_equal(commit2[0], g["kzg_commit_shifted"])
 
 
+@pytest.mark.parametrize("log_h,w,log_small", [(3, 2, 0), (3, 2, 2), (6, 3, 4), (10, 16, 7), (11, 5, 8)])
+def test_evaluations_on_a_domain_smaller_than_the_polynomial(ctx, log_h, w, log_small):
+    """get_evaluations_on_domain is a Horner loop over ANY coset (kzg/src/pcs.rs:278-286), also one with fewer
+    points than the committed polynomial has coefficients; here: fold mod X^n - s^n, then a size-n coset NTT."""
+    from plonky3_eon_b200 import TwoAdicMultiplicativeCoset
+    h = 1 << log_h
+    pcs = pcs_new(ctx, h - 1, 12345)
+    rng = np.random.default_rng(1000 + log_h * 31 + log_small)
+    evw = fr.random_wire(rng, h * w).reshape(h, w, 4)
+    dom = TwoAdicMultiplicativeCoset(1, log_h)
+    _, pdata = pcs.commit([(dom, evw)])
+    coeffs = odft.mat_from_wire(pdata[0].coeffs())
+    for shift in (1, fr.GENERATOR, 0x1234567890ABCDEF % P):
+        small = TwoAdicMultiplicativeCoset(shift, log_small)
+        got = pcs.get_evaluations_on_domain(pdata, 0, small)
+        assert got.shape == (1 << log_small, w, 4)
+        want = okzg.get_evaluations_on_domain({"coeffs": coeffs, "domain": None, "evals": None}, (shift, log_small))
+        assert odft.mat_from_wire(got) == want
+    pdata[0].free()
+
+
 @pytest.mark.parametrize("log_h,w", [(0, 2), (1, 1), (3, 3), (6, 4)])
 def test_commit_open_vs_oracle(ctx, log_h, w):
     # heights 1 and 8 are the reference's end-to-end shapes (eon-uni-stark/tests/fib_air.rs:127-131)
