@@ -158,6 +158,8 @@ int eon_msm_set_sort_mode(eon_ctx* ctx, int mode);
 int eon_msm_set_slice_schedule(eon_ctx* ctx, int mode);
 /* rounds the most recent MSM on this context actually used */
 unsigned eon_msm_rounds_used(const eon_ctx* ctx);
+/* window bits c of the most recent MSM on this context (whole-SRS tables, range tables or the plain per-window c) */
+unsigned eon_msm_window_bits_used(const eon_ctx* ctx);
 /* copy SRS points [first, first + n) back to the host as affine wire points */
 int eon_srs_read(eon_ctx* ctx, size_t first, size_t n, uint64_t* h_xy);
 

@@ -417,6 +417,7 @@ int eon_msm_set_slice_schedule(eon_ctx* ctx, int mode) {
 }
 
 unsigned eon_msm_rounds_used(const eon_ctx* ctx) { return ctx ? ctx->msm_rounds_used : 0; }
+unsigned eon_msm_window_bits_used(const eon_ctx* ctx) { return ctx ? ctx->msm_c_used : 0; }
 
 int eon_msm_set_rounds(eon_ctx* ctx, int rounds) {
   if (!ctx || rounds < -1 || rounds > 6) return EON_ERR_BAD_ARG;

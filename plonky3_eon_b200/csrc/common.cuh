@@ -120,6 +120,7 @@ struct eon_ctx {
   int msm_sort_mode = -1;        // -1 automatic, 0 one-pass atomic scatter, 1 two-pass coalesced sort
   int msm_slice_mode = -1;       // round 0 of the pairwise rounds by table slice: -1 automatic, 0 off, 1 on
   unsigned msm_rounds_used = 0;  // rounds of the most recent MSM (reporting)
+  unsigned msm_c_used = 0;       // window bits of the most recent MSM (reporting)
 
   // second stream + events: the host-buffer entry points move column groups over PCIe while the
   // previous group computes (created on first use)

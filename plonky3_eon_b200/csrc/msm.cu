@@ -602,6 +602,7 @@ int msm_run(eon_ctx* ctx, const G1Affine* d_bases, const Fr* d_scalars, size_t n
   }
   msm_set_rounds(sh, n, msm_pick_rounds(ctx, n, sh));
   ctx->msm_rounds_used = sh.rounds;
+  ctx->msm_c_used = sh.c;
   // column batches: bound the sort + pairwise-round workspace (entries 4 B, round outputs 32 + 16 B,
   // level products ~5 B, prefix products 16 B per entry slot)
   size_t per_slot = 4 + (sh.rounds ? 32 + 16 + 5 + 16 : 0);

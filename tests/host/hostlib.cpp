@@ -9,7 +9,8 @@ template <class F> static F ld(const uint32_t* p) { F x; memcpy(x.v, p, 32); ret
 template <class F> static void st(uint32_t* p, const F& x) { memcpy(p, x.v, 32); }
 
 extern "C" {
-// which: 0 = Fr, 1 = Fq.  op: 0 mul, 1 add, 2 sub, 3 neg, 4 inv, 5 from_mont, 6 to_mont, 7 sqr
+// which: 0 = Fr, 1 = Fq.  op: 0 mul, 1 add, 2 sub, 3 neg, 4 inv (binary GCD), 5 from_mont, 6 to_mont, 7 sqr,
+// 8 inv by Fermat (cross-check)
 void host_fp_op(int which, int op, const uint32_t* a, const uint32_t* b, uint32_t* r, int n) {
   for (int i = 0; i < n; i++, a += 8, b += 8, r += 8) {
     if (which == 0) {
@@ -22,6 +23,7 @@ void host_fp_op(int which, int op, const uint32_t* a, const uint32_t* b, uint32_
         case 4: z = fp_inv(x); break;
         case 5: fp_from_mont(z.v, x); break;
         case 6: z = fp_to_mont<FrParams>(x.v); break;
+        case 8: z = fp_inv_fermat(x); break;
         default: z = fp_sqr(x);
       }
       st(r, z);
@@ -35,6 +37,7 @@ void host_fp_op(int which, int op, const uint32_t* a, const uint32_t* b, uint32_
         case 4: z = fp_inv(x); break;
         case 5: fp_from_mont(z.v, x); break;
         case 6: z = fp_to_mont<FqParams>(x.v); break;
+        case 8: z = fp_inv_fermat(x); break;
         default: z = fp_sqr(x);
       }
       st(r, z);

@@ -77,6 +77,26 @@ def test_field_ops(lib, which, mod):
         assert to_int(r[i]) * x * Rinv % mod == ((1 << 256) % mod if x else 0)
 
 
+@pytest.mark.parametrize("which,mod", [(0, fr.P), (1, g1.Q)])
+def test_binary_gcd_inverse(lib, which, mod):
+    """fp_inv (binary extended Euclid, csrc/fp.cuh) against pow(x, -1, p) and against the Fermat chain it replaced:
+    edge values, powers of two (long runs of halvings), values next to the modulus and random elements."""
+    rng = np.random.default_rng(2024 + which)
+    R = (1 << 256) % mod
+    vals = EDGE(mod) + [1 << k for k in range(0, 254, 7)] + [mod - (1 << k) for k in range(0, 250, 11)]
+    vals += [(1 << k) - 1 for k in (2, 31, 32, 33, 64, 127, 128, 200, 253)] + [3, 5, mod // 3, R, (R * R) % mod]
+    a = np.concatenate([np.array([from_int(v % mod) for v in vals]), rand_mont(rng, mod, 3000)])
+    n = len(a)
+    r, f = np.zeros_like(a), np.zeros_like(a)
+    lib.host_fp_op(which, 4, _ptr(a), _ptr(a), _ptr(r), n)
+    lib.host_fp_op(which, 8, _ptr(a[:64]), _ptr(a[:64]), _ptr(f[:64]), 64)
+    assert np.array_equal(r[:64], f[:64])
+    for i in range(n):
+        x = to_int(a[i])                       # Montgomery form of x / R
+        want = pow(x, -1, mod) * R * R % mod if x else 0
+        assert to_int(r[i]) == want, (which, i, hex(x))
+
+
 def test_fr_mul_matches_reference_limb_algorithm(lib):
     rng = np.random.default_rng(5)
     a = fr.random_wire(rng, 64)
