@@ -39,6 +39,7 @@ IMAD_PER_MODMUL = 272  # 136 32-bit limb MACs, lo + hi
 MODMUL_PER_MIXED_ADD = 10
 DTYPE = "u256 (8x32-bit Montgomery limbs, BN254 Fr/Fq)"
 P_TOP = 0x30644e72e131a029  # top 64-bit limb of the Fr modulus
+MSM_WINDOW_BITS = -1        # msm workload: forced window bits of the (shard) tables, -1 = the library's cost model
 
 
 def shared_config(args):
@@ -265,9 +266,18 @@ class Harness:
         torch.cuda.set_device(self.local)
         self.dev = torch.device("cuda", self.local)
         self.cpus = bind_to_gpu_numa_node(self.local) if self.world > 1 else None
+        self.host_group = None
         if self.world > 1:
             dist.init_process_group("nccl", device_id=self.dev)
+            # a second, CPU-side group: ranks that only WAIT (while rank 0 drives every GPU through one eon_mctx) must
+            # not sit in an NCCL barrier, whose spinning kernel would time-slice their GPU with rank 0's work
+            self.host_group = dist.new_group(backend="gloo")
         self.stream = torch.cuda.current_stream()
+
+    def host_barrier(self):
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier(group=self.host_group)
 
     def barrier(self):
         self.torch.cuda.synchronize()
@@ -406,7 +416,9 @@ def msm_leg(H, ctx, log_n, cols, steps, warmup, C):
     ctx.call("eon_srs_generate_unsafe", field.to_wire(ALPHA), n)
     if world > 1:
         ctx.call("eon_srs_set_window_tables", 0)            # the whole-SRS tables are not needed: shard tables below
-        ctx.call("eon_srs_set_range_tables", first, cnt, 0)
+        ctx.call("eon_srs_set_range_tables", first, cnt, max(MSM_WINDOW_BITS, 0))
+    elif MSM_WINDOW_BITS >= 0:
+        ctx.call("eon_srs_set_window_tables", MSM_WINDOW_BITS)
     d_sc = synth_device(cnt, cols, 0, H.dev, seed=4242 + 7919 * rank)   # seed 42: bn254/benches/bench_curve.rs:40
     d_part = torch.zeros((cols, 8), dtype=torch.int64, device=H.dev)
     d_all = torch.zeros((world, cols, 8), dtype=torch.int64, device=H.dev)
@@ -726,7 +738,7 @@ def run_eon(args):
     # ---- one process, all N GPUs: the multi-device context (rank 0 alone; the others wait) --------------------------
     mctx_obj = None
     if not args.no_e2e and not args.no_mctx:
-        H.barrier()
+        H.host_barrier()
         if rank == 0:
             ndev = max(world, args.mctx_devices or 0) if world > 1 else (args.mctx_devices or 1)
             ndev = min(ndev, torch.cuda.device_count())
@@ -755,7 +767,7 @@ def run_eon(args):
                 m.close()
             except Exception as e:  # report, do not lose the main line
                 mctx_obj = {"error": str(e)[:300]}
-        H.barrier()
+        H.host_barrier()
 
     # ---- standalone MSM 2^24 (BASELINE configs[2], the metric's second half) ----------------------------------------
     msm_obj = None
@@ -863,6 +875,8 @@ def run_msm(args):
     if args.msm_rounds >= 0:
         ctx.call("eon_msm_set_rounds", args.msm_rounds)
     sampler = ClockSampler(H.local)
+    global MSM_WINDOW_BITS
+    MSM_WINDOW_BITS = args.window_bits
     if H.rank == 0:
         sampler.start()
     res, phases = msm_leg(H, ctx, args.log_n, args.msm_cols, args.steps, args.warmup, C)

@@ -3,6 +3,7 @@
 #include <stdlib.h>
 
 #include <algorithm>
+#include <functional>
 
 #include "common.cuh"
 
@@ -115,6 +116,7 @@ void eon_ctx_destroy(eon_ctx* ctx) {
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->copy_stream2) cudaStreamDestroy(ctx->copy_stream2);
   if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
+  if (ctx->prio_stream) cudaStreamDestroy(ctx->prio_stream);
   delete ctx;
 }
 
@@ -605,6 +607,39 @@ static int lde_on_aux(eon_ctx* ctx, const Fr* d_coeffs, Fr* d_lde, unsigned lde_
   return EON_OK;
 }
 
+// While an LDE transform shares the GPU with an MSM, the MSM runs on a HIGH-PRIORITY stream: its CTAs are scheduled
+// first, so the transform (normal priority, auxiliary stream) fills exactly the cycles the MSM leaves idle -- its
+// single-warp inversion trees and bucket reduction, its sort passes -- instead of delaying the MSM's wide kernels.
+// (A stream cannot be made lower than the caller's default-priority stream, hence the MSM moves up.)
+// EON_MSM_PRIO=0: everything on the caller's stream as before.
+static bool msm_prio_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("EON_MSM_PRIO");
+    v = e ? (atoi(e) != 0) : 1;
+  }
+  return v != 0;
+}
+// f() issues MSM work on ctx->stream; here that is the high-priority stream, ordered after what the caller's
+// stream has queued so far; ev_pipe[ev_slot] is recorded when the MSM work is done (the caller's stream is NOT made
+// to wait: see msm_prio_join).
+static int msm_on_prio(eon_ctx* ctx, int ev_slot, const std::function<int()>& f) {
+  EON_TRY(pipe_init(ctx));
+  EON_CUDA(ctx, cudaEventRecord(ctx->ev_pipe[ev_slot], ctx->stream));
+  EON_CUDA(ctx, cudaStreamWaitEvent(ctx->prio_stream, ctx->ev_pipe[ev_slot], 0));
+  cudaStream_t main_stream = ctx->stream;
+  ctx->stream = ctx->prio_stream;
+  int rc = f();
+  ctx->stream = main_stream;
+  EON_TRY(rc);
+  EON_CUDA(ctx, cudaEventRecord(ctx->ev_pipe[ev_slot], ctx->prio_stream));
+  return EON_OK;
+}
+static int msm_prio_join(eon_ctx* ctx, int ev_slot) {
+  EON_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_pipe[ev_slot], 0));
+  return EON_OK;
+}
+
 static int kzg_commit_locked(eon_ctx* ctx, const uint64_t* d_evals, unsigned log_h, size_t width,
                              const uint64_t shift[4], uint64_t* h_commit_xy, eon_handle* out_handle,
                              unsigned lde_log_size = 0, const uint64_t* lde_shift = nullptr, Fr* d_lde = nullptr) {
@@ -633,11 +668,21 @@ static int kzg_commit_locked(eon_ctx* ctx, const uint64_t* d_evals, unsigned log
   EON_TRY(coeff_buffer_get(ctx, mat_bytes(log_h, width) + 32, &d_coeffs, &cap));
   int rc = ntt_inverse(ctx, (const Fr*)d_evals, d_coeffs, log_h, width, s, LAYOUT_NATURAL);
   if (rc == EON_OK && want_lde) rc = lde_on_aux(ctx, d_coeffs, d_lde, lde_log_size, lde_log_size - log_h, width, ls, width, 19);
-  if (rc == EON_OK) rc = msm_to_host(ctx, ctx->d_srs, d_coeffs, h, width, width, h_commit_xy);
-  if (rc == EON_OK && want_lde)  // the call returns with the LDE complete as well
+  if (rc == EON_OK) {
+    if (want_lde && msm_prio_enabled()) {
+      rc = msm_on_prio(ctx, 18, [&] { return msm_to_host(ctx, ctx->d_srs, d_coeffs, h, width, width, h_commit_xy); });
+      if (rc == EON_OK) rc = msm_prio_join(ctx, 18);
+    } else {
+      rc = msm_to_host(ctx, ctx->d_srs, d_coeffs, h, width, width, h_commit_xy);
+    }
+  }
+  if (rc == EON_OK && want_lde) {  // the call returns with the LDE complete as well, and later work on the caller's
+    // stream is ordered after it
     if (cudaStreamSynchronize(ctx->aux_stream) != cudaSuccess) rc = fail(ctx, EON_ERR_CUDA, "LDE stream failed");
+  }
   if (rc != EON_OK) {
     if (ctx->aux_stream) cudaStreamSynchronize(ctx->aux_stream);
+    if (ctx->prio_stream) cudaStreamSynchronize(ctx->prio_stream);
     cudaFree(d_coeffs);
     return rc;
   }
@@ -743,10 +788,15 @@ static std::vector<std::pair<size_t, size_t>> column_groups(size_t width, size_t
 }
 
 static int pipe_init(eon_ctx* ctx) {
-  if (ctx->copy_stream && ctx->copy_stream2 && ctx->aux_stream && ctx->ev_pipe[19]) return EON_OK;
+  if (ctx->copy_stream && ctx->copy_stream2 && ctx->aux_stream && ctx->prio_stream && ctx->ev_pipe[19]) return EON_OK;
   if (!ctx->copy_stream) EON_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
   if (!ctx->copy_stream2) EON_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream2, cudaStreamNonBlocking));
   if (!ctx->aux_stream) EON_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking));
+  if (!ctx->prio_stream) {
+    int least = 0, greatest = 0;
+    EON_CUDA(ctx, cudaDeviceGetStreamPriorityRange(&least, &greatest));
+    EON_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->prio_stream, cudaStreamNonBlocking, greatest));
+  }
   for (auto& e : ctx->ev_pipe)
     if (!e) EON_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   return EON_OK;
@@ -836,8 +886,16 @@ static int kzg_commit_host(eon_ctx* ctx, const uint64_t* h_evals, size_t h_ld_in
         if (e != cudaSuccess) rc = fail(ctx, EON_ERR_CUDA, std::string("LDE download failed: ") + cudaGetErrorString(e));
       }
     }
-    if (rc == EON_OK) rc = msm_run(ctx, ctx->d_srs, d_coeffs + c0, h, gw, width, (G1Affine*)d_commit + c0);
+    if (rc == EON_OK) {
+      if (want_lde && msm_prio_enabled()) {
+        // (MSMs of successive groups stay in order on the one high-priority stream: they share the MSM workspace)
+        rc = msm_on_prio(ctx, 16, [&] { return msm_run(ctx, ctx->d_srs, d_coeffs + c0, h, gw, width, (G1Affine*)d_commit + c0); });
+      } else {
+        rc = msm_run(ctx, ctx->d_srs, d_coeffs + c0, h, gw, width, (G1Affine*)d_commit + c0);
+      }
+    }
   }
+  if (rc == EON_OK && want_lde && msm_prio_enabled()) rc = msm_prio_join(ctx, 16);
   if (rc == EON_OK) {
     cudaError_t e = cudaMemcpyAsync(h_commit_xy, d_commit, width * sizeof(G1Affine), cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
@@ -848,6 +906,7 @@ static int kzg_commit_host(eon_ctx* ctx, const uint64_t* h_evals, size_t h_ld_in
     cudaStreamSynchronize(ctx->copy_stream);
     if (ctx->aux_stream) cudaStreamSynchronize(ctx->aux_stream);
     cudaStreamSynchronize(ctx->copy_stream2);
+    if (ctx->prio_stream) cudaStreamSynchronize(ctx->prio_stream);
     cudaStreamSynchronize(ctx->stream);
     cudaFree(d_coeffs);
     return rc;

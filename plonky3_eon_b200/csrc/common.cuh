@@ -128,6 +128,7 @@ struct eon_ctx {
   cudaStream_t copy_stream2 = nullptr;
   cudaStream_t aux_stream = nullptr;    // second compute stream: the hinted LDE runs beside the MSM, whose
                                         // sort / gather phases leave the integer pipe idle  // opposite PCIe direction (downloads while uploads are in flight)
+  cudaStream_t prio_stream = nullptr;   // high-priority compute stream: the MSM while an LDE transform runs beside it
   cudaEvent_t ev_pipe[20] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
                              nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 
@@ -179,8 +180,9 @@ inline int scratch_get(eon_ctx* ctx, int id, size_t bytes, void** out) {
   Scratch& s = ctx->scratch[id];
   if (bytes > s.cap) {
     if (s.ptr) {
-      // outstanding work on the stream may still use the old buffer
-      EON_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+      // outstanding work on ANY stream of the context (caller's, auxiliary, high-priority, copy streams) may still
+      // use the old buffer: growing a scratch buffer is rare, so wait for the whole device
+      EON_CUDA(ctx, cudaDeviceSynchronize());
       EON_CUDA(ctx, cudaFree(s.ptr));
       s.ptr = nullptr;
       s.cap = 0;

@@ -18,6 +18,8 @@
 // order of additions.
 #include <stdlib.h>
 
+#include <algorithm>
+
 #include "msm.cuh"
 
 namespace eon {
@@ -334,47 +336,161 @@ k_msm_fold_tasks(const MsmTask* __restrict__ tasks, const u32* __restrict__ ntas
 }
 
 // ---- 5. bucket reduction ----------------------------------------------------------------------
-// thread per (segment, chunk): running sums over `chunk` consecutive buckets.
-//   S = sum B_b,  T = sum (b - lo + 1) * B_b   =>   contribution = T + lo * S
-__global__ void __launch_bounds__(MSM_THREADS)
-k_msm_reduce_chunks(const G1Xyzz* __restrict__ buckets, MsmShape sh, size_t nseg, G1Xyzz* __restrict__ partials) {
-  size_t g = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-  if (g >= nseg * sh.nchunks) return;
-  size_t seg = g / sh.nchunks;
-  u32 ch = (u32)(g % sh.nchunks);
-  u32 lo = ch * sh.chunk;
-  const G1Xyzz* B = buckets + seg * sh.NB + lo;
-  G1Xyzz S = G1Xyzz::identity(), T = G1Xyzz::identity();
-  for (int b = (int)sh.chunk - 1; b >= 0; b--) {
-    G1Xyzz x = B[b];
-    g1_add(S, x);
-    g1_add(T, S);
+// Per segment: sum_b (b + 1) B_b over its NB = 2^(c-1) buckets.  The usual running sums are one long dependent
+// chain per thread, and this phase runs when the GPU is otherwise empty (2.3 ms^-1 ... a lone warp takes ~1200 cycles
+// per Fq product), so the chain length IS the time: 64 + 18 + 23 XYZZ additions + a Fermat inversion measured
+// 1.16 ms per MSM whatever the column count.  Here the bucket index is split b = hi L + lo (L = 2^ceil(log NB / 2)):
+//     sum_b (b+1) B_b  =  S  +  sum_lo lo C_lo  +  L sum_hi hi R_hi,     R_hi = sum_lo B[hi][lo]   (row sums)
+//                                                                          C_lo = sum_hi B[hi][lo]   (column sums)
+//                                                                          S    = sum_hi R_hi
+//   k_bucket_rowcol     all row and column sums: P lanes per sum (serial strip + shuffle tree), same 2 additions
+//                       per bucket as the running sums but in chains of NB^(1/2) / P + log P
+//   k_bucket_weighted   one CTA per vector (R or C of a segment): sum_i i X_i = sum_(j>=1) suffix_j by a block-wide
+//                       suffix scan and a block-wide sum, 21 additions deep
+//   k_bucket_finish     S + W_C + L W_R per segment
+// ~45 additions deep instead of ~130, and no scalar multiplications.
+__device__ __forceinline__ G1Xyzz ld_xyzz(const G1Xyzz* p) {
+  const uint4* q = reinterpret_cast<const uint4*>(p);
+  uint4 w[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) w[i] = __ldg(q + i);
+  G1Xyzz r;
+  u32* d = reinterpret_cast<u32*>(&r);
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    d[4 * i] = w[i].x; d[4 * i + 1] = w[i].y; d[4 * i + 2] = w[i].z; d[4 * i + 3] = w[i].w;
   }
-  if (lo) {
-    G1Xyzz ls = g1_mul_u32(S, lo);
-    g1_add(T, ls);
-  }
-  partials[g] = T;
+  return r;
+}
+__device__ __forceinline__ void st_xyzz(G1Xyzz* p, const G1Xyzz& v) {
+  uint4* q = reinterpret_cast<uint4*>(p);
+  const u32* d = reinterpret_cast<const u32*>(&v);
+#pragma unroll
+  for (int i = 0; i < 8; i++) q[i] = make_uint4(d[4 * i], d[4 * i + 1], d[4 * i + 2], d[4 * i + 3]);
+}
+__device__ __forceinline__ G1Xyzz shfl_down_xyzz(const G1Xyzz& v, u32 delta, int width = 32) {
+  G1Xyzz r;
+  const u32* s = reinterpret_cast<const u32*>(&v);
+  u32* d = reinterpret_cast<u32*>(&r);
+#pragma unroll
+  for (int i = 0; i < 32; i++) d[i] = __shfl_down_sync(0xffffffffu, s[i], delta, width);
+  return r;
 }
 
-// block per segment: sum its nchunks partials (serial per thread, then shared-memory tree)
+// grid: ceil(nseg * (H + L) * P / 128) CTAs of 128 threads; group g (P lanes) sums vector g % (H + L) of segment
+// g / (H + L): vectors [0, H) are rows, [H, H + L) columns.
+template <int P>
 __global__ void __launch_bounds__(128)
-k_msm_reduce_segment(const G1Xyzz* __restrict__ partials, u32 nchunks, G1Xyzz* __restrict__ segsum) {
-  __shared__ G1Xyzz sh[128];
-  const G1Xyzz* P = partials + (size_t)blockIdx.x * nchunks;
+k_bucket_rowcol(const G1Xyzz* __restrict__ buckets, u32 logL, u32 logH, size_t nseg, G1Xyzz* __restrict__ rows,
+                G1Xyzz* __restrict__ cols) {
+  const u32 L = 1u << logL, H = 1u << logH;
+  const size_t g = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) / P;
+  const u32 sub = threadIdx.x & (P - 1);
+  const bool live = g < nseg * (size_t)(H + L);  // whole groups are live or not: shuffles stay converged per group
+  const size_t seg = live ? g / (H + L) : 0;
+  const u32 w = live ? (u32)(g % (H + L)) : 0;
+  const G1Xyzz* B = buckets + (seg << (logL + logH));
   G1Xyzz acc = G1Xyzz::identity();
-  for (u32 i = threadIdx.x; i < nchunks; i += blockDim.x) g1_add(acc, P[i]);
-  sh[threadIdx.x] = acc;
-  __syncthreads();
-  for (u32 s = blockDim.x / 2; s > 0; s >>= 1) {
-    if (threadIdx.x < s) {
-      G1Xyzz a = sh[threadIdx.x];
-      g1_add(a, sh[threadIdx.x + s]);
-      sh[threadIdx.x] = a;
+  if (live) {
+    if (w < H) {
+      for (u32 i = sub; i < L; i += P) g1_add(acc, ld_xyzz(B + ((size_t)w << logL) + i));
+    } else {
+      const u32 lo = w - H;
+      for (u32 i = sub; i < H; i += P) g1_add(acc, ld_xyzz(B + ((size_t)i << logL) + lo));
+    }
+  }
+#pragma unroll
+  for (int d = P / 2; d >= 1; d >>= 1) {
+    const G1Xyzz t = shfl_down_xyzz(acc, d, P);
+    if (sub < (u32)d) g1_add(acc, t);
+  }
+  if (live && sub == 0) st_xyzz(w < H ? rows + seg * H + w : cols + seg * L + (w - H), acc);
+}
+
+// One CTA per vector: blockIdx.x = 2 seg + which (0: the H row sums -> W_R and S, 1: the L column sums -> W_C).
+// out[3 seg + 0] = W_R, [3 seg + 1] = W_C, [3 seg + 2] = S.  The vector is walked from its top in strips of
+// blockDim elements (one strip up to c = 17, i.e. 256 buckets per side); `above` carries the sum of the strips
+// already done, so that every thread ends up with the suffix sum of the whole vector from its element on.
+constexpr int BW_THREADS = 256;  // 255 registers per thread: the XYZZ additions below run without spills
+__global__ void __launch_bounds__(BW_THREADS)
+k_bucket_weighted(const G1Xyzz* __restrict__ rows, const G1Xyzz* __restrict__ cols, u32 logL, u32 logH,
+                  G1Xyzz* __restrict__ out) {
+  __shared__ G1Xyzz s_tot[32];
+  __shared__ G1Xyzz s_carry[32];
+  __shared__ G1Xyzz s_above;
+  const size_t seg = blockIdx.x >> 1;
+  const u32 which = blockIdx.x & 1;
+  const u32 n = 1u << (which ? logL : logH);
+  const G1Xyzz* X = which ? cols + (seg << logL) : rows + (seg << logH);
+  const u32 tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = blockDim.x >> 5;
+  G1Xyzz wsum = G1Xyzz::identity();  // thread 0: sum_i i X_i so far
+  if (tid == 0) s_above = G1Xyzz::identity();
+  const u32 strips = (n + blockDim.x - 1) / blockDim.x;
+  for (u32 sidx = strips; sidx-- > 0;) {
+    const u32 e = sidx * blockDim.x + tid;  // this thread's element
+    G1Xyzz x = e < n ? ld_xyzz(X + e) : G1Xyzz::identity();
+    // inclusive suffix sums inside the warp: x = sum of the warp's elements at lanes >= lane
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const G1Xyzz t = shfl_down_xyzz(x, d);
+      if (lane + d < 32) g1_add(x, t);
+    }
+    __syncthreads();  // s_tot / s_carry of the previous strip are no longer read; s_above is written
+    if (lane == 0) s_tot[wid] = x;
+    __syncthreads();
+    if (wid == 0) {
+      G1Xyzz y = lane < nw ? s_tot[lane] : G1Xyzz::identity();
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const G1Xyzz t = shfl_down_xyzz(y, d);
+        if (lane + d < 32) g1_add(y, t);
+      }
+      // carry into warp a = the totals of the warps after it + everything above this strip
+      G1Xyzz nxt = shfl_down_xyzz(y, 1);
+      if (lane + 1 >= 32) nxt = G1Xyzz::identity();
+      g1_add(nxt, s_above);
+      s_carry[lane] = nxt;
     }
     __syncthreads();
+    g1_add(x, s_carry[wid]);  // x = suffix sum over the whole vector from element e
+    // sum_i i X_i = sum of the suffix sums from element 1 on
+    G1Xyzz c = (e >= 1 && e < n) ? x : G1Xyzz::identity();
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) {
+      const G1Xyzz t = shfl_down_xyzz(c, d);
+      if (lane < (u32)d) g1_add(c, t);
+    }
+    __syncthreads();  // every warp has read s_carry
+    if (lane == 0) s_tot[wid] = c;
+    if (tid == 0) s_above = x;  // suffix from the first element of this strip = everything from here up
+    __syncthreads();
+    if (wid == 0) {
+      G1Xyzz y = lane < nw ? s_tot[lane] : G1Xyzz::identity();
+#pragma unroll
+      for (int d = 16; d >= 1; d >>= 1) {
+        const G1Xyzz t = shfl_down_xyzz(y, d);
+        if (lane < (u32)d) g1_add(y, t);
+      }
+      if (lane == 0) g1_add(wsum, y);
+    }
   }
-  if (threadIdx.x == 0) segsum[blockIdx.x] = sh[0];
+  __syncthreads();
+  if (tid == 0) {
+    st_xyzz(out + 3 * seg + which, wsum);
+    if (which == 0) st_xyzz(out + 3 * seg + 2, s_above);  // S = the suffix sum from element 0
+  }
+}
+
+// segsum[seg] = S + W_C + 2^logL W_R
+__global__ void __launch_bounds__(32) k_bucket_finish(const G1Xyzz* __restrict__ parts, u32 logL, size_t nseg,
+                                                      G1Xyzz* __restrict__ segsum) {
+  const size_t seg = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (seg >= nseg) return;
+  G1Xyzz t = ld_xyzz(parts + 3 * seg);
+  for (u32 i = 0; i < logL; i++) t = g1_dbl(t);
+  g1_add(t, ld_xyzz(parts + 3 * seg + 1));
+  g1_add(t, ld_xyzz(parts + 3 * seg + 2));
+  st_xyzz(segsum + seg, t);
 }
 
 // ---- 6. window combination + to-affine ----------------------------------------------------------
@@ -471,7 +587,9 @@ static int msm_batch(eon_ctx* ctx, const G1Affine* d_bases, const Fr* d_scalars,
   EON_TRY(scratch_get(ctx, SC_MSM_BUCKETS, total_buckets * sizeof(G1Xyzz), &p_bkt));
   EON_TRY(scratch_get(ctx, SC_MSM_TASKS, (size_t)max_tasks * sizeof(MsmTask), &p_tasks));
   EON_TRY(scratch_get(ctx, SC_MSM_TASKPART, (size_t)max_tasks * sizeof(G1Xyzz), &p_tpart));
-  EON_TRY(scratch_get(ctx, SC_MSM_PARTIALS, nseg * sh.nchunks * sizeof(G1Xyzz), &p_part));
+  // row sums, column sums (<= 2^ceil((c-1)/2) each) and 3 partial results per segment of the bucket reduction
+  EON_TRY(scratch_get(ctx, SC_MSM_PARTIALS, nseg * ((size_t)2 << ((sh.c - 1 + 1) / 2)) * sizeof(G1Xyzz) + nseg * 3 * sizeof(G1Xyzz),
+                      &p_part));
   EON_TRY(scratch_get(ctx, SC_MSM_SEGSUM, nseg * sizeof(G1Xyzz), &p_seg));
   EON_TRY(scratch_get(ctx, SC_MSM_MISC, 256, &p_misc));
   void* p_segtot;
@@ -558,11 +676,24 @@ static int msm_batch(eon_ctx* ctx, const G1Affine* d_bases, const Fr* d_scalars,
 
   phase_begin(ctx, PH_MSM_REDUCE);
   {
-    size_t threads = nseg * sh.nchunks;
-    unsigned blocks = (unsigned)((threads + MSM_THREADS - 1) / MSM_THREADS);
-    k_msm_reduce_chunks<<<blocks, MSM_THREADS, 0, st>>>((const G1Xyzz*)p_bkt, sh, nseg, (G1Xyzz*)p_part);
+    const u32 logNB = sh.c - 1, logL = (logNB + 1) / 2, logH = logNB - logL;
+    const size_t nvec = nseg << logL;  // >= the row and the column count of a segment
+    G1Xyzz* rows = (G1Xyzz*)p_part;            // [nseg][H]
+    G1Xyzz* cols = rows + nvec;                // [nseg][L]
+    G1Xyzz* parts = cols + nvec;               // [nseg][3]
+    const size_t groups = nseg * (((size_t)1 << logH) + ((size_t)1 << logL));
+    // lanes per row / column sum: the whole warp while there are few sums (short chains matter), narrower groups
+    // once there is enough work to fill the GPU without paying for idle tree lanes
+    const int P = groups * 32 <= (size_t)ctx->num_sms * 1024 ? 32 : (groups * 16 <= (size_t)ctx->num_sms * 2048 ? 16 : 8);
+    const unsigned grid = (unsigned)((groups * P + 127) / 128);
+    if (P == 32) k_bucket_rowcol<32><<<grid, 128, 0, st>>>((const G1Xyzz*)p_bkt, logL, logH, nseg, rows, cols);
+    else if (P == 16) k_bucket_rowcol<16><<<grid, 128, 0, st>>>((const G1Xyzz*)p_bkt, logL, logH, nseg, rows, cols);
+    else k_bucket_rowcol<8><<<grid, 128, 0, st>>>((const G1Xyzz*)p_bkt, logL, logH, nseg, rows, cols);
     EON_LAUNCHED(ctx);
-    k_msm_reduce_segment<<<(unsigned)nseg, 128, 0, st>>>((const G1Xyzz*)p_part, sh.nchunks, (G1Xyzz*)p_seg);
+    const unsigned bt = std::min<unsigned>(BW_THREADS, std::max(32u, 1u << logL));
+    k_bucket_weighted<<<(unsigned)(2 * nseg), bt, 0, st>>>(rows, cols, logL, logH, parts);
+    EON_LAUNCHED(ctx);
+    k_bucket_finish<<<(unsigned)((nseg + 31) / 32), 32, 0, st>>>(parts, logL, nseg, (G1Xyzz*)p_seg);
     EON_LAUNCHED(ctx);
     k_msm_combine<<<(unsigned)((ncols + 31) / 32), 32, 0, st>>>((const G1Xyzz*)p_seg, sh, ncols, d_out);
     EON_LAUNCHED(ctx);
