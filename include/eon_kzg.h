@@ -156,6 +156,12 @@ int eon_msm_set_sort_mode(eon_ctx* ctx, int mode);
  * order, -1 = automatic (slices when the table exceeds the L2 and every base is used by several columns).
  * Results are identical either way. */
 int eon_msm_set_slice_schedule(eon_ctx* ctx, int mode);
+/* An MSM over few columns (2..4: the shard of one GPU when 16 trace columns are split over 4-8 GPUs, the two chunk
+ * columns of commit_quotient) spends a third of its time in phases that leave the GPU idle -- the single-warp
+ * inversion trees of the batched-affine rounds, the bucket reduction.  1 / -1 (automatic): such an MSM runs as two
+ * half-batches on two streams, so that the idle phases of one half overlap the wide kernels of the other;
+ * 0 = one batch.  Results are identical either way. */
+int eon_msm_set_split(eon_ctx* ctx, int mode);
 /* rounds the most recent MSM on this context actually used */
 unsigned eon_msm_rounds_used(const eon_ctx* ctx);
 /* window bits c of the most recent MSM on this context (whole-SRS tables, range tables or the plain per-window c) */

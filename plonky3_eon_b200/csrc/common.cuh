@@ -98,7 +98,10 @@ struct eon_ctx {
   uint64_t launches = 0;
   std::mutex mu;  // callers may share a ctx across threads: one call at a time
 
-  eon::Scratch scratch[eon::SC_COUNT];
+  // two banks: bank 1 is the workspace of the second half-batch when an MSM over few columns runs as two concurrent
+  // halves on two streams (msm_run); everything else lives in bank 0
+  eon::Scratch scratch[2][eon::SC_COUNT];
+  int bank = 0;
   std::map<eon::TwiddleKey, eon::Fr*> twiddles;
   size_t twiddle_bytes = 0;  // device bytes behind `twiddles` (bounded: see get_twiddles)
   // opt-in shared-memory sizes (cudaFuncSetAttribute) are per device: set once per context, not per process
@@ -129,6 +132,9 @@ struct eon_ctx {
   cudaStream_t aux_stream = nullptr;    // second compute stream: the hinted LDE runs beside the MSM, whose
                                         // sort / gather phases leave the integer pipe idle  // opposite PCIe direction (downloads while uploads are in flight)
   cudaStream_t prio_stream = nullptr;   // high-priority compute stream: the MSM while an LDE transform runs beside it
+  cudaStream_t split_stream = nullptr;  // second half-batch of an MSM over few columns (msm_run), high priority
+  cudaEvent_t ev_split[2] = {nullptr, nullptr};
+  int msm_split_mode = -1;              // -1 automatic (2..4 columns, >= 2^16 points), 0 never, 1 whenever >= 2 columns
   cudaEvent_t ev_pipe[20] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
                              nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 
@@ -177,7 +183,7 @@ inline int fail(eon_ctx* ctx, int code, const std::string& msg) {
   } while (0)
 
 inline int scratch_get(eon_ctx* ctx, int id, size_t bytes, void** out) {
-  Scratch& s = ctx->scratch[id];
+  Scratch& s = ctx->scratch[ctx->bank][id];
   if (bytes > s.cap) {
     if (s.ptr) {
       // outstanding work on ANY stream of the context (caller's, auxiliary, high-priority, copy streams) may still

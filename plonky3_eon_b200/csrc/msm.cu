@@ -742,6 +742,41 @@ int msm_run(eon_ctx* ctx, const G1Affine* d_bases, const Fr* d_scalars, size_t n
   size_t batch = budget / per_col;
   if (batch < 1) batch = 1;
   if (batch > 64) batch = 64;
+  // Few columns: two half-batches on two streams.  A batch of 2 columns of 2^20 points spends ~1.8 of its 6.8 ms in
+  // phases that leave the GPU idle (three inversion trees, the bucket reduction: single-warp dependent chains);
+  // with two independent halves in flight those phases of one half run under the wide kernels of the other.
+  // (At 8+ columns it loses: every base is gathered by half as many columns per launch, which is what the slice
+  // schedule of round 0 lives on -- measured 47.1 vs 45.1 ms at 16 columns.)
+  static const int split_env = getenv("EON_MSM_SPLIT") ? atoi(getenv("EON_MSM_SPLIT")) : -1;
+  const int split_mode = ctx->msm_split_mode >= 0 ? ctx->msm_split_mode : split_env;
+  const bool split = ncols >= 2 && ncols <= batch && ctx->bank == 0 &&
+                     (split_mode == 1 || (split_mode != 0 && ncols <= 4 && n >= ((size_t)1 << 16)));
+  if (split) {
+    if (!ctx->split_stream) {
+      int least = 0, greatest = 0;
+      EON_CUDA(ctx, cudaDeviceGetStreamPriorityRange(&least, &greatest));
+      EON_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->split_stream, cudaStreamNonBlocking, greatest));
+      for (auto& e : ctx->ev_split) EON_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    const size_t h0 = (ncols + 1) / 2;
+    cudaStream_t main_stream = ctx->stream;
+    // the second half is ordered after everything queued so far (the scalars are produced on the main stream)
+    EON_CUDA(ctx, cudaEventRecord(ctx->ev_split[0], main_stream));
+    EON_CUDA(ctx, cudaStreamWaitEvent(ctx->split_stream, ctx->ev_split[0], 0));
+    int rc = msm_batch(ctx, bases, d_scalars, n, h0, ld, sh, d_out);
+    if (rc == EON_OK) {
+      ctx->stream = ctx->split_stream;
+      ctx->bank = 1;
+      rc = msm_batch(ctx, bases, d_scalars + h0, n, ncols - h0, ld, sh, d_out + h0);
+      ctx->bank = 0;
+      ctx->stream = main_stream;
+    }
+    // join in any case: nothing may outlive the call on the second stream
+    cudaError_t e = cudaEventRecord(ctx->ev_split[1], ctx->split_stream);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(main_stream, ctx->ev_split[1], 0);
+    if (rc == EON_OK && e != cudaSuccess) rc = fail(ctx, EON_ERR_CUDA, std::string("msm split join failed: ") + cudaGetErrorString(e));
+    return rc;
+  }
   for (size_t c0 = 0; c0 < ncols; c0 += batch) {
     size_t nc = std::min(batch, ncols - c0);
     EON_TRY(msm_batch(ctx, bases, d_scalars + c0, n, nc, ld, sh, d_out + c0));
@@ -786,11 +821,17 @@ int srs_build_tables(eon_ctx* ctx, unsigned window_bits) {
 }
 
 // cost model shared by the table policies: n * W(c) mixed additions (10 modmul) + 2^(c-1) bucket-reduction steps
+// MEASURED (B200, one column, profiles/r02d_msm_window_sweep.txt): 2^21 points: c = 17 6.74 ms, c = 20 7.31 ms,
+// c = 16 7.41 ms; 2^24 points: c = 20 39.2 ms, c = 19 45.2 ms, c = 18 61.9 ms.  Every bucket costs far more than
+// its two reduction additions (the finisher's serial chain, the reduction's dependent steps): 200 products per
+// bucket reproduces the measured optimum 17 up to 2^22 points and 20 from 2^23 on.  c = 18, 19 are excluded: their
+// shapes run the two-pass sort with one bucket set per tile and measured far off the model (finisher 3-5x slower).
 static u32 msm_best_window(size_t n) {
   u32 best_c = 0;
   double best = 0;
   for (u32 c = 10; c <= 20; c++) {
-    double cost = (double)n * msm_windows(c) * 10.0 + (double)(1u << (c - 1)) * 60.0;
+    if (c == 18 || c == 19) continue;
+    double cost = (double)n * msm_windows(c) * 10.0 + (double)(1u << (c - 1)) * 200.0;
     if (!best_c || cost < best) {
       best_c = c;
       best = cost;

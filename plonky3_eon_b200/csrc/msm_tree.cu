@@ -31,7 +31,10 @@
 namespace eon {
 
 constexpr int TREE_THREADS = 128;
-constexpr u64 TREE_TOP = 256;      // level size at which the values are inverted directly
+// level size at which the values are inverted directly: with the binary-GCD inversion (fp.cuh) 2048 inversions on
+// 64 warps cost the same ~25 us as 256, and every level of the product tree saved is two launches and ~28
+// dependent products less per round
+constexpr u64 TREE_TOP = 2048;
 
 enum { PAIR_TRIVIAL = 0, PAIR_ADD = 1, PAIR_DBL = 2 };
 
@@ -496,7 +499,7 @@ SlicePlan msm_slice_plan(const eon_ctx* ctx, u64 nbases, u64 total_slots, u32 ro
   p.on = rounds > 0 && nbins <= SLICE_MAX_BINS && total_slots / 2 < 0xffffffffull;
   if (mode == 0) p.on = false;
   else if (mode != 1)
-    p.on = p.on && nbins <= SLICE_ORDER_MAX && nbases * sizeof(G1Affine) > (96ull << 20) && total_slots >= 4 * nbases;
+    p.on = p.on && nbins <= SLICE_ORDER_MAX && nbases * sizeof(G1Affine) > (96ull << 20) && total_slots >= 2 * nbases;
   return p;
 }
 

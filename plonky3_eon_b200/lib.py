@@ -61,6 +61,7 @@ _SIGS = {
     "eon_msm_window_bits_used": (C.c_uint, [C.c_void_p]),
     "eon_msm_set_sort_mode": (C.c_int, [C.c_void_p, C.c_int]),
     "eon_msm_set_slice_schedule": (C.c_int, [C.c_void_p, C.c_int]),
+    "eon_msm_set_split": (C.c_int, [C.c_void_p, C.c_int]),
     "eon_msm_srs_dev": (C.c_int, [C.c_void_p, _u64p, C.c_size_t, C.c_size_t, C.c_size_t, _u64p]),
     "eon_msm_srs": (C.c_int, [C.c_void_p, _u64p, C.c_size_t, C.c_size_t, C.c_size_t, _u64p]),
     "eon_msm_points": (C.c_int, [C.c_void_p, _u64p, _u64p, C.c_size_t, _u64p]),

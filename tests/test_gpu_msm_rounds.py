@@ -113,3 +113,34 @@ def test_slice_schedule_multi_slice_table(ctx):
         dl.append(a)
         a = a * alpha % fr.P
     assert T.pt(outs[1][0]) == g1.msm_via_dlog(dl, col0)
+
+
+@pytest.mark.parametrize("log_n,ncols,bits", [(6, 2, 0), (10, 3, 0), (12, 5, 0), (15, 4, 13), (16, 2, 17), (17, 3, 17)])
+def test_two_stream_split_matches_one_batch(ctx, log_n, ncols, bits):
+    """An MSM over few columns runs as two half-batches on two streams (csrc/msm.cu msm_run, workspace bank 1):
+    forced on for every shape here (odd column counts, table and plain paths, rounds on) it must give the same
+    points as the single batch, and the first column must equal the dlog shortcut."""
+    n, alpha = 1 << log_n, 12345
+    pcs = T.pcs_new(ctx, n - 1, alpha)
+    ctx.call("eon_srs_set_window_tables", bits)
+    rng = np.random.default_rng(100 + log_n + ncols)
+    sc = fr.random_wire(rng, n * ncols).reshape(n, ncols, 4)
+    sc[: n // 3, ncols - 1] = 0                      # a sparse last column: very different bucket loads per half
+    outs = []
+    for split, rounds in ((0, -1), (1, -1), (1, 2), (1, 0)):
+        ctx.call("eon_msm_set_split", split)
+        ctx.call("eon_msm_set_rounds", rounds)
+        out = np.zeros((ncols, 8), dtype=np.uint64)
+        ctx.call("eon_msm_srs", sc, n, ncols, ncols, out)
+        outs.append(out)
+    ctx.call("eon_msm_set_split", -1)
+    ctx.call("eon_msm_set_rounds", -1)
+    ctx.call("eon_srs_set_window_tables", 0)
+    for o in outs[1:]:
+        assert np.array_equal(outs[0], o)
+    col0 = fr.from_wire(np.ascontiguousarray(sc[:, 0, :]))
+    dl, a = [], 1
+    for _ in range(n):
+        dl.append(a)
+        a = a * alpha % fr.P
+    assert T.pt(outs[1][0]) == g1.msm_via_dlog(dl, col0)
