@@ -134,6 +134,7 @@ struct eon_ctx {
   cudaStream_t prio_stream = nullptr;   // high-priority compute stream: the MSM while an LDE transform runs beside it
   cudaStream_t split_stream = nullptr;  // second half-batch of an MSM over few columns (msm_run), high priority
   cudaEvent_t ev_split[2] = {nullptr, nullptr};
+  cudaEvent_t ev_stagger = nullptr;     // set by msm_run for ONE msm_batch: recorded after that batch's sort
   int msm_split_mode = -1;              // -1 automatic (2..4 columns, >= 2^16 points), 0 never, 1 whenever >= 2 columns
   cudaEvent_t ev_pipe[20] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
                              nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};

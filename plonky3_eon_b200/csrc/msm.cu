@@ -231,7 +231,7 @@ struct AccSrc {
   const G1Affine* bases;
   const u32* entries;
   u64 seg_cap;
-  const G1Affine* pts;
+  const G1Affine* pts;  // partial sums after the pairwise rounds (msm_tree.cu)
   u32 rshift;
 };
 
@@ -636,6 +636,10 @@ static int msm_batch(eon_ctx* ctx, const G1Affine* d_bases, const Fr* d_scalars,
     }
   }
 
+  if (ctx->ev_stagger) {  // two-stream split: the second half-batch starts here (see msm_run)
+    EON_CUDA(ctx, cudaEventRecord(ctx->ev_stagger, st));
+    ctx->ev_stagger = nullptr;
+  }
   phase_begin(ctx, PH_MSM_ACCUM);
   {
     AccSrc src;
@@ -760,10 +764,19 @@ int msm_run(eon_ctx* ctx, const G1Affine* d_bases, const Fr* d_scalars, size_t n
     }
     const size_t h0 = (ncols + 1) / 2;
     cudaStream_t main_stream = ctx->stream;
-    // the second half is ordered after everything queued so far (the scalars are produced on the main stream)
-    EON_CUDA(ctx, cudaEventRecord(ctx->ev_split[0], main_stream));
-    EON_CUDA(ctx, cudaStreamWaitEvent(ctx->split_stream, ctx->ev_split[0], 0));
+    // The second half is ordered after everything queued so far (the scalars are produced on the main stream) --
+    // and, staggered, after the SORT of the first half: two halves started together run in lockstep, their idle
+    // phases coincide and nothing is gained; half a phase apart, the inversion trees and the bucket reduction of
+    // one half fall under the pair rounds of the other.  EON_MSM_STAGGER=0: start together.
+    static const int stagger_env = getenv("EON_MSM_STAGGER") ? atoi(getenv("EON_MSM_STAGGER")) : 1;
+    if (stagger_env) ctx->ev_stagger = ctx->ev_split[0];
+    else EON_CUDA(ctx, cudaEventRecord(ctx->ev_split[0], main_stream));
     int rc = msm_batch(ctx, bases, d_scalars, n, h0, ld, sh, d_out);
+    if (ctx->ev_stagger) {  // the first half failed before its sort was queued
+      ctx->ev_stagger = nullptr;
+      cudaEventRecord(ctx->ev_split[0], main_stream);
+    }
+    EON_CUDA(ctx, cudaStreamWaitEvent(ctx->split_stream, ctx->ev_split[0], 0));
     if (rc == EON_OK) {
       ctx->stream = ctx->split_stream;
       ctx->bank = 1;

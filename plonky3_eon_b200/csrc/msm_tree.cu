@@ -39,7 +39,11 @@ constexpr u64 TREE_TOP = 2048;
 enum { PAIR_TRIVIAL = 0, PAIR_ADD = 1, PAIR_DBL = 2 };
 
 struct TreeSrc {
-  const G1Affine* pts;  // rounds >= 1
+  // rounds >= 1: the previous round's sums as two arrays (x | y).  k_tree_fwd needs the x coordinates only (the
+  // denominators x2 - x1), so with the coordinates apart it streams half the bytes of an array of points
+  // (round 1 + 2 of a 2^20 x 16 commit: 12 -> 6 GB of reads).
+  const Fq* pts_x;
+  const Fq* pts_y;
   const u32* entries;   // round 0: entry = base index | sign << 31, or ENTRY_NONE
   const G1Affine* bases;
 };
@@ -110,7 +114,7 @@ __device__ __forceinline__ uint2 ldg_rec(const uint2* p) {
 // One operand of a pair, loaded lazily: x first (the common path needs nothing else).
 template <bool R0>
 struct Operand {
-  const G1Affine* p;  // null: ENTRY_NONE
+  const Fq* py;       // where the y coordinate lives; null: ENTRY_NONE
   bool neg;
   bool keep;          // slice schedule: the point comes from an L2-resident table slice
   Fq x;
@@ -118,7 +122,8 @@ struct Operand {
   __device__ __forceinline__ void open_entry(const G1Affine* bases, u32 v) {
     keep = true;
     neg = (v & SIGN_BIT) != 0;
-    p = (v == ENTRY_NONE) ? nullptr : bases + (v & ~SIGN_BIT);
+    const G1Affine* p = (v == ENTRY_NONE) ? nullptr : bases + (v & ~SIGN_BIT);
+    py = p ? &p->y : nullptr;
     x = p ? load(&p->x) : Fq::zero();
   }
   __device__ __forceinline__ void open(const TreeSrc& s, u64 slot) {
@@ -126,19 +131,21 @@ struct Operand {
     if (R0) {
       u32 v = __ldg(s.entries + slot);
       neg = (v & SIGN_BIT) != 0;
-      p = (v == ENTRY_NONE) ? nullptr : s.bases + (v & ~SIGN_BIT);
+      const G1Affine* p = (v == ENTRY_NONE) ? nullptr : s.bases + (v & ~SIGN_BIT);
+      py = p ? &p->y : nullptr;
+      x = p ? ldg_fq(&p->x) : Fq::zero();
     } else {
       neg = false;
-      p = s.pts + slot;
+      py = s.pts_y + slot;
+      x = ldg_fq(s.pts_x + slot);
     }
-    x = p ? ldg_fq(&p->x) : Fq::zero();
   }
   __device__ __forceinline__ Fq y() const {
-    if (!p) return Fq::zero();
-    Fq v = load(&p->y);
+    if (!py) return Fq::zero();
+    Fq v = load(py);
     return neg ? fp_neg(v) : v;
   }
-  __device__ __forceinline__ bool is_identity() const { return !p || (x.is_zero() && load(&p->y).is_zero()); }
+  __device__ __forceinline__ bool is_identity() const { return !py || (x.is_zero() && load(py).is_zero()); }
 };
 
 // Denominator of pair j and what kind of pair it is.  Used identically by k_tree_fwd and by both
@@ -256,7 +263,7 @@ __device__ __forceinline__ G1Affine pair_sum(const Operand<R0>& P, const Operand
 template <bool R0, int TREE_B>
 __global__ void __launch_bounds__(TREE_THREADS, 4)
 k_tree_bwd(TreeSrc src, u64 npairs, const Fq* __restrict__ T0inv, const Fq* __restrict__ pre_all,
-           G1Affine* __restrict__ out) {
+           Fq* __restrict__ out_x, Fq* __restrict__ out_y, u32 ostride) {
   const u64 t = blockIdx.x * (u64)blockDim.x + threadIdx.x;
   const u64 j0 = t * TREE_B;
   if (j0 >= npairs) return;
@@ -271,8 +278,8 @@ k_tree_bwd(TreeSrc src, u64 npairs, const Fq* __restrict__ T0inv, const Fq* __re
     Fq d;
     const int kind = pair_denominator<R0>(P, Q, d);
     const G1Affine r = pair_sum<R0>(P, Q, kind, d, inv, pre_all + j0 + i);
-    st_fq(&out[j0 + i].x, r.x);
-    st_fq(&out[j0 + i].y, r.y);
+    st_fq(out_x + (j0 + i) * ostride, r.x);
+    st_fq(out_y + (j0 + i) * ostride, r.y);
   }
 }
 
@@ -434,7 +441,7 @@ template <int TREE_B>
 __global__ void __launch_bounds__(TREE_THREADS, 4)
 k_tree_bwd_sliced(const uint2* __restrict__ rec_e, const u32* __restrict__ rec_dest, u64 npairs,
                   const G1Affine* __restrict__ bases, const Fq* __restrict__ T0inv, const Fq* __restrict__ pre_all,
-                  G1Affine* __restrict__ out) {
+                  Fq* __restrict__ out_x, Fq* __restrict__ out_y, u32 ostride) {
   const u64 k0 = (u64)blockIdx.x * (TREE_THREADS * TREE_B) + threadIdx.x;
   if (k0 >= npairs) return;
   const int cnt = (int)min((u64)TREE_B, (npairs - k0 + TREE_THREADS - 1) / TREE_THREADS);
@@ -450,8 +457,8 @@ k_tree_bwd_sliced(const uint2* __restrict__ rec_e, const u32* __restrict__ rec_d
     Fq d;
     const int kind = pair_denominator<true>(P, Q, d);
     const G1Affine r = pair_sum<true>(P, Q, kind, d, inv, pre_all + k);
-    st_fq_stream(&out[dest].x, r.x);
-    st_fq_stream(&out[dest].y, r.y);
+    st_fq_stream(out_x + (u64)dest * ostride, r.x);
+    st_fq_stream(out_y + (u64)dest * ostride, r.y);
   }
 }
 
@@ -464,20 +471,26 @@ static void launch_fwd(bool r0, unsigned grid, cudaStream_t st, const TreeSrc& s
 }
 template <int B>
 static void launch_bwd(bool r0, unsigned grid, cudaStream_t st, const TreeSrc& src, u64 npairs, const Fq* T0inv,
-                       const Fq* pre, G1Affine* out) {
-  if (r0) k_tree_bwd<true, B><<<grid, TREE_THREADS, 0, st>>>(src, npairs, T0inv, pre, out);
-  else k_tree_bwd<false, B><<<grid, TREE_THREADS, 0, st>>>(src, npairs, T0inv, pre, out);
+                       const Fq* pre, Fq* out_x, Fq* out_y, u32 ostride) {
+  if (r0) k_tree_bwd<true, B><<<grid, TREE_THREADS, 0, st>>>(src, npairs, T0inv, pre, out_x, out_y, ostride);
+  else k_tree_bwd<false, B><<<grid, TREE_THREADS, 0, st>>>(src, npairs, T0inv, pre, out_x, out_y, ostride);
 }
 
-// pairs per thread (one shared denominator product per thread): 8, 16 or 32
-static int tree_b() {
-  static int b = 0;
-  if (!b) {
+// Pairs per thread (one shared denominator product per thread): 8, 16 or 32.  More pairs per thread = fewer
+// products for the shared inversion (3 / B per pair), but also B x more pairs in flight per resident thread, and
+// the in-flight pairs of round 0 gather from the window tables: with few columns (few pairs in total) a launch
+// with B = 32 has a quarter of the table in flight at once and the gathers miss the L2.  MEASURED (2^20 rows,
+// profiles/r02g_pairs_per_thread.txt): 16 columns 43.40 / 43.49 / 44.28 ms for B = 32 / 16 / 8, 8 columns 22.61 /
+// 22.42 / 22.68, 4 columns 12.24 / 12.16 / 12.11, 2 columns 7.31 / 7.16 / 7.08.  EON_TREE_B / EON_TREE_SLICED_B force.
+static int tree_b_policy(u64 pairs_round0) { return pairs_round0 < (48ull << 20) ? 8 : (pairs_round0 < (100ull << 20) ? 16 : 32); }
+static int tree_b(u64 pairs_round0) {
+  static int b = -1;
+  if (b < 0) {
     const char* e = getenv("EON_TREE_B");
-    b = e ? atoi(e) : 32;
-    if (b != 8 && b != 16 && b != 32) b = 32;
+    b = e ? atoi(e) : 0;
+    if (b != 8 && b != 16 && b != 32) b = 0;
   }
-  return b;
+  return b ? b : tree_b_policy(pairs_round0);
 }
 
 static int env_int(const char* name, int dflt) {
@@ -505,14 +518,14 @@ SlicePlan msm_slice_plan(const eon_ctx* ctx, u64 nbases, u64 total_slots, u32 ro
 
 template <int B>
 static void launch_sliced(bool fwd, unsigned grid, cudaStream_t st, const uint2* rec_e, const u32* rec_dest, u64 npairs,
-                          const G1Affine* bases, Fq* T0, Fq* pre, G1Affine* out) {
+                          const G1Affine* bases, Fq* T0, Fq* pre, Fq* out_x, Fq* out_y, u32 ostride) {
   if (fwd) k_tree_fwd_sliced<B><<<grid, TREE_THREADS, 0, st>>>(rec_e, npairs, bases, T0, pre);
-  else k_tree_bwd_sliced<B><<<grid, TREE_THREADS, 0, st>>>(rec_e, rec_dest, npairs, bases, T0, pre, out);
+  else k_tree_bwd_sliced<B><<<grid, TREE_THREADS, 0, st>>>(rec_e, rec_dest, npairs, bases, T0, pre, out_x, out_y, ostride);
 }
 
 int msm_tree_rounds(eon_ctx* ctx, const G1Affine* d_bases, const SlicePlan& plan, const u32* d_entries,
                     u64 total_slots, u32 rounds, const G1Affine** out_pts) {
-  const u64 TREE_B = (u64)tree_b();
+  const u64 TREE_B = (u64)tree_b(total_slots / 2);
   if (rounds == 0 || (total_slots & ((1ull << rounds) - 1)))
     return fail(ctx, EON_ERR_BAD_ARG, "msm_tree_rounds: slot count not aligned to 2^rounds");
   cudaStream_t st = ctx->stream;
@@ -521,8 +534,9 @@ int msm_tree_rounds(eon_ctx* ctx, const G1Affine* d_bases, const SlicePlan& plan
   EON_TRY(scratch_get(ctx, SC_MSM_TREE_A, m0 * sizeof(G1Affine), &bufA));
   EON_TRY(scratch_get(ctx, SC_MSM_TREE_B, (m0 / 2 + 1) * sizeof(G1Affine), &bufB));
   // level sizes of round 0 (the largest round): n0 = ceil(m0 / B), n(l+1) = ceil(n(l) / 8)
-  static const int sliced_b_env = env_int("EON_TREE_SLICED_B", 32);
-  const u64 SLICED_B = (sliced_b_env == 8 || sliced_b_env == 16) ? (u64)sliced_b_env : 32;
+  static const int sliced_b_env = env_int("EON_TREE_SLICED_B", 0);
+  const u64 SLICED_B = (sliced_b_env == 8 || sliced_b_env == 16 || sliced_b_env == 32) ? (u64)sliced_b_env
+                                                                                         : (u64)tree_b_policy(m0);
   const bool sliced = plan.on;
   const u64 nbins = plan.nbins;
   const u64 n0_sliced = ((m0 + TREE_THREADS * SLICED_B - 1) / (TREE_THREADS * SLICED_B)) * TREE_THREADS;
@@ -536,17 +550,23 @@ int msm_tree_rounds(eon_ctx* ctx, const G1Affine* d_bases, const SlicePlan& plan
   EON_TRY(scratch_get(ctx, SC_MSM_TREE_P, m0 * sizeof(Fq), &bufP));
 
   TreeSrc src;
-  src.pts = nullptr;
+  src.pts_x = src.pts_y = nullptr;
   src.entries = d_entries;
   src.bases = d_bases;
   u64 npairs = m0;
-  G1Affine* outs[2] = {(G1Affine*)bufA, (G1Affine*)bufB};
+  Fq* outs[2] = {(Fq*)bufA, (Fq*)bufB};  // a round's sums: npairs x coordinates, then npairs y coordinates
   // pair records of the slice schedule live in round 1's output buffer, which is idle during round 0
   // (12 bytes per pair against the 32 bytes per pair of that buffer)
   uint2* rec_e = (uint2*)bufB;
   u32* rec_dest = (u32*)(rec_e + m0);
   for (u32 r = 0; r < rounds; r++) {
-    G1Affine* out = outs[r & 1];
+    // intermediate rounds write the coordinates apart (the next k_tree_fwd reads x only); the last round writes
+    // points (x, y interleaved): the finisher reads both coordinates of consecutive sums (measured: with the
+    // coordinates apart there too it lost 0.6 ms of the 0.9 ms the forward passes gained)
+    const bool last = r + 1 == rounds;
+    const u32 ostride = last ? 2 : 1;
+    Fq* out_x = outs[r & 1];
+    Fq* out_y = last ? out_x + 1 : out_x + npairs;
     const bool sl = sliced && r == 0;
     std::vector<std::pair<Fq*, u64>> lv;  // (array, size) per level
     Fq* T = (Fq*)bufT;
@@ -571,9 +591,9 @@ int msm_tree_rounds(eon_ctx* ctx, const G1Affine* d_bases, const SlicePlan& plan
       EON_LAUNCHED(ctx);
       k_pair_scatter<<<gp, 256, 0, st>>>(pairs, npairs, (u32)nbins, plan.shift, cursor, rec_e, rec_dest);
       EON_LAUNCHED(ctx);
-      if (SLICED_B == 8) launch_sliced<8>(true, g0, st, rec_e, rec_dest, npairs, d_bases, lv[0].first, (Fq*)bufP, out);
-      else if (SLICED_B == 16) launch_sliced<16>(true, g0, st, rec_e, rec_dest, npairs, d_bases, lv[0].first, (Fq*)bufP, out);
-      else launch_sliced<32>(true, g0, st, rec_e, rec_dest, npairs, d_bases, lv[0].first, (Fq*)bufP, out);
+      if (SLICED_B == 8) launch_sliced<8>(true, g0, st, rec_e, rec_dest, npairs, d_bases, lv[0].first, (Fq*)bufP, out_x, out_y, ostride);
+      else if (SLICED_B == 16) launch_sliced<16>(true, g0, st, rec_e, rec_dest, npairs, d_bases, lv[0].first, (Fq*)bufP, out_x, out_y, ostride);
+      else launch_sliced<32>(true, g0, st, rec_e, rec_dest, npairs, d_bases, lv[0].first, (Fq*)bufP, out_x, out_y, ostride);
     } else if (TREE_B == 8) launch_fwd<8>(r == 0, g0, st, src, npairs, lv[0].first, (Fq*)bufP);
     else if (TREE_B == 16) launch_fwd<16>(r == 0, g0, st, src, npairs, lv[0].first, (Fq*)bufP);
     else launch_fwd<32>(r == 0, g0, st, src, npairs, lv[0].first, (Fq*)bufP);
@@ -593,18 +613,19 @@ int msm_tree_rounds(eon_ctx* ctx, const G1Affine* d_bases, const SlicePlan& plan
     phase_end(ctx, PH_MSM_TREE_INV);
     phase_begin(ctx, PH_MSM_TREE_BWD);
     if (sl) {
-      if (SLICED_B == 8) launch_sliced<8>(false, g0, st, rec_e, rec_dest, npairs, d_bases, lv[0].first, (Fq*)bufP, out);
-      else if (SLICED_B == 16) launch_sliced<16>(false, g0, st, rec_e, rec_dest, npairs, d_bases, lv[0].first, (Fq*)bufP, out);
-      else launch_sliced<32>(false, g0, st, rec_e, rec_dest, npairs, d_bases, lv[0].first, (Fq*)bufP, out);
-    } else if (TREE_B == 8) launch_bwd<8>(r == 0, g0, st, src, npairs, lv[0].first, (const Fq*)bufP, out);
-    else if (TREE_B == 16) launch_bwd<16>(r == 0, g0, st, src, npairs, lv[0].first, (const Fq*)bufP, out);
-    else launch_bwd<32>(r == 0, g0, st, src, npairs, lv[0].first, (const Fq*)bufP, out);
+      if (SLICED_B == 8) launch_sliced<8>(false, g0, st, rec_e, rec_dest, npairs, d_bases, lv[0].first, (Fq*)bufP, out_x, out_y, ostride);
+      else if (SLICED_B == 16) launch_sliced<16>(false, g0, st, rec_e, rec_dest, npairs, d_bases, lv[0].first, (Fq*)bufP, out_x, out_y, ostride);
+      else launch_sliced<32>(false, g0, st, rec_e, rec_dest, npairs, d_bases, lv[0].first, (Fq*)bufP, out_x, out_y, ostride);
+    } else if (TREE_B == 8) launch_bwd<8>(r == 0, g0, st, src, npairs, lv[0].first, (const Fq*)bufP, out_x, out_y, ostride);
+    else if (TREE_B == 16) launch_bwd<16>(r == 0, g0, st, src, npairs, lv[0].first, (const Fq*)bufP, out_x, out_y, ostride);
+    else launch_bwd<32>(r == 0, g0, st, src, npairs, lv[0].first, (const Fq*)bufP, out_x, out_y, ostride);
     EON_LAUNCHED(ctx);
     phase_end(ctx, PH_MSM_TREE_BWD);
-    src.pts = out;
+    src.pts_x = out_x;
+    src.pts_y = out_y;
     npairs /= 2;
   }
-  *out_pts = src.pts;
+  *out_pts = reinterpret_cast<const G1Affine*>(src.pts_x);  // the last round wrote points
   return EON_OK;
 }
 

@@ -188,6 +188,17 @@ static int get_twiddles(eon_ctx* ctx, unsigned log_n, const Fr& shift, int inver
   return EON_OK;
 }
 
+// 16-byte asynchronous global -> shared copy (LDGSTS): the tile goes from HBM to shared memory without a stop in
+// registers, and all of a thread's units are in flight at once
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  const u32 d = (u32)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+}
+__device__ __forceinline__ Fr fr_lds(const uint4* p) { return fr_from_units(p[0], p[1]); }
+
 // ---- one HBM pass: r butterfly layers on a shared-memory tile -----------------------------
 struct PassParams {
   const uint4* src;
@@ -206,6 +217,7 @@ struct PassParams {
   int out_rev;  // destination row = bitrev_{log_n}(position)   (only with l0 == 0)
   int dif;      // 0: forward DIT butterflies, layers ascending; 1: inverse butterflies, descending
   int scale;    // last pass of a transform: 1 = multiply every output by scale_c, 2 = canonicalise
+  int tw_smem;  // the pass's 2^r - 1 twiddles are the same for every element of a tile: staged in shared memory
   Fr scale_c;
 };
 
@@ -231,7 +243,12 @@ __device__ __forceinline__ void split_vidx(const PassParams& p, u64 vidx, u64& l
   }
 }
 
-template <int MINB, bool R4, bool SH>
+// TWS (fixed-operand twiddles only): the twiddles of the pass are staged in shared memory.  Inside a tile the
+// twiddle of layer t depends on the tile row only -- index ((row & (2^t - 1)) << l0) + lo, and lo (the position
+// inside the 2^l0 block) is the same for all cv virtual columns of a tile when w is a multiple of cv (or l0 = 0) --
+// so a tile uses 2^r - 1 pairs (8 KiB at r = 7) instead of fetching 48 bytes per butterfly from the L2 in the
+// middle of the dependent IMAD chains.
+template <int MINB, bool R4, bool SH, bool TWS = false>
 __global__ void __launch_bounds__(NTT_THREADS, MINB) k_ntt_pass(const PassParams p) {
   typedef typename TwOf<SH>::T Tw;
   extern __shared__ uint4 smem[];
@@ -240,6 +257,7 @@ __global__ void __launch_bounds__(NTT_THREADS, MINB) k_ntt_pass(const PassParams
   const u32 tile_elems = R << p.log_cv;
   uint4* s_lo = smem;
   uint4* s_hi = smem + tile_elems + 4;  // +64 B: the two 16-byte planes of one element hit different banks
+  uint4* s_tw = s_hi + tile_elems + 4;  // TWS: (2^r - 1) x 64 bytes, layer t at entry 2^t - 1
   const u32 tid = threadIdx.x;
 
   const u64 tile = blockIdx.x;
@@ -252,42 +270,46 @@ __global__ void __launch_bounds__(NTT_THREADS, MINB) k_ntt_pass(const PassParams
   // ---- load tile (16-byte units, consecutive threads -> consecutive units) ----
   const bool plain_in = (p.k == 0 && !p.in_rev && p.ld_src == p.w);
   const bool plain_out = (p.ld_dst == p.w);
-  // LD_BATCH independent 16-byte loads are issued before the first of them is stored to shared memory (a load
-  // immediately followed by its store serialises the global round trips: 16 per thread and tile)
-  constexpr int LD_BATCH = 8;
-  for (u32 ub = tid; ub < tile_elems * 2; ub += NTT_THREADS * LD_BATCH) {
-    uint4 val[LD_BATCH];
-    u32 se[LD_BATCH];  // shared-memory slot: element | half << 31, or ~0u for nothing
-#pragma unroll
-    for (int q = 0; q < LD_BATCH; q++) {
-      const u32 u = ub + q * NTT_THREADS;
-      const u32 e = u >> 1, half = u & 1;
-      const u32 m = e >> p.log_cv, vc = e & (cv - 1);
-      se[q] = ~0u;
-      if (u >= tile_elems * 2 || vc >= ncv) continue;
-      const u64 vidx = v0 + vc;
-      u64 src_elem;
-      if (plain_in) {
-        src_elem = (row_base + m) * p.V + vidx;
-      } else {
-        u64 lo;
-        u32 col;
-        split_vidx(p, vidx, lo, col);
-        u64 pos = ((row_base + m) << p.l0) + lo;
-        u64 srow = pos >> p.k;
-        if (p.in_rev) {
-          u32 bits = p.log_n - p.k;
-          srow = bits ? (u64)(__brev((u32)srow) >> (32 - bits)) : 0;
-        }
-        src_elem = srow * p.ld_src + col;
+  // every 16-byte unit of the tile as one asynchronous copy straight into its shared-memory slot
+  for (u32 u = tid; u < tile_elems * 2; u += NTT_THREADS) {
+    const u32 e = u >> 1, half = u & 1;
+    const u32 m = e >> p.log_cv, vc = e & (cv - 1);
+    if (vc >= ncv) continue;
+    const u64 vidx = v0 + vc;
+    u64 src_elem;
+    if (plain_in) {
+      src_elem = (row_base + m) * p.V + vidx;
+    } else {
+      u64 lo;
+      u32 col;
+      split_vidx(p, vidx, lo, col);
+      u64 pos = ((row_base + m) << p.l0) + lo;
+      u64 srow = pos >> p.k;
+      if (p.in_rev) {
+        u32 bits = p.log_n - p.k;
+        srow = bits ? (u64)(__brev((u32)srow) >> (32 - bits)) : 0;
       }
-      val[q] = p.src[src_elem * 2 + half];
-      se[q] = e | (half << 31);
+      src_elem = srow * p.ld_src + col;
     }
-#pragma unroll
-    for (int q = 0; q < LD_BATCH; q++)
-      if (se[q] != ~0u) ((se[q] >> 31) ? s_hi : s_lo)[se[q] & 0x7fffffffu] = val[q];
+    cp_async16((half ? s_hi : s_lo) + e, p.src + src_elem * 2 + half);
   }
+  if constexpr (TWS) {
+    // the tile's twiddles: entry i = layer t = floor(log2(i + 1)), row bits jr = i + 1 - 2^t
+    u64 lo_tile = 0;
+    if (p.l0) {
+      u32 col;
+      split_vidx(p, v0, lo_tile, col);
+    }
+    const u32 ntw = R - 1;
+    for (u32 u = tid; u < ntw * 4; u += NTT_THREADS) {
+      const u32 i = u >> 2, q = u & 3;
+      const u32 t = 31 - __clz(i + 1);
+      const u32 jr = i + 1 - (1u << t);
+      const u64 g = ((1ull << (p.l0 + t)) - 1) + ((u64)jr << p.l0) + lo_tile;
+      cp_async16(s_tw + i * 4 + q, p.tw + g * 4 + q);
+    }
+  }
+  cp_async_wait_all();
   __syncthreads();
 
   // ---- butterfly layers ----
@@ -321,7 +343,53 @@ __global__ void __launch_bounds__(NTT_THREADS, MINB) k_ntt_pass(const PassParams
         Fr x1 = fr_from_units(s_lo[e1], s_hi[e1]);
         Fr x2 = fr_from_units(s_lo[e2], s_hi[e2]);
         Fr x3 = fr_from_units(s_lo[e3], s_hi[e3]);
-        if constexpr (SH) {
+        if constexpr (SH && TWS) {
+          const u32 jr = b & tmask;
+          const uint4* tA = s_tw + (((1u << t) - 1) + jr) * 4;
+          const uint4* tB0 = s_tw + (((2u << t) - 1) + jr) * 4;
+          const uint4* tB1 = tB0 + (4u << t);
+          if (!p.dif) {
+            {
+              Tw twA;
+              twA.w = fr_lds(tA);
+              twA.wq = fr_lds(tA + 2);
+              bf_dit(x0, x1, twA);
+              bf_dit(x2, x3, twA);
+            }
+            {
+              Tw twB;
+              twB.w = fr_lds(tB0);
+              twB.wq = fr_lds(tB0 + 2);
+              bf_dit(x0, x2, twB);
+            }
+            {
+              Tw twB;
+              twB.w = fr_lds(tB1);
+              twB.wq = fr_lds(tB1 + 2);
+              bf_dit(x1, x3, twB);
+            }
+          } else {
+            {
+              Tw twB;
+              twB.w = fr_lds(tB0);
+              twB.wq = fr_lds(tB0 + 2);
+              bf_dif(x0, x2, twB);
+            }
+            {
+              Tw twB;
+              twB.w = fr_lds(tB1);
+              twB.wq = fr_lds(tB1 + 2);
+              bf_dif(x1, x3, twB);
+            }
+            {
+              Tw twA;
+              twA.w = fr_lds(tA);
+              twA.wq = fr_lds(tA + 2);
+              bf_dif(x0, x1, twA);
+              bf_dif(x2, x3, twA);
+            }
+          }
+        } else if constexpr (SH) {
           // 64-byte twiddle pairs: fetched right before their use, so that at most one is live beside the quartet
           if (!p.dif) {
             {
@@ -395,7 +463,14 @@ __global__ void __launch_bounds__(NTT_THREADS, MINB) k_ntt_pass(const PassParams
         split_vidx(p, v0 + vc, lo, col);
         j += lo;
       }
-      const Tw tw = tw_ldg<SH>(p.tw, tw_base + j);
+      Tw tw;
+      if constexpr (SH && TWS) {
+        const uint4* tp = s_tw + (((1u << t) - 1) + (b & tmask)) * 4;
+        tw.w = fr_lds(tp);
+        tw.wq = fr_lds(tp + 2);
+      } else {
+        tw = tw_ldg<SH>(p.tw, tw_base + j);
+      }
       Fr a = fr_from_units(s_lo[e0], s_hi[e0]);
       Fr bb = fr_from_units(s_lo[e1], s_hi[e1]);
       Fr o0 = a, o1 = bb;
@@ -485,6 +560,17 @@ static std::vector<PassPlan> plan_passes(u32 first, u32 last, size_t w) {
     out.push_back({first, 0, log_cv_for(((u64)w) << first)});
     return out;
   }
+  // Narrow matrices (w < 16: the column shard of one GPU when 16 trace columns are split over 4-8 GPUs): at l0 =
+  // first a tile row holds only w << first < 16 elements, so an evenly sized first pass would stage a tile of a
+  // few hundred elements for 256 threads.  Give that pass all the layers a full tile can hold instead (r = 10 at
+  // w = 2) and spread the remaining layers evenly.
+  if (log_cv_for(((u64)w) << first) < 4 && last - first > rmax_at(first)) {
+    const u32 r0 = rmax_at(first);
+    out.push_back({first, r0, log_cv_for(((u64)w) << first)});
+    std::vector<PassPlan> rest = plan_passes(first + r0, last, w);
+    out.insert(out.end(), rest.begin(), rest.end());
+    return out;
+  }
   // greedy count
   u32 n = 0;
   for (u32 l = first; l < last; n++) l += std::min(rmax_at(l), last - l);
@@ -521,7 +607,13 @@ static int launch_pass(eon_ctx* ctx, PassParams& p, const PassPlan& pl, unsigned
   u64 tiles_hi = 1ull << (log_n - pl.l0 - pl.r);
   u64 grid = tiles_hi * p.tiles_v;
   if (grid == 0 || grid > 0x7fffffffull) return fail(ctx, EON_ERR_BAD_ARG, "ntt: grid too large");
-  size_t smem = ((size_t)1 << (pl.r + pl.log_cv)) * 32 + 64;
+  size_t smem = ((size_t)1 << (pl.r + pl.log_cv)) * 32 + 128;
+  // twiddles in shared memory: fixed-operand form, and one twiddle set per tile (see k_ntt_pass)
+  static const int tws_env = getenv("EON_NTT_TWS") ? atoi(getenv("EON_NTT_TWS")) : 1;
+  const bool tws = p_shoup && tws_env && pl.r >= 1 &&
+                   (pl.l0 == 0 || (p.w_shift >= 0 && w >= ((size_t)1 << pl.log_cv)));
+  p.tw_smem = tws ? 1 : 0;
+  if (tws) smem += (((size_t)1 << pl.r) - 1) * 64;
   static int radix4 = -1;
   if (radix4 < 0) {
     const char* e = getenv("EON_NTT_RADIX4");
@@ -533,7 +625,7 @@ static int launch_pass(eon_ctx* ctx, PassParams& p, const PassPlan& pl, unsigned
     minb = e ? atoi(e) : (ntt_tile_elems() == 1024 ? 4 : 3);
   }
   if (!ctx->ntt_attr_set) {  // per context: the attribute belongs to the context's device
-    const int mx = (int)(NTT_TILE_MAX * 32 + 64);
+    const int mx = (int)(NTT_TILE_MAX * 32 + 128 + 2048 * 64);  // tile + (TWS) up to 2^11 - 1 twiddle pairs
     EON_CUDA(ctx, cudaFuncSetAttribute(k_ntt_pass<3, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
     EON_CUDA(ctx, cudaFuncSetAttribute(k_ntt_pass<4, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
     EON_CUDA(ctx, cudaFuncSetAttribute(k_ntt_pass<2, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
@@ -541,6 +633,8 @@ static int launch_pass(eon_ctx* ctx, PassParams& p, const PassPlan& pl, unsigned
     EON_CUDA(ctx, cudaFuncSetAttribute(k_ntt_pass<4, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
     EON_CUDA(ctx, cudaFuncSetAttribute(k_ntt_pass<3, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
     EON_CUDA(ctx, cudaFuncSetAttribute(k_ntt_pass<2, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+    EON_CUDA(ctx, cudaFuncSetAttribute(k_ntt_pass<3, true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+    EON_CUDA(ctx, cudaFuncSetAttribute(k_ntt_pass<2, true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
     ctx->ntt_attr_set = true;
   }
   if (p_shoup) {  // fixed-operand twiddles: radix-4 quartets only; 2 CTAs per SM unless EON_NTT_MINB asks for 3
@@ -549,7 +643,10 @@ static int launch_pass(eon_ctx* ctx, PassParams& p, const PassPlan& pl, unsigned
       const char* e = getenv("EON_NTT_MINB");
       minb_sh = e ? atoi(e) : 2;
     }
-    if (minb_sh >= 3) k_ntt_pass<3, true, true><<<(unsigned)grid, NTT_THREADS, smem, ctx->stream>>>(p);
+    if (tws) {
+      if (minb_sh >= 3) k_ntt_pass<3, true, true, true><<<(unsigned)grid, NTT_THREADS, smem, ctx->stream>>>(p);
+      else k_ntt_pass<2, true, true, true><<<(unsigned)grid, NTT_THREADS, smem, ctx->stream>>>(p);
+    } else if (minb_sh >= 3) k_ntt_pass<3, true, true><<<(unsigned)grid, NTT_THREADS, smem, ctx->stream>>>(p);
     else k_ntt_pass<2, true, true><<<(unsigned)grid, NTT_THREADS, smem, ctx->stream>>>(p);
   } else if (radix4) {
     if (minb >= 4) k_ntt_pass<4, true, false><<<(unsigned)grid, NTT_THREADS, smem, ctx->stream>>>(p);
