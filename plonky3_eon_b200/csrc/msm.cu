@@ -764,11 +764,11 @@ int msm_run(eon_ctx* ctx, const G1Affine* d_bases, const Fr* d_scalars, size_t n
     }
     const size_t h0 = (ncols + 1) / 2;
     cudaStream_t main_stream = ctx->stream;
-    // The second half is ordered after everything queued so far (the scalars are produced on the main stream) --
-    // and, staggered, after the SORT of the first half: two halves started together run in lockstep, their idle
-    // phases coincide and nothing is gained; half a phase apart, the inversion trees and the bucket reduction of
-    // one half fall under the pair rounds of the other.  EON_MSM_STAGGER=0: start together.
-    static const int stagger_env = getenv("EON_MSM_STAGGER") ? atoi(getenv("EON_MSM_STAGGER")) : 1;
+    // The second half is ordered after everything queued so far (the scalars are produced on the main stream).
+    // EON_MSM_STAGGER=1 starts it after the SORT of the first half instead, so that the halves do not run in
+    // lockstep; measured (profiles/r02h_stagger.txt) within noise of starting together: 7.23 vs 7.15 ms at 2
+    // columns, 12.32 vs 12.28 at 4 -- off by default.
+    static const int stagger_env = getenv("EON_MSM_STAGGER") ? atoi(getenv("EON_MSM_STAGGER")) : 0;
     if (stagger_env) ctx->ev_stagger = ctx->ev_split[0];
     else EON_CUDA(ctx, cudaEventRecord(ctx->ev_split[0], main_stream));
     int rc = msm_batch(ctx, bases, d_scalars, n, h0, ld, sh, d_out);

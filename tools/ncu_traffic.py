@@ -13,6 +13,7 @@ constant in bench.py.
 import csv
 import json
 import os
+import re
 import sys
 from collections import OrderedDict
 
@@ -28,8 +29,8 @@ def launches(path):
         if len(r) < len(hdr):
             continue
         rec = dict(zip(hdr, r))
-        name = rec["Kernel Name"].split("(")[0].split("<")[0].split("::")[-1].split()[-1]   # "void k_x<..>(..)" -> k_x
-        e = d.setdefault(int(rec["ID"]), {"name": name})
+        m = re.search(r"\b(k_[a-z0-9_]+)", rec["Kernel Name"])   # "void eon::k_x<..>(..)" -> k_x; other kernels as they are
+        e = d.setdefault(int(rec["ID"]), {"name": m.group(1) if m else rec["Kernel Name"][:40]})
         v = float(rec["Metric Value"].replace(",", ""))
         unit = rec.get("Metric Unit", "")
         if rec["Metric Name"].startswith("dram__bytes"):
