@@ -798,6 +798,24 @@ static std::vector<std::pair<size_t, size_t>> column_groups(size_t width, size_t
   return g;
 }
 
+// Column groups of the commit upload: groups of 4 columns (128-byte row pieces, >= 85 % of the contiguous PCIe rate),
+// at most 8 groups.  The transforms of a group (coset iDFT, and the hinted LDE on the auxiliary stream) run while
+// the next groups cross PCIe; ONE MSM over all columns follows.  Measured at 2^20 x 16 against the former scheme
+// (a small first group, then an MSM per group so that the MSM of group g hides the upload of group g + 1): the
+// upload (10 ms) now hides under the 9 ms of transforms instead, the MSM runs once at its 16-column efficiency and
+// without the LDE beside it.  EON_PIPE_MSM_PER_GROUP=1 restores the former scheme.
+static std::vector<std::pair<size_t, size_t>> upload_groups(size_t width, size_t bytes) {
+  std::vector<std::pair<size_t, size_t>> g;
+  if (width < 8 || bytes < ((size_t)32 << 20) || getenv("EON_NO_PIPELINE")) {
+    g.push_back(std::make_pair((size_t)0, width));
+    return g;
+  }
+  size_t gw = 4;
+  while ((width + gw - 1) / gw > 8) gw += 4;
+  for (size_t c0 = 0; c0 < width; c0 += gw) g.push_back(std::make_pair(c0, std::min(gw, width - c0)));
+  return g;
+}
+
 static int pipe_init(eon_ctx* ctx) {
   if (ctx->copy_stream && ctx->copy_stream2 && ctx->aux_stream && ctx->prio_stream && ctx->ev_pipe[19]) return EON_OK;
   if (!ctx->copy_stream) EON_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
@@ -837,7 +855,9 @@ static int kzg_commit_host(eon_ctx* ctx, const uint64_t* h_evals, size_t h_ld_in
   if (b && !h_evals) return fail(ctx, EON_ERR_BAD_ARG, "null evals");
   void* d_in = nullptr;
   EON_TRY(scratch_get(ctx, SC_IO_A, b + 32, &d_in));
-  auto groups = column_groups(width, b, true);
+  static const int per_group_env = getenv("EON_PIPE_MSM_PER_GROUP") ? atoi(getenv("EON_PIPE_MSM_PER_GROUP")) : 0;
+  const bool msm_per_group = per_group_env != 0;
+  auto groups = msm_per_group ? column_groups(width, b, true) : upload_groups(width, b);
   if (groups.size() == 1 && !want_lde) {
     if (b && h_ld_in == width) EON_CUDA(ctx, cudaMemcpyAsync(d_in, h_evals, b, cudaMemcpyHostToDevice, ctx->stream));
     else if (b)
@@ -872,8 +892,8 @@ static int kzg_commit_host(eon_ctx* ctx, const uint64_t* h_evals, size_t h_ld_in
   if (rc == EON_OK && want_lde) rc = scratch_get(ctx, SC_IO_B, mat_bytes(lde_log_size, width) + 32, &d_lde);
   const size_t pitch = width * sizeof(Fr);
   // earlier work on the compute stream may still read d_in (same scratch): copies wait for it
-  if (rc == EON_OK && cudaEventRecord(ctx->ev_pipe[7], ctx->stream) != cudaSuccess) rc = fail(ctx, EON_ERR_CUDA, "event");
-  if (rc == EON_OK) cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_pipe[7], 0);
+  if (rc == EON_OK && cudaEventRecord(ctx->ev_pipe[17], ctx->stream) != cudaSuccess) rc = fail(ctx, EON_ERR_CUDA, "event");
+  if (rc == EON_OK) cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_pipe[17], 0);
   for (size_t g = 0; rc == EON_OK && g < groups.size(); g++) {
     const size_t c0 = groups[g].first, gw = groups[g].second;
     cudaError_t e = cudaMemcpy2DAsync((Fr*)d_in + c0, pitch, (const Fr*)h_evals + c0, hpitch_in, gw * sizeof(Fr), h,
@@ -900,8 +920,11 @@ static int kzg_commit_host(eon_ctx* ctx, const uint64_t* h_evals, size_t h_ld_in
     // (no priority inversion here, unlike the device-resident entry point: with host buffers the LDE has to finish
     // EARLY, its 2^lde_log_size x width download is the long pole and hides under the MSM; measured at 2^20 x 16:
     // 52.9 ms this way, 64.2 ms with the MSM on the high-priority stream)
-    if (rc == EON_OK) rc = msm_run(ctx, ctx->d_srs, d_coeffs + c0, h, gw, width, (G1Affine*)d_commit + c0);
+    if (rc == EON_OK && msm_per_group)
+      rc = msm_run(ctx, ctx->d_srs, d_coeffs + c0, h, gw, width, (G1Affine*)d_commit + c0);
   }
+  // one MSM over all columns, after the last group's iDFT (the uploads and the LDE downloads are long under way)
+  if (rc == EON_OK && !msm_per_group) rc = msm_run(ctx, ctx->d_srs, d_coeffs, h, width, width, (G1Affine*)d_commit);
   if (rc == EON_OK) {
     cudaError_t e = cudaMemcpyAsync(h_commit_xy, d_commit, width * sizeof(G1Affine), cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);

@@ -1,4 +1,11 @@
-"""Multi-GPU sharding of the KZG hot path (one process per GPU, torch.distributed for plumbing).
+"""Multi-GPU sharding of the KZG hot path for ONE-PROCESS-PER-GPU callers (torch.distributed for plumbing).
+
+A single process that owns several GPUs needs none of this: `MultiContext` (lib.py; `eon_mctx_*` in
+include/eon_kzg.h, csrc/multi.cu) takes whole host matrices and shards them inside the library.  The helpers here
+are the same two axes for a launcher that already runs one rank per GPU (torchrun), each a thin caller of the C ABI:
+`eon_kzg_commit[_lde]_ld` on this rank's columns of the shared host matrix, and for a lone MSM
+`eon_srs_set_range_tables` + `eon_msm_srs_range_partial_dev` + ncclAllGather + `eon_g1_sum_cols_dev` (partial sums
+never leave the devices).
 
 The reference has no distributed layer; the path shards along two independent axes
 (SURVEY §8e), neither of which needs a data-path collective:
@@ -57,6 +64,31 @@ class GpuBackend:
         self.ctx.call("eon_g1_sum", p, p.shape[0], out)
         return out
 
+    # -- device path of the index-range MSM: partial sums stay in HBM between the MSM, the all_gather and the add --
+    def msm_partial_device(self, scalars, first, n, ncols, device):
+        """Partial sums of this rank's shard as an int64 tensor [ncols * 8] on `device` (window tables sized for
+        the shard are built on first use)."""
+        import ctypes as C
+
+        import torch
+        if n >= (1 << 14) and getattr(self, "_range", None) != (first, n):
+            self.ctx.call("eon_srs_set_range_tables", first, n, 0)
+            self._range = (first, n)
+        d_sc = torch.from_numpy(np.ascontiguousarray(scalars, dtype=np.uint64).view(np.int64)).to(device)
+        part = torch.zeros(ncols * 8, dtype=torch.int64, device=device)
+        torch.cuda.current_stream(device).synchronize()      # the context may run on another stream
+        self.ctx.call("eon_msm_srs_range_partial_dev", C.c_void_p(d_sc.data_ptr()), first, n, ncols, ncols,
+                      C.c_void_p(part.data_ptr()))
+        self.ctx.sync()
+        return part
+
+    def sum_cols_device(self, parts, nparts, ncols):
+        """parts: int64 tensor [nparts * ncols * 8] on the device -> uint64 [ncols, 8] on the host."""
+        import ctypes as C
+        out = np.zeros((ncols, 8), dtype=np.uint64)
+        self.ctx.call("eon_g1_sum_cols_dev", C.c_void_p(parts.data_ptr()), nparts, ncols, out)
+        return out
+
 
 def _all_gather_u64(arr, group=None, device=None):
     """all_gather of a uint64 numpy array (same shape on every rank) -> list of arrays, rank order."""
@@ -74,6 +106,15 @@ def _all_gather_u64(arr, group=None, device=None):
 def sharded_msm(backend, scalars_local, first, n_local, ncols, group=None, device=None):
     """Index-range sharded MSM.  Every rank passes its own scalar rows [first, first + n_local) and
     gets the full result [ncols, 8] (identical on all ranks)."""
+    if hasattr(backend, "msm_partial_device") and device is not None and getattr(device, "type", "") == "cuda":
+        import torch
+        import torch.distributed as dist
+        world = dist.get_world_size(group)
+        part = backend.msm_partial_device(scalars_local, first, n_local, ncols, device)
+        allp = torch.empty(world * ncols * 8, dtype=torch.int64, device=device)
+        dist.all_gather_into_tensor(allp, part, group=group)    # NCCL over NVLink: world x ncols x 64 bytes
+        torch.cuda.current_stream(device).synchronize()
+        return backend.sum_cols_device(allp, world, ncols)
     partial = backend.msm_srs_range(scalars_local, first, n_local, ncols)
     parts = _all_gather_u64(partial, group, device)            # world x [ncols, 8]
     out = np.zeros((ncols, 8), dtype=np.uint64)
