@@ -360,4 +360,181 @@ class GpuKzgPcs {
   Context ctx_;
 };
 
+// ---- the same Pcs over ONE multi-device context (eon_mctx_*): the compiled twin of rust/p3-eon-gpu/src/pcs.rs -------
+// Whole host matrices in, the library shards their columns over its GPUs.  `commit` can carry the LDE hint,
+// `commit_quotient` is the single batched call (no split_evals upload), `open` is ONE eon_mctx_kzg_open_batch whose
+// flat [matrix][point][column] results are cut back into the nested OpenedValues / KzgProof.
+class MultiContext {
+ public:
+  explicit MultiContext(const std::vector<int>& devices) {
+    eon_mctx* m = nullptr;
+    int rc = eon_mctx_create(devices.data(), (int)devices.size(), &m);
+    if (rc != EON_OK) throw EonError(rc, "eon_mctx_create failed (no sm_100 device? there is no CPU fallback)");
+    m_ = std::shared_ptr<eon_mctx>(m, [](eon_mctx* p) { eon_mctx_destroy(p); });
+  }
+  eon_mctx* raw() const { return m_.get(); }
+  void check(int rc) const {
+    if (rc == EON_OK) return;
+    std::string msg = eon_mctx_last_error(m_.get());
+    if (rc == EON_ERR_SRS_TOO_SHORT) throw DegreeTooLarge(rc, msg);
+    throw EonError(rc, msg);
+  }
+
+ private:
+  std::shared_ptr<eon_mctx> m_;
+};
+
+struct MultiMatrixProverData {
+  Domain domain;
+  RowMajorMatrix evals;
+  std::shared_ptr<eon_handle> handle;
+  std::shared_ptr<std::pair<Domain, RowMajorMatrix>> lde;  // produced inside commit() under an LDE hint
+};
+using MultiProverData = std::vector<MultiMatrixProverData>;
+
+class MultiGpuKzgPcs {
+ public:
+  static MultiGpuKzgPcs new_unsafe(MultiContext ctx, size_t max_degree, const Fr& alpha) {
+    ctx.check(eon_mctx_srs_generate_unsafe(ctx.raw(), GpuDft::wire(alpha), max_degree + 1));
+    return MultiGpuKzgPcs(std::move(ctx));
+  }
+  // eon-uni-stark/src/prover.rs:186-187 then :307-322: the prover evaluates every committed trace on the quotient
+  // coset right away; with the hint commit() produces that matrix in the same call
+  MultiGpuKzgPcs with_lde_hint(unsigned added_bits, const Fr& shift) const {
+    MultiGpuKzgPcs r = *this;
+    r.hint_ = true;
+    r.hint_bits_ = added_bits;
+    r.hint_shift_ = shift;
+    return r;
+  }
+
+  std::pair<KzgCommitment, MultiProverData> commit(std::vector<std::pair<Domain, RowMajorMatrix>> evaluations) const {
+    KzgCommitment commitment;
+    MultiProverData prover;
+    for (auto& de : evaluations) {
+      const Domain& domain = de.first;
+      RowMajorMatrix& evals = de.second;
+      if (evals.height() != domain.size()) throw std::logic_error("evaluation height must match domain size");
+      MatrixCommitment mc;
+      mc.columns.resize(evals.width());
+      eon_handle h = 0;
+      std::shared_ptr<std::pair<Domain, RowMajorMatrix>> lde;
+      if (hint_ && evals.width() > 0) {
+        Domain ld(hint_shift_, domain.log_size + hint_bits_);
+        RowMajorMatrix out(std::vector<Fr>(ld.size() * evals.width()), evals.width());
+        ctx_.check(eon_mctx_kzg_commit_lde(ctx_.raw(), evals.wire(), domain.log_size, evals.width(),
+                                           GpuDft::wire(domain.shift), reinterpret_cast<uint64_t*>(mc.columns.data()), &h,
+                                           ld.log_size, GpuDft::wire(ld.shift), out.wire()));
+        lde = std::make_shared<std::pair<Domain, RowMajorMatrix>>(ld, std::move(out));
+      } else {
+        ctx_.check(eon_mctx_kzg_commit(ctx_.raw(), evals.wire(), domain.log_size, evals.width(),
+                                       GpuDft::wire(domain.shift), reinterpret_cast<uint64_t*>(mc.columns.data()), &h));
+      }
+      commitment.matrices.push_back(std::move(mc));
+      prover.push_back(MultiMatrixProverData{domain, std::move(evals), own(h), lde});
+    }
+    return {std::move(commitment), std::move(prover)};
+  }
+
+  // override of the trait default (commit/src/pcs.rs:82-102): one call, chunk i = rows i, i + c, ... of the matrix
+  std::pair<KzgCommitment, MultiProverData> commit_quotient(const Domain& quotient_domain, const RowMajorMatrix& evals,
+                                                            size_t num_chunks) const {
+    const unsigned log_chunks = log2_strict(num_chunks);
+    if (evals.height() != quotient_domain.size()) throw std::logic_error("evaluation height must match domain size");
+    const size_t w = evals.width();
+    std::vector<G1> cols(num_chunks * w);
+    std::vector<eon_handle> hs(num_chunks, 0);
+    ctx_.check(eon_mctx_kzg_commit_quotient(ctx_.raw(), evals.wire(), quotient_domain.log_size, w, log_chunks,
+                                            GpuDft::wire(quotient_domain.shift), reinterpret_cast<uint64_t*>(cols.data()),
+                                            hs.data()));
+    auto doms = quotient_domain.split_domains(num_chunks);
+    auto subs = quotient_domain.split_evals(num_chunks, evals);
+    KzgCommitment commitment;
+    MultiProverData prover;
+    for (size_t i = 0; i < num_chunks; i++) {
+      MatrixCommitment mc;
+      mc.columns.assign(cols.begin() + i * w, cols.begin() + (i + 1) * w);
+      commitment.matrices.push_back(std::move(mc));
+      prover.push_back(MultiMatrixProverData{doms[i], std::move(subs[i]), own(hs[i]), nullptr});
+    }
+    return {std::move(commitment), std::move(prover)};
+  }
+
+  RowMajorMatrix get_evaluations_on_domain(const MultiProverData& pd, size_t idx, const Domain& domain) const {
+    const MultiMatrixProverData& m = pd.at(idx);
+    if (m.domain.shift == domain.shift && m.domain.log_size == domain.log_size) return m.evals;
+    if (m.lde && m.lde->first.shift == domain.shift && m.lde->first.log_size == domain.log_size) return m.lde->second;
+    RowMajorMatrix out(std::vector<Fr>(domain.size() * m.evals.width()), m.evals.width());
+    ctx_.check(eon_mctx_kzg_evals_on_coset(ctx_.raw(), *m.handle, domain.log_size, GpuDft::wire(domain.shift), out.wire()));
+    return out;
+  }
+
+  std::pair<OpenedValues, KzgProof> open(
+      const std::vector<std::pair<const MultiProverData*, std::vector<std::vector<Fr>>>>& rounds) const {
+    std::vector<eon_handle> handles;
+    std::vector<size_t> npoints, widths;
+    std::vector<Fr> points;
+    for (const auto& rd : rounds) {
+      if (rd.first->size() != rd.second.size()) throw std::logic_error("one list of points per matrix");
+      for (size_t mi = 0; mi < rd.first->size(); mi++) {
+        handles.push_back(*(*rd.first)[mi].handle);
+        npoints.push_back(rd.second[mi].size());
+        widths.push_back((*rd.first)[mi].evals.width());
+        points.insert(points.end(), rd.second[mi].begin(), rd.second[mi].end());
+      }
+    }
+    size_t total = 0;
+    for (size_t i = 0; i < handles.size(); i++) total += npoints[i] * widths[i];
+    std::vector<Fr> vals(total ? total : 1);
+    std::vector<G1> wits(total ? total : 1);
+    if (!handles.empty())
+      ctx_.check(eon_mctx_kzg_open_batch(ctx_.raw(), handles.size(), handles.data(), npoints.data(),
+                                         reinterpret_cast<const uint64_t*>(points.data()),
+                                         reinterpret_cast<uint64_t*>(vals.data()), reinterpret_cast<uint64_t*>(wits.data())));
+    OpenedValues values;
+    KzgProof proof;
+    size_t k = 0, i = 0;
+    for (const auto& rd : rounds) {
+      std::vector<std::vector<std::vector<Fr>>> mv;
+      std::vector<std::vector<std::vector<G1>>> mp;
+      for (size_t mi = 0; mi < rd.first->size(); mi++, i++) {
+        const size_t w = widths[i], np = npoints[i];
+        std::vector<std::vector<Fr>> pv;
+        std::vector<std::vector<G1>> pw;
+        for (size_t p = 0; p < np; p++) {
+          pv.emplace_back(vals.begin() + k + p * w, vals.begin() + k + (p + 1) * w);
+          pw.emplace_back(wits.begin() + k + p * w, wits.begin() + k + (p + 1) * w);
+        }
+        k += np * w;
+        mv.push_back(std::move(pv));
+        mp.push_back(std::move(pw));
+      }
+      values.push_back(std::move(mv));
+      proof.rounds.push_back(std::move(mp));
+    }
+    return {std::move(values), std::move(proof)};
+  }
+
+  RowMajorMatrix coset_lde_batch(const RowMajorMatrix& m, unsigned added_bits, const Fr& shift) const {
+    const unsigned log_h = log2_strict(m.height());
+    RowMajorMatrix out(std::vector<Fr>((m.height() << added_bits) * m.width()), m.width());
+    ctx_.check(eon_mctx_coset_lde_batch(ctx_.raw(), m.wire(), out.wire(), log_h, m.width(), added_bits, GpuDft::wire(shift)));
+    return out;
+  }
+
+ private:
+  explicit MultiGpuKzgPcs(MultiContext ctx) : ctx_(std::move(ctx)) {}
+  std::shared_ptr<eon_handle> own(eon_handle h) const {
+    MultiContext keep = ctx_;
+    return std::shared_ptr<eon_handle>(new eon_handle(h), [keep](eon_handle* p) {
+      eon_mctx_handle_free(keep.raw(), *p);
+      delete p;
+    });
+  }
+  MultiContext ctx_;
+  bool hint_ = false;
+  unsigned hint_bits_ = 0;
+  Fr hint_shift_ = Fr::one();
+};
+
 }  // namespace p3eon

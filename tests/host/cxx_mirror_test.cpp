@@ -168,6 +168,46 @@ static void test_commit_quotient(const Context& ctx) {
   }
 }
 
+// The PCS call sequence of eon_uni_stark::prove (prover.rs:186-187, 307-322, 371-372, 416-442) through the
+// single-device mirror and through the multi-device one (device 0 listed twice: two column shards): identical
+// commitments, evaluations, opened values and witnesses.
+static void test_multi_device_sequence(const Context& ctx) {
+  const unsigned log_h = 10;
+  const size_t h = 1u << log_h, w = 5;
+  std::mt19937_64 rng(11);
+  std::vector<Fr> v(h * w), qv(2 * h);
+  for (auto& x : v) x = random_fr(rng);
+  for (auto& x : qv) x = random_fr(rng);
+  Domain dom(Fr::one(), log_h);
+  Domain qdom = dom.create_disjoint_domain(2 * h);
+  const Fr zeta = random_fr(rng);
+  const Fr zeta_next = dom.next_point(zeta);
+
+  GpuKzgPcs one = GpuKzgPcs::new_unsafe(ctx, 2 * h - 1, fr(12345));
+  auto [c1, pd1] = one.commit({{dom, RowMajorMatrix(v, w)}});
+  RowMajorMatrix lde1 = one.get_evaluations_on_domain(pd1, 0, qdom);
+  auto [qc1, qpd1] = one.commit_quotient(qdom, RowMajorMatrix(qv, 1), 2);
+  auto [ov1, pr1] = one.open({{&pd1, {{zeta, zeta_next}}}, {&qpd1, {{zeta}, {zeta}}}});
+
+  MultiGpuKzgPcs many = MultiGpuKzgPcs::new_unsafe(MultiContext({0, 0}), 2 * h - 1, fr(12345)).with_lde_hint(1, fr_generator());
+  auto [c2, pd2] = many.commit({{dom, RowMajorMatrix(v, w)}});
+  RowMajorMatrix lde2 = many.get_evaluations_on_domain(pd2, 0, qdom);
+  auto [qc2, qpd2] = many.commit_quotient(qdom, RowMajorMatrix(qv, 1), 2);
+  auto [ov2, pr2] = many.open({{&pd2, {{zeta, zeta_next}}}, {&qpd2, {{zeta}, {zeta}}}});
+
+  CHECK(c1.matrices[0].columns == c2.matrices[0].columns);
+  CHECK(lde1.values == lde2.values);
+  CHECK(many.coset_lde_batch(RowMajorMatrix(v, w), 1, fr_generator()).values == lde1.values);
+  CHECK(qc1.matrices.size() == 2 && qc2.matrices.size() == 2);
+  for (int i = 0; i < 2; i++) CHECK(qc1.matrices[i].columns == qc2.matrices[i].columns);
+  CHECK(ov1 == ov2);
+  CHECK(pr1.rounds.size() == 2 && pr2.rounds.size() == 2);
+  for (size_t r = 0; r < pr1.rounds.size(); r++) CHECK(pr1.rounds[r] == pr2.rounds[r]);
+  // a domain the hint does not cover still goes through eon_mctx_kzg_evals_on_coset
+  Domain other(fr(7), log_h + 1);
+  CHECK(one.get_evaluations_on_domain(pd1, 0, other).values == many.get_evaluations_on_domain(pd2, 0, other).values);
+}
+
 int main() {
   try {
     Context ctx(0);
@@ -177,6 +217,7 @@ int main() {
     test_pcs_roundtrip(ctx);
     test_guards(ctx);
     test_commit_quotient(ctx);
+    test_multi_device_sequence(ctx);
   } catch (const std::exception& e) {
     std::printf("FAIL: exception %s\n", e.what());
     return 2;
