@@ -646,6 +646,7 @@ def run_eon(args):
     rounds_commit = int(ctx.lib.eon_msm_rounds_used(ctx.h))
 
     # ---- host-buffer legs -------------------------------------------------------------------------------------------
+    ms_rowblock = None
     if args.no_e2e:
         ms_e2e = ms_e2e2 = None
     else:
@@ -659,9 +660,42 @@ def run_eon(args):
         ms_e2e2 = H.timed(step_e2e_two_calls, args.steps)
         ok = ok and bool(np.array_equal(commits, commits_first))
         parity["e2e_eq_device"] = H.all_ok(ok)
+        # few columns per rank: contiguous row blocks over PCIe, the column <-> row exchange over NVLink
+        if world > 1 and cols <= args.rowblock_max_cols and rows % world == 0 and cols_total % world == 0:
+            from plonky3_eon_b200 import dist as edist
+            rb_pipe = edist.RowBlockCommitLde(ctx, log_rows, cols_total, ab, H.dev)
+            lde_pin.zero_()
+
+            def step_e2e_rowblock():
+                h = rb_pipe.step(host_pin, lde_pin, shift_one, shift_lde, commits)
+                ctx.call("eon_handle_free", h)
+                gather_commits()
+            for _ in range(max(1, args.warmup)):
+                step_e2e_rowblock()
+            ms_rowblock = H.timed(step_e2e_rowblock, args.steps)
+            torch.cuda.synchronize()
+            ok = bool(np.array_equal(commits, commits_first))
+            sums = rb_pipe.shard_checksums()                                   # [dest rank] of my columns
+            all_sums = torch.empty(world * world, dtype=torch.int64, device=H.dev)
+            H.dist.all_gather_into_tensor(all_sums, sums)
+            all_sums = all_sums.view(world, world).cpu().numpy()              # [src rank][dest rank]
+            lrb = (rows << ab) // world
+            mine = lde_pin.numpy()[rank * lrb:(rank + 1) * lrb]                 # my row block, all columns
+            for j in range(world):
+                a, b_ = column_shard(cols_total, world, j)
+                with np.errstate(over="ignore"):
+                    got = np.int64(mine[:, a:b_].sum(dtype=np.int64))
+                ok = ok and bool(got == all_sums[j][rank])
+            ok = ok and bool(np.array_equal(mine[:, c0:c1].view(np.uint64),
+                                            d_lde[rank * lrb:(rank + 1) * lrb].cpu().numpy().view(np.uint64)))
+            parity["rowblock_e2e_eq_device"] = H.all_ok(ok)
+            del rb_pipe
 
     units = rows * cols_total * args.steps
     value = units / (ms_dev * 1e-3)
+    ms_e2e_strided = ms_e2e
+    if ms_rowblock is not None and ms_rowblock < ms_e2e:
+        ms_e2e = ms_rowblock           # the faster transport is what a caller would use at this shard width
     e2e_value = units / (ms_e2e * 1e-3) if ms_e2e else None
 
     # ---- open: KzgPcs::open of the committed trace at (zeta, zeta * omega) ----------------------------------------
@@ -839,8 +873,13 @@ def run_eon(args):
             "value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
             "h2d_bytes_per_step": rows * cols_total * 32, "d2h_bytes_per_step": (rows << ab) * cols_total * 32 + cols_total * 64,
             "bytes_are": "whole job (all ranks); every rank moves its columns of the one host matrix",
-            "call": "eon_kzg_commit_lde_ld (Pcs::commit with an LDE hint) on this rank's columns of the pinned host "
-                    "matrix, LDE columns written back into the pinned host result",
+            "call": ("plonky3_eon_b200.dist.RowBlockCommitLde: contiguous row blocks over PCIe, all_to_all over NVLink, "
+                     "eon_coset_lde_batch_dev + eon_kzg_commit_dev on this rank's columns"
+                     if (ms_rowblock is not None and ms_rowblock == ms_e2e) else
+                     "eon_kzg_commit_lde_ld (Pcs::commit with an LDE hint) on this rank's columns of the pinned host "
+                     "matrix, LDE columns written back into the pinned host result"),
+            "strided_ms_per_step": ms_e2e_strided / args.steps,
+            "rowblock_ms_per_step": (ms_rowblock / args.steps) if ms_rowblock is not None else None,
             "two_calls_ms_per_step": ms_e2e2 / args.steps, "two_calls_value": units / (ms_e2e2 * 1e-3),
             "two_calls": "eon_kzg_commit_ld then eon_kzg_evals_on_coset_ld (unhinted Pcs::commit + "
                          "get_evaluations_on_domain)"},
@@ -986,6 +1025,8 @@ def main():
     ap.add_argument("--no-weak", action="store_true", help="N > 1: skip the weak-scaling side number")
     ap.add_argument("--no-mctx", action="store_true", help="skip the one-process multi-device-context leg")
     ap.add_argument("--mctx-devices", type=int, default=0, help="GPUs the multi-device-context leg drives (default: N)")
+    ap.add_argument("--rowblock-max-cols", type=int, default=4,
+                    help="N > 1: columns per rank up to which the e2e leg also tries the row-block transport")
     ap.add_argument("--msm-log-n", type=int, default=24, help="standalone MSM side leg: log2 points (0 = skip)")
     ap.add_argument("--check-e2e", action="store_true", help="also compare the fused and two-call device LDE bytes")
     ap.add_argument("--warmup-ref", type=int, default=0,

@@ -145,3 +145,72 @@ def sharded_commit(pcs, domain, evals_local, width, group=None, device=None):
     (commitment [width, 8] on every rank, this rank's MatrixProverData)."""
     commit, pdata = pcs.commit([(domain, evals_local)])
     return gather_column_commitments(commit[0], width, group, device), pdata[0]
+
+
+class RowBlockCommitLde:
+    """Host-buffer `commit` + hinted LDE of ONE row-major host matrix over N ranks that own FEW columns each.
+
+    With 2 columns per rank (16 trace columns over 8 GPUs) the strided copies of the `_ld` entry points move
+    64-byte row pieces, and the LDE download — the long pole of the step, and the transfer the host serves slowest
+    when every GPU copies at once — reaches two thirds of the contiguous rate at best.  Here every rank moves
+    CONTIGUOUS row blocks over PCIe and the column <-> row exchange happens over NVLink (two `all_to_all`s, the path's
+    one real exchange step, SURVEY §8e "row-block H2D + NVLink all-to-all"):
+
+        host rows [r h/N, (r+1) h/N) x W  --H2D-->  pack by destination  --all_to_all-->  all rows of my W/N columns
+        coset LDE of my columns (queued first: its way back is the long pole)
+        LDE [2h x W/N]  --all_to_all (row chunks)-->  my row block of every column shard  --unpack-->  --D2H--> host rows
+        KzgPcs::commit of my columns (coset iDFT + MSM) meanwhile, on the main stream
+
+    Results are the same bytes as `eon_kzg_commit_lde` on the whole matrix: every column goes through the same
+    `eon_coset_lde_batch_dev` / `eon_kzg_commit_dev` calls, only the transport differs.
+    """
+
+    def __init__(self, ctx, log_rows, cols_total, added_bits, device, group=None):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist, self.ctx, self.group, self.device = torch, dist, ctx, group, device
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        rows = 1 << log_rows
+        if rows % self.world or cols_total % self.world:
+            raise ValueError("rows and columns must divide evenly over the ranks")
+        self.log_rows, self.ab, self.W = log_rows, added_bits, cols_total
+        self.w, self.rb, self.lrb = cols_total // self.world, rows // self.world, (rows << added_bits) // self.world
+        i64 = torch.int64
+        self.d_blk = torch.empty((self.rb, cols_total, 4), dtype=i64, device=device)
+        self.d_send = torch.empty((self.world, self.rb, self.w, 4), dtype=i64, device=device)
+        self.d_evals = torch.empty((rows, self.w, 4), dtype=i64, device=device)
+        self.d_lde = torch.empty((rows << added_bits, self.w, 4), dtype=i64, device=device)
+        self.d_lrecv = torch.empty((self.world, self.lrb, self.w, 4), dtype=i64, device=device)
+        self.d_lout = torch.empty((self.lrb, cols_total, 4), dtype=i64, device=device)
+        self.side = torch.cuda.Stream(device)
+        self.ev = torch.cuda.Event()
+
+    def step(self, host_evals, host_lde, shift_wire, lde_shift_wire, commits_out):
+        """host_evals / host_lde: pinned int64 tensors [rows, W, 4] / [rows << ab, W, 4] (the whole matrices);
+        commits_out: uint64 numpy [W/N, 8].  Returns the prover-data handle of this rank's columns."""
+        import ctypes as C
+        torch, dist = self.torch, self.dist
+        main = torch.cuda.current_stream(self.device)
+        r0 = self.rank * self.rb
+        self.d_blk.copy_(host_evals[r0:r0 + self.rb], non_blocking=True)                       # contiguous H2D
+        self.d_send.copy_(self.d_blk.view(self.rb, self.world, self.w, 4).permute(1, 0, 2, 3))  # pack by destination
+        dist.all_to_all_single(self.d_evals.view(-1), self.d_send.view(-1), group=self.group)   # rows of MY columns
+        self.ctx.call("eon_coset_lde_batch_dev", C.c_void_p(self.d_evals.data_ptr()), C.c_void_p(self.d_lde.data_ptr()),
+                      self.log_rows, self.w, self.ab, lde_shift_wire)                            # queued, not synchronised
+        self.ev.record(main)
+        with torch.cuda.stream(self.side):
+            self.side.wait_event(self.ev)
+            dist.all_to_all_single(self.d_lrecv.view(-1), self.d_lde.view(-1), group=self.group)  # row chunks out
+            self.d_lout.copy_(self.d_lrecv.permute(1, 0, 2, 3).reshape(self.lrb, self.W, 4))     # [row][shard][col]
+            l0 = self.rank * self.lrb
+            host_lde[l0:l0 + self.lrb].copy_(self.d_lout, non_blocking=True)                     # contiguous D2H
+        h = C.c_uint64(0)
+        self.ctx.call("eon_kzg_commit_dev", C.c_void_p(self.d_evals.data_ptr()), self.log_rows, self.w, shift_wire,
+                      commits_out, C.byref(h))                                                   # coset iDFT + MSM
+        main.wait_stream(self.side)
+        return h
+
+    def shard_checksums(self):
+        """Sum (mod 2^64) of every destination rank's row chunk of this rank's LDE columns: what the receiving rank
+        must find in its host block (parity of the transport)."""
+        return self.d_lde.view(self.world, -1).sum(dim=1)
