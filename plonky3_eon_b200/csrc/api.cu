@@ -106,6 +106,11 @@ void eon_ctx_destroy(eon_ctx* ctx) {
     for (auto& s : bank)
       if (s.ptr) cudaFree(s.ptr);
   if (ctx->split_stream) cudaStreamDestroy(ctx->split_stream);
+  for (int b = 0; b < 2; b++) {
+    if (ctx->tiny_stream[b]) cudaStreamDestroy(ctx->tiny_stream[b]);
+    for (cudaEvent_t e : ctx->ev_tiny[b])
+      if (e) cudaEventDestroy(e);
+  }
   for (cudaEvent_t e : ctx->ev_split)
     if (e) cudaEventDestroy(e);
   for (auto& kv : ctx->twiddles) cudaFree(kv.second);
@@ -824,7 +829,8 @@ static int pipe_init(eon_ctx* ctx) {
   if (!ctx->prio_stream) {
     int least = 0, greatest = 0;
     EON_CUDA(ctx, cudaDeviceGetStreamPriorityRange(&least, &greatest));
-    EON_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->prio_stream, cudaStreamNonBlocking, greatest));
+    // one level below the top: the top is kept for the single-warp phases of a split MSM (msm_run)
+    EON_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->prio_stream, cudaStreamNonBlocking, greatest < least ? greatest + 1 : greatest));
   }
   for (auto& e : ctx->ev_pipe)
     if (!e) EON_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));

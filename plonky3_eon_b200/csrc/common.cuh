@@ -135,6 +135,12 @@ struct eon_ctx {
   cudaStream_t split_stream = nullptr;  // second half-batch of an MSM over few columns (msm_run), high priority
   cudaEvent_t ev_split[2] = {nullptr, nullptr};
   cudaEvent_t ev_stagger = nullptr;     // set by msm_run for ONE msm_batch: recorded after that batch's sort
+  // While two half-batches share the GPU, the single-warp phases of one half (inversion trees, bucket reduction)
+  // would queue behind the wide grids of the other; they run on a stream of the HIGHEST priority (one per half),
+  // the wide kernels one level below (tiny_on: set by msm_run around the two msm_batch calls).
+  cudaStream_t tiny_stream[2] = {nullptr, nullptr};
+  cudaEvent_t ev_tiny[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
+  bool tiny_on = false;
   int msm_split_mode = -1;              // -1 automatic (2..4 columns, >= 2^16 points), 0 never, 1 whenever >= 2 columns
   cudaEvent_t ev_pipe[20] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
                              nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -200,6 +206,22 @@ inline int scratch_get(eon_ctx* ctx, int id, size_t bytes, void** out) {
   }
   *out = s.ptr;
   return EON_OK;
+}
+
+// Latency-critical launches of an MSM (see eon_ctx::tiny_stream): tiny_begin() returns the stream to launch them on
+// (ordered after what ctx->stream has queued so far), tiny_end() orders ctx->stream after them.  Without a split
+// in flight both are no-ops on ctx->stream.
+inline cudaStream_t tiny_begin(eon_ctx* ctx) {
+  if (!ctx->tiny_on) return ctx->stream;
+  cudaStream_t ts = ctx->tiny_stream[ctx->bank];
+  cudaEventRecord(ctx->ev_tiny[ctx->bank][0], ctx->stream);
+  cudaStreamWaitEvent(ts, ctx->ev_tiny[ctx->bank][0], 0);
+  return ts;
+}
+inline void tiny_end(eon_ctx* ctx) {
+  if (!ctx->tiny_on) return;
+  cudaEventRecord(ctx->ev_tiny[ctx->bank][1], ctx->tiny_stream[ctx->bank]);
+  cudaStreamWaitEvent(ctx->stream, ctx->ev_tiny[ctx->bank][1], 0);
 }
 
 inline cudaEvent_t phase_event(eon_ctx* ctx) {

@@ -695,12 +695,14 @@ static int msm_batch(eon_ctx* ctx, const G1Affine* d_bases, const Fr* d_scalars,
     else k_bucket_rowcol<8><<<grid, 128, 0, st>>>((const G1Xyzz*)p_bkt, logL, logH, nseg, rows, cols);
     EON_LAUNCHED(ctx);
     const unsigned bt = std::min<unsigned>(BW_THREADS, std::max(32u, 1u << logL));
-    k_bucket_weighted<<<(unsigned)(2 * nseg), bt, 0, st>>>(rows, cols, logL, logH, parts);
+    cudaStream_t ts = tiny_begin(ctx);  // three single-CTA-per-segment launches in a dependent chain
+    k_bucket_weighted<<<(unsigned)(2 * nseg), bt, 0, ts>>>(rows, cols, logL, logH, parts);
     EON_LAUNCHED(ctx);
-    k_bucket_finish<<<(unsigned)((nseg + 31) / 32), 32, 0, st>>>(parts, logL, nseg, (G1Xyzz*)p_seg);
+    k_bucket_finish<<<(unsigned)((nseg + 31) / 32), 32, 0, ts>>>(parts, logL, nseg, (G1Xyzz*)p_seg);
     EON_LAUNCHED(ctx);
-    k_msm_combine<<<(unsigned)((ncols + 31) / 32), 32, 0, st>>>((const G1Xyzz*)p_seg, sh, ncols, d_out);
+    k_msm_combine<<<(unsigned)((ncols + 31) / 32), 32, 0, ts>>>((const G1Xyzz*)p_seg, sh, ncols, d_out);
     EON_LAUNCHED(ctx);
+    tiny_end(ctx);
   }
   phase_end(ctx, PH_MSM_REDUCE);
   return EON_OK;
@@ -759,9 +761,17 @@ int msm_run(eon_ctx* ctx, const G1Affine* d_bases, const Fr* d_scalars, size_t n
     if (!ctx->split_stream) {
       int least = 0, greatest = 0;
       EON_CUDA(ctx, cudaDeviceGetStreamPriorityRange(&least, &greatest));
-      EON_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->split_stream, cudaStreamNonBlocking, greatest));
+      // wide kernels of the second half one level below the top; the top level is for the single-warp phases
+      const int wide = greatest < least ? greatest + 1 : greatest;
+      EON_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->split_stream, cudaStreamNonBlocking, wide));
       for (auto& e : ctx->ev_split) EON_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      for (int b = 0; b < 2; b++) {
+        EON_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->tiny_stream[b], cudaStreamNonBlocking, greatest));
+        for (auto& e : ctx->ev_tiny[b]) EON_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      }
     }
+    static const int tiny_env = getenv("EON_MSM_TINY_PRIO") ? atoi(getenv("EON_MSM_TINY_PRIO")) : 1;
+    ctx->tiny_on = tiny_env != 0;
     const size_t h0 = (ncols + 1) / 2;
     cudaStream_t main_stream = ctx->stream;
     // The second half is ordered after everything queued so far (the scalars are produced on the main stream).
@@ -784,6 +794,7 @@ int msm_run(eon_ctx* ctx, const G1Affine* d_bases, const Fr* d_scalars, size_t n
       ctx->bank = 0;
       ctx->stream = main_stream;
     }
+    ctx->tiny_on = false;
     // join in any case: nothing may outlive the call on the second stream
     cudaError_t e = cudaEventRecord(ctx->ev_split[1], ctx->split_stream);
     if (e == cudaSuccess) e = cudaStreamWaitEvent(main_stream, ctx->ev_split[1], 0);

@@ -600,15 +600,19 @@ int msm_tree_rounds(eon_ctx* ctx, const G1Affine* d_bases, const SlicePlan& plan
     EON_LAUNCHED(ctx);
     phase_end(ctx, PH_MSM_TREE_FWD);
     phase_begin(ctx, PH_MSM_TREE_INV);
-    for (size_t l = 0; l + 1 < lv.size(); l++) {
-      k_tree_up<<<grid_for(lv[l + 1].second), TREE_THREADS, 0, st>>>(lv[l].first, lv[l].second, lv[l + 1].first);
+    {
+      cudaStream_t ts = tiny_begin(ctx);  // the product tree: a dependent chain of small launches
+      for (size_t l = 0; l + 1 < lv.size(); l++) {
+        k_tree_up<<<grid_for(lv[l + 1].second), TREE_THREADS, 0, ts>>>(lv[l].first, lv[l].second, lv[l + 1].first);
+        EON_LAUNCHED(ctx);
+      }
+      k_tree_top<<<(unsigned)((lv.back().second + 31) / 32), 32, 0, ts>>>(lv.back().first, lv.back().second);
       EON_LAUNCHED(ctx);
-    }
-    k_tree_top<<<(unsigned)((lv.back().second + 31) / 32), 32, 0, st>>>(lv.back().first, lv.back().second);
-    EON_LAUNCHED(ctx);
-    for (size_t l = lv.size() - 1; l-- > 0;) {
-      k_tree_down<<<grid_for(lv[l + 1].second), TREE_THREADS, 0, st>>>(lv[l].first, lv[l].second, lv[l + 1].first);
-      EON_LAUNCHED(ctx);
+      for (size_t l = lv.size() - 1; l-- > 0;) {
+        k_tree_down<<<grid_for(lv[l + 1].second), TREE_THREADS, 0, ts>>>(lv[l].first, lv[l].second, lv[l + 1].first);
+        EON_LAUNCHED(ctx);
+      }
+      tiny_end(ctx);
     }
     phase_end(ctx, PH_MSM_TREE_INV);
     phase_begin(ctx, PH_MSM_TREE_BWD);
