@@ -17,6 +17,12 @@
  *   G1      affine, 8 x u64: [x: 4 x u64][y: 4 x u64], Montgomery Fq (R = 2^256),
  *           identity = all zero (halo2curves G1Affine::identity()).
  *
+ * Preconditions the reference's types guarantee and this ABI does NOT re-check on the hot path: every Fr handed
+ * over (matrix entries, scalars) is canonical (< r; the reference's Fr is always reduced, field.rs:96-105) and
+ * every affine point of eon_srs_load_affine / eon_msm_points lies on the curve (halo2curves' G1 cannot hold
+ * anything else).  Shifts and opening points ARE checked (EON_ERR_BAD_ARG); compressed points are validated by
+ * eon_g1_decompress / eon_srs_load_compressed (EON_ERR_BAD_POINT).
+ *
  * All functions return EON_OK (0) or a negative error code; none aborts or unwinds.
  * `eon_last_error(ctx)` gives a human-readable message for the last failure on that ctx.
  * There is NO CPU fallback: every entry point fails with EON_ERR_CUDA if no sm_100 device

@@ -174,3 +174,47 @@ def test_prover_data_is_released_with_its_python_object(single):
         used.append(total - free)
     # 32 MiB of coefficients per commit: a leak would add 32 MiB per cycle after the pool of 4 is in use
     assert used[-1] - used[5] < (16 << 20), used
+
+
+def test_ragged_shapes_and_mmcs_through_the_multi_device_context(single, multi):
+    """Fewer columns than devices, zero-width matrices, non-power-of-two KzgMmcs heights (kzg/src/mmcs.rs:155-237:
+    coefficient-form matrices of mixed heights opened at one index): same bytes as the single-device calls."""
+    from plonky3_eon_b200 import GpuKzgMmcs, GpuKzgPcs, TwoAdicMultiplicativeCoset
+    outs = []
+    for ctx in (single, multi):
+        pcs = GpuKzgPcs.new(63, ALPHA, ctx=ctx)
+        dom = TwoAdicMultiplicativeCoset(1, 5)
+        res = []
+        for w in (1, 0):                                   # one column (fewer than devices), then none
+            evals = rand_matrix(300 + w, 32, w) if w else np.zeros((32, 0, 4), dtype=np.uint64)
+            commit, pd = pcs.commit([(dom, evals)])
+            res.append(commit[0])
+            if w:
+                res.append(pd[0].coeffs())
+                res.append(np.array(pcs.get_evaluations_on_domain(pd, 0, TwoAdicMultiplicativeCoset(3, 3))))  # smaller
+                opened, proof = pcs.open([(pd, [[5, 6, 7]])])
+                res.extend(opened[0][0] + proof[0][0])
+            pd[0].free()
+        mm = GpuKzgMmcs(ctx)
+        mats = [rand_matrix(400, 48, 5), rand_matrix(401, 7, 2), rand_matrix(402, 64, 1)]   # heights 48, 7, 64
+        commit, pdm = mm.commit(mats)
+        res.extend(commit)
+        opened, wits = mm.open_batch(37, pdm)
+        res.extend(opened + wits)
+        pdm.free()
+        outs.append(res)
+    assert len(outs[0]) == len(outs[1])
+    for a, b in zip(*outs):
+        assert a.shape == b.shape and np.array_equal(a, b)
+
+
+def test_multi_device_context_rejects_bad_calls(multi):
+    from plonky3_eon_b200 import EonError
+    out = np.zeros((4, 4), dtype=np.uint64)
+    with pytest.raises(EonError):
+        multi.call("eon_kzg_evals_on_coset", C.c_uint64(987654321), 4, fr.to_wire([3])[0], out)
+    with pytest.raises(EonError):                           # shift 0 is not a coset (field/src/coset.rs:77-86)
+        multi.call("eon_coset_dft_batch", rand_matrix(1, 4, 2), np.zeros((4, 2, 4), dtype=np.uint64), 2, 2,
+                   np.zeros(4, dtype=np.uint64))
+    with pytest.raises(EonError):                           # ld < ncols
+        multi.call("eon_msm_srs", rand_matrix(2, 4, 2), 4, 2, 1, out)
