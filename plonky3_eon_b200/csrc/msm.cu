@@ -744,7 +744,14 @@ int msm_run(eon_ctx* ctx, const G1Affine* d_bases, const Fr* d_scalars, size_t n
   // level products ~5 B, prefix products 16 B per entry slot)
   size_t per_slot = 4 + (sh.rounds ? 32 + 16 + 5 + 16 : 0);
   size_t per_col = sh.seg_cap * sh.nsets * per_slot + (size_t)sh.nsets * sh.NB * (sizeof(G1Xyzz) + 16);
-  size_t budget = (size_t)24 << 30;
+  // 64 GiB of the 180 while the tables are small enough for the slice schedule (<= 32 slices: up to 2^20 points at
+  // c = 17): the 32 quotient columns of an opening at two points stay ONE batch -- every base gathered by all of them
+  // per launch, one set of single-warp phases: open 72.6 -> 70.6 ms.  Larger tables are gathered at random whatever
+  // the batch, and there wider batches measured SLOWER (2^24 x 8 columns, c = 20: 460.9 ms at 3 columns per batch
+  // against 432.7 ms at 1; profiles/r02p_msm_batch_budget.txt): 24 GiB.  EON_MSM_BUDGET_GB overrides.
+  static const size_t budget_gb = getenv("EON_MSM_BUDGET_GB") ? (size_t)atoll(getenv("EON_MSM_BUDGET_GB")) : 0;
+  const bool sliceable = sh.merged && (((u64)sh.W * sh.tab_stride) >> 19) + 1 <= SLICE_ORDER_MAX;
+  size_t budget = (budget_gb ? budget_gb : (sliceable ? 64 : 24)) << 30;
   size_t batch = budget / per_col;
   if (batch < 1) batch = 1;
   if (batch > 64) batch = 64;
