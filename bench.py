@@ -73,26 +73,99 @@ def ncu_traffic(key):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe).  Sampled in-process through
+    NVML on a thread (a `nvidia-smi -lms` child needs longer to start than 5 steps of 43 ms take, and would come
+    back with no samples); the nvidia-smi loop remains as the fallback when pynvml is missing."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
-    def __init__(self, dev):
+    def __init__(self, dev, period_s=0.01):
         self.dev = dev
+        self.period = period_s
         self.proc = None
+        self.thread = None
+        self.sm, self.power, self.reasons = [], [], set()
+        self.mx = None
+        self.nv = None
+        self.handle = None
+        self.source = None
+        try:  # set up before the timed region: nvmlInit takes tens of ms
+            import pynvml
+            pynvml.nvmlInit()
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(self._nvml_index(pynvml, dev))
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nv = pynvml
+            self.masks = {
+                "hw_slowdown": pynvml.nvmlClocksThrottleReasonHwSlowdown,
+                "hw_thermal_slowdown": pynvml.nvmlClocksThrottleReasonHwThermalSlowdown,
+                "sw_thermal_slowdown": pynvml.nvmlClocksThrottleReasonSwThermalSlowdown,
+                "sw_power_cap": pynvml.nvmlClocksThrottleReasonSwPowerCap,
+            }
+        except Exception:
+            self.nv = None
+
+    @staticmethod
+    def _nvml_index(pynvml, dev):
+        """NVML enumerates every GPU of the box; CUDA only the visible ones, in CUDA_VISIBLE_DEVICES order."""
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            ids = [v.strip() for v in vis.split(",") if v.strip()]
+            if dev < len(ids) and ids[dev].isdigit():
+                return int(ids[dev])
+        return dev
+
+    def _sample(self):
+        nv = self.nv
+        self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM)))
+        try:
+            self.power.append(nv.nvmlDeviceGetPowerUsage(self.handle) / 1000.0)
+        except Exception:
+            pass
+        r = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+        for n, m in self.masks.items():
+            if r & m:
+                self.reasons.add(n)
+
+    def _loop(self):
+        while not self._stop.is_set():
+            try:
+                self._sample()
+            except Exception:
+                break
+            self._stop.wait(self.period)
 
     def start(self):
+        if self.nv is not None:
+            import threading
+            self._stop = threading.Event()
+            self.thread = threading.Thread(target=self._loop, daemon=True)
+            self.thread.start()
+            self.source = "nvml thread, %d ms period" % int(self.period * 1000)
+            return
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i",
                  str(self.dev)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.source = "nvidia-smi -lms 100"
         except Exception:
             self.proc = None
 
     def stop(self):
+        if self.thread is not None:
+            try:
+                self._sample()      # at least one sample taken with the last kernels still in flight / just retired
+            except Exception:
+                pass
+            self._stop.set()
+            self.thread.join(timeout=2)
+            return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.mx,
+                    "sm_min_mhz": min(self.sm) if self.sm else None,
+                    "power_w_max": max(self.power) if self.power else None,
+                    "samples": len(self.sm), "reasons": sorted(self.reasons), "source": self.source}
         if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "samples": 0, "reasons": ["nvml and nvidia-smi unavailable"]}
         time.sleep(0.15)
         self.proc.terminate()
         try:
@@ -101,7 +174,6 @@ class ClockSampler:
             self.proc.kill()
             out = ""
         sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for line in out.strip().splitlines():
             f = [x.strip() for x in line.split(",")]
             if len(f) < 7:
@@ -111,11 +183,11 @@ class ClockSampler:
                 mx.append(float(f[1]))
             except ValueError:
                 continue
-            for n, v in zip(names, f[3:7]):
+            for n, v in zip(self.NAMES, f[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(n)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "reasons": sorted(reasons), "source": self.source}
 
 
 def synth_column(c, rows):

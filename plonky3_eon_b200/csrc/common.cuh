@@ -106,6 +106,7 @@ struct eon_ctx {
   size_t twiddle_bytes = 0;  // device bytes behind `twiddles` (bounded: see get_twiddles)
   // opt-in shared-memory sizes (cudaFuncSetAttribute) are per device: set once per context, not per process
   bool ntt_attr_set = false;
+  bool ntt_db_attr_set = false;
   bool sort_attr_set = false;
 
   eon::G1Affine* d_srs = nullptr;

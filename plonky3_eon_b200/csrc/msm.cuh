@@ -105,6 +105,41 @@ __device__ __forceinline__ void for_each_digit_canonical(const u32 (&k)[8], cons
   }
 }
 
+// The same digits with the window size known at compile time (C = sh.c, W = ceil(255 / C) = sh.W): every digit is
+// one funnel shift and a mask at a fixed limb / bit position, where the generic walk above is a data-dependent
+// loop over a 64-bit bit buffer (~33 instructions per digit in the SASS of the sort kernels, which visit every
+// digit three times).  C = 0 selects the generic walk.
+// ALL (C != 0 only): f is also called for zero digits (d == 0), so a warp stays converged through the whole walk
+// and f may use full-mask warp collectives.
+template <int C, bool ALL = false, class F>
+__device__ __forceinline__ void for_each_digit_c(const u32 (&k)[8], const MsmShape& sh, F f) {
+  if constexpr (C == 0) {
+    for_each_digit_canonical(k, sh, f);
+  } else {
+    constexpr u32 W = (255 + C - 1) / C;
+    constexpr u32 mask = (1u << C) - 1;
+    constexpr u32 half = 1u << (C - 1);
+    u32 carry = 0;
+#pragma unroll
+    for (u32 w = 0; w < W; w++) {
+      const u32 o = C * w, j = o >> 5, sft = o & 31;  // compile-time after unrolling; j <= 7 because o < 255
+      const u32 lo = k[j];
+      const u32 hi = (j + 1 < 8) ? k[(j + 1) & 7] : 0u;
+      u32 raw = (sft ? __funnelshift_r(lo, hi, sft) : lo) & mask;
+      raw += carry;
+      int d;
+      if (raw >= half && w + 1 < W) {
+        d = (int)raw - (int)(1u << C);
+        carry = 1;
+      } else {
+        d = (int)raw;
+        carry = 0;
+      }
+      if (ALL || d != 0) f(w, d);
+    }
+  }
+}
+
 template <class F>
 __device__ __forceinline__ void for_each_digit(const Fr& s, const MsmShape& sh, F f) {
   u32 k[8];

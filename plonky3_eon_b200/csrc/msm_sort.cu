@@ -54,9 +54,27 @@ __device__ __forceinline__ u32 smem_rank(u32* counter, u32 key) {
   return atomicAdd(counter + key, 1u);
 }
 
+// The same for a CONVERGED warp (every lane calls, `on` says whether the lane has an entry): full-mask collectives,
+// no divergence bookkeeping (the divergent form above compiles to ~100 instructions per call site with its
+// BRA.DIV / WARPSYNC paths, and the coarse pass has 60 call sites per thread).
+__device__ __forceinline__ u32 smem_rank_conv(u32* counter, u32 key, bool on) {
+  const u32 act = __ballot_sync(0xffffffffu, on);
+  if (act == 0) return 0;
+  const u32 leader = __ffs(act) - 1;
+  const u32 k0 = __shfl_sync(0xffffffffu, key, leader);
+  if (__all_sync(0xffffffffu, !on || key == k0)) {
+    const u32 lane = threadIdx.x & 31;
+    u32 base = 0;
+    if (lane == leader) base = atomicAdd(counter + k0, __popc(act));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    return base + __popc(act & ((1u << lane) - 1));
+  }
+  return on ? atomicAdd(counter + key, 1u) : 0u;
+}
+
 // Bin histogram.  grid: ncols * ceil(n / tile) blocks, column index fastest (as the coarse pass).
 // bin_count[(col * nsets + set) * nbins + k] += entries of the tile whose bucket >> fb == k
-template <bool MERGED>
+template <bool MERGED, int C>
 __global__ void __launch_bounds__(SORT_THREADS)
 k_bin_hist(const Fr* __restrict__ scalars, size_t n, size_t ld, u32 ncols, MsmShape sh, u32 nbins, u32 fb, u32 tile,
            u32* __restrict__ bin_count) {
@@ -79,7 +97,7 @@ k_bin_hist(const Fr* __restrict__ scalars, size_t n, size_t ld, u32 ncols, MsmSh
   for (int q = 0; q < 4; q++) {
     u32 kk[8];
     fp_from_mont(kk, sc[q]);
-    for_each_digit_canonical(kk, sh, [&](u32 w, int d) {
+    for_each_digit_c<C>(kk, sh, [&](u32 w, int d) {
       u32 b = (u32)(d < 0 ? -d : d) - 1;
       atomicAdd(&smem[(MERGED ? 0 : w * nbins) + (b >> fb)], 1u);
     });
@@ -153,7 +171,11 @@ k_sort_count(const unsigned short* __restrict__ tmp_key, const u32* __restrict__
 // Shared memory: cnt[tile_bins] | off[tile_bins + 1] | gbase[tile_bins] | stage_pay[tile * W] u32 |
 // stage_key[tile * W] u16.  The tile's entries are grouped by bin in shared memory first, so the copy
 // to the temporary array is coalesced (consecutive threads -> consecutive slots of a run).
-template <bool MERGED>
+// MERGED (window tables, the commit path) with NB <= 2^16: the staged key is the bucket index itself, so the
+// copy-out is flat -- one thread per staged slot, the bin read back from the key -- instead of one warp per bin
+// (~30 entries per run at 2^20 x 16: 70 instructions per run, 36 % of the kernel's instructions in ncu's source
+// view, profiles/r02q_sort_kernels.txt).
+template <bool MERGED, int C>
 __global__ void __launch_bounds__(SORT_THREADS)
 k_sort_coarse(const Fr* __restrict__ scalars, size_t n, size_t ld, u32 ncols, MsmShape sh, u32 nbins, u32 fb, u32 tile,
               u32* __restrict__ region_cursor, u32* __restrict__ tmp_pay, unsigned short* __restrict__ tmp_key) {
@@ -189,7 +211,7 @@ k_sort_coarse(const Fr* __restrict__ scalars, size_t n, size_t ld, u32 ncols, Ms
   // histogram of the tile by bin
 #pragma unroll
   for (int q = 0; q < 4; q++) {
-    for_each_digit_canonical(kk[q], sh, [&](u32 w, int d) {
+    for_each_digit_c<C>(kk[q], sh, [&](u32 w, int d) {
       u32 b = (u32)(d < 0 ? -d : d) - 1;
       atomicAdd(&s_cnt[(MERGED ? 0 : w * nbins) + (b >> fb)], 1u);
     });
@@ -216,35 +238,56 @@ k_sort_coarse(const Fr* __restrict__ scalars, size_t n, size_t ld, u32 ncols, Ms
       u32 c = s_cnt[k];
       s_off[k] = run;
       run += c;
-      s_gbase[k] = c ? atomicAdd(&region_cursor[seg0 * nbins + k], c) : 0;
+      // first slot of the bin's run in the temporary array, minus the bin's first staged slot
+      s_gbase[k] = (c ? atomicAdd(&region_cursor[seg0 * nbins + k], c) : 0) - run + c;
       s_cnt[k] = 0;
     }
     if (tid == SORT_THREADS - 1) s_off[tile_bins] = run;
   }
   __syncthreads();
   // group the entries by bin in shared memory
+  const bool flat = MERGED && sh.NB <= 65536u;  // the bucket index fits the 16-bit staged key
 #pragma unroll
   for (int q = 0; q < 4; q++) {
     const u32 i = (u32)(i0 + tid + q * SORT_THREADS);
     const u32 base0 = MERGED ? (u32)sh.base_first + i : i;  // entry = base index: + w * tab_stride with tables
     const u32 stride = MERGED ? (u32)sh.tab_stride : 0u;
-    for_each_digit_canonical(kk[q], sh, [&](u32 w, int d) {
-      u32 b = (u32)(d < 0 ? -d : d) - 1;
+    for_each_digit_c<C, C != 0>(kk[q], sh, [&](u32 w, int d) {
+      const bool on = d != 0;  // (always true on the generic walk, which skips zero digits)
+      u32 b = on ? (u32)(d < 0 ? -d : d) - 1 : 0u;
       u32 bin = (MERGED ? 0 : w * nbins) + (b >> fb);
-      u32 slot = s_off[bin] + smem_rank(s_cnt, bin);
-      s_pay[slot] = (base0 + w * stride) | ((u32)d & SIGN_BIT);
-      s_key[slot] = (unsigned short)(b & fmask);
+      u32 rank;
+      if constexpr (C != 0) rank = smem_rank_conv(s_cnt, bin, on);
+      else rank = smem_rank(s_cnt, bin);
+      if (on) {
+        u32 slot = s_off[bin] + rank;
+        s_pay[slot] = (base0 + w * stride) | ((u32)d & SIGN_BIT);
+        s_key[slot] = (unsigned short)(flat ? b : (b & fmask));  // flat: the bucket index itself
+      }
     });
   }
   __syncthreads();
-  // coalesced copy-out, one warp per bin: lanes -> consecutive slots of the bin's run
-  for (u32 bin = wid; bin < tile_bins; bin += SORT_THREADS / 32) {
-    const u32 o0 = s_off[bin], o1 = s_off[bin + 1];
-    if (o0 == o1) continue;
-    const size_t dst = (seg0 + (MERGED ? 0 : bin / nbins)) * sh.seg_cap + s_gbase[bin];
-    for (u32 idx = o0 + lane; idx < o1; idx += 32) {
-      tmp_pay[dst + (idx - o0)] = s_pay[idx];
-      tmp_key[dst + (idx - o0)] = s_key[idx];
+  if (flat) {
+    // coalesced copy-out, flat over the staged slots (grouped by bin, so consecutive threads write consecutive
+    // slots of a run); the bin is read back from the staged bucket index
+    const u32 total = s_off[tile_bins];
+    const size_t dst0 = seg0 * sh.seg_cap;
+    for (u32 idx = tid; idx < total; idx += SORT_THREADS) {
+      const u32 b = s_key[idx];
+      const size_t dst = dst0 + (u32)(s_gbase[b >> fb] + idx);
+      tmp_pay[dst] = s_pay[idx];
+      tmp_key[dst] = (unsigned short)(b & fmask);
+    }
+  } else {
+    // one warp per bin: lanes -> consecutive slots of the bin's run (bin and low bucket bits together need 17 bits)
+    for (u32 bin = wid; bin < tile_bins; bin += SORT_THREADS / 32) {
+      const u32 o0 = s_off[bin], o1 = s_off[bin + 1];
+      if (o0 == o1) continue;
+      const size_t dst = (seg0 + (MERGED ? 0 : bin / nbins)) * sh.seg_cap;
+      for (u32 idx = o0 + lane; idx < o1; idx += 32) {
+        tmp_pay[dst + (u32)(s_gbase[bin] + idx)] = s_pay[idx];
+        tmp_key[dst + (u32)(s_gbase[bin] + idx)] = s_key[idx];
+      }
     }
   }
 }
@@ -282,13 +325,31 @@ k_sort_fine(const u32* __restrict__ tmp_pay, const unsigned short* __restrict__ 
   const bool staged = wlen <= SORT_WIN_CAP;
   if (staged)
     for (u32 j = tid; j < wlen; j += SORT_FINE_THREADS) s_win[j] = ENTRY_NONE;
+  // The run is read FINE_U entries per thread at a time: all loads of a batch are in flight before the first
+  // shared-memory atomic needs its value (one load -> one atomic per iteration left the kernel waiting on DRAM
+  // latency: long-scoreboard stall 10 per issue in ncu, profiles/r02q_sort_kernels.txt).
+  constexpr int FINE_U = 8;
   if (ORDERED && staged) {
     for (u32 j = tid; j < fine * ns; j += SORT_FINE_THREADS) s_cnt2[j] = 0;
     __syncthreads();
-    for (u32 i = tbegin + tid; i < tend; i += SORT_FINE_THREADS) {
-      const u32 key = tmp_key[off + i];
-      const u32 sl = min((tmp_pay[off + i] & ~SIGN_BIT) >> slice_shift, ns - 1);
-      atomicAdd(&s_cnt2[key * ns + sl], 1u);
+    for (u32 i0 = tbegin; i0 < tend; i0 += SORT_FINE_THREADS * FINE_U) {
+      u32 key[FINE_U], pay[FINE_U];
+#pragma unroll
+      for (int u = 0; u < FINE_U; u++) {
+        const u32 i = i0 + u * SORT_FINE_THREADS + tid;
+        if (i < tend) {
+          key[u] = tmp_key[off + i];
+          pay[u] = tmp_pay[off + i];
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < FINE_U; u++) {
+        const u32 i = i0 + u * SORT_FINE_THREADS + tid;
+        if (i < tend) {
+          const u32 sl = min((pay[u] & ~SIGN_BIT) >> slice_shift, ns - 1);
+          atomicAdd(&s_cnt2[key[u] * ns + sl], 1u);
+        }
+      }
     }
     __syncthreads();
     for (u32 f = tid; f < fine; f += SORT_FINE_THREADS) {
@@ -301,20 +362,46 @@ k_sort_fine(const u32* __restrict__ tmp_pay, const unsigned short* __restrict__ 
       s_cur[f] = run;  // the bucket's end
     }
     __syncthreads();
-    for (u32 i = tbegin + tid; i < tend; i += SORT_FINE_THREADS) {
-      const u32 key = tmp_key[off + i];
-      const u32 pay = tmp_pay[off + i];
-      const u32 sl = min((pay & ~SIGN_BIT) >> slice_shift, ns - 1);
-      s_win[smem_rank(s_cnt2, key * ns + sl) - begin] = pay;
+    for (u32 i0 = tbegin; i0 < tend; i0 += SORT_FINE_THREADS * FINE_U) {
+      u32 key[FINE_U], pay[FINE_U];
+#pragma unroll
+      for (int u = 0; u < FINE_U; u++) {
+        const u32 i = i0 + u * SORT_FINE_THREADS + tid;
+        if (i < tend) {
+          key[u] = tmp_key[off + i];
+          pay[u] = tmp_pay[off + i];
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < FINE_U; u++) {
+        const u32 i = i0 + u * SORT_FINE_THREADS + tid;
+        if (i < tend) {
+          const u32 sl = min((pay[u] & ~SIGN_BIT) >> slice_shift, ns - 1);
+          s_win[smem_rank(s_cnt2, key[u] * ns + sl) - begin] = pay[u];
+        }
+      }
     }
   } else {
     __syncthreads();
-    for (u32 i = tbegin + tid; i < tend; i += SORT_FINE_THREADS) {
-      u32 key = tmp_key[off + i];
-      u32 pay = tmp_pay[off + i];
-      u32 pos = smem_rank(s_cur, key);
-      if (staged) s_win[pos - begin] = pay;
-      else entries[off + pos] = pay;
+    for (u32 i0 = tbegin; i0 < tend; i0 += SORT_FINE_THREADS * FINE_U) {
+      u32 key[FINE_U], pay[FINE_U];
+#pragma unroll
+      for (int u = 0; u < FINE_U; u++) {
+        const u32 i = i0 + u * SORT_FINE_THREADS + tid;
+        if (i < tend) {
+          key[u] = tmp_key[off + i];
+          pay[u] = tmp_pay[off + i];
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < FINE_U; u++) {
+        const u32 i = i0 + u * SORT_FINE_THREADS + tid;
+        if (i < tend) {
+          const u32 pos = smem_rank(s_cur, key[u]);
+          if (staged) s_win[pos - begin] = pay[u];
+          else entries[off + pos] = pay[u];
+        }
+      }
     }
   }
   __syncthreads();
@@ -349,9 +436,13 @@ int msm_sort_entries(eon_ctx* ctx, const Fr* d_scalars, size_t n, size_t ncols, 
   const size_t tiles = (n + tile - 1) / tile;
   if (tiles * ncols > 0x7fffffffull || total_bins > 0x7fffffffull) return 1;
   if (!ctx->sort_attr_set) {  // per context: the attribute belongs to the context's device
-    EON_CUDA(ctx, cudaFuncSetAttribute(k_sort_coarse<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    EON_CUDA(ctx, cudaFuncSetAttribute(k_sort_coarse<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)(SORT_COARSE_SMEM + 16)));
-    EON_CUDA(ctx, cudaFuncSetAttribute(k_sort_coarse<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    EON_CUDA(ctx, cudaFuncSetAttribute(k_sort_coarse<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)(SORT_COARSE_SMEM + 16)));
+    EON_CUDA(ctx, cudaFuncSetAttribute(k_sort_coarse<true, 17>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)(SORT_COARSE_SMEM + 16)));
+    EON_CUDA(ctx, cudaFuncSetAttribute(k_sort_coarse<false, 17>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)(SORT_COARSE_SMEM + 16)));
     EON_CUDA(ctx, cudaFuncSetAttribute(k_sort_fine<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)(((size_t)(1u << 12) + SORT_WIN_CAP) * sizeof(u32))));
@@ -370,14 +461,18 @@ int msm_sort_entries(eon_ctx* ctx, const Fr* d_scalars, size_t n, size_t ncols, 
   cudaStream_t st = ctx->stream;
   const unsigned grid_tiles = (unsigned)(tiles * ncols);
 
+  // window size known at compile time for the shapes the cost model picks (c = 17 up to 2^22 points)
+  const bool c17 = sh.c == 17 && sh.W == 15;
   phase_begin(ctx, PH_MSM_DIGITS);
   EON_CUDA(ctx, cudaMemsetAsync(bin_count, 0, total_bins * sizeof(u32), st));
-  if (sh.merged)
-    k_bin_hist<true><<<grid_tiles, SORT_THREADS, tile_bins * sizeof(u32), st>>>(d_scalars, n, ld, (u32)ncols, sh, nbins,
-                                                                                fb, tile, bin_count);
-  else
-    k_bin_hist<false><<<grid_tiles, SORT_THREADS, tile_bins * sizeof(u32), st>>>(d_scalars, n, ld, (u32)ncols, sh, nbins,
-                                                                                 fb, tile, bin_count);
+#define EON_SORT_LAUNCH(K, SMEM, ...)                                                                          \
+  do {                                                                                                         \
+    if (sh.merged && c17) K<true, 17><<<grid_tiles, SORT_THREADS, SMEM, st>>>(__VA_ARGS__);                    \
+    else if (sh.merged) K<true, 0><<<grid_tiles, SORT_THREADS, SMEM, st>>>(__VA_ARGS__);                       \
+    else if (c17) K<false, 17><<<grid_tiles, SORT_THREADS, SMEM, st>>>(__VA_ARGS__);                           \
+    else K<false, 0><<<grid_tiles, SORT_THREADS, SMEM, st>>>(__VA_ARGS__);                                     \
+  } while (0)
+  EON_SORT_LAUNCH(k_bin_hist, tile_bins * sizeof(u32), d_scalars, n, ld, (u32)ncols, sh, nbins, fb, tile, bin_count);
   EON_LAUNCHED(ctx);
   k_bin_scan<<<(unsigned)nseg, 1024, 0, st>>>(bin_count, nbins, tmp_start, region_cursor);
   EON_LAUNCHED(ctx);
@@ -386,12 +481,9 @@ int msm_sort_entries(eon_ctx* ctx, const Fr* d_scalars, size_t n, size_t ncols, 
   phase_begin(ctx, PH_MSM_SCATTER);
   if (sh.rounds)  // unused slots (bucket padding, segment tails) must read as ENTRY_NONE
     EON_CUDA(ctx, cudaMemsetAsync(d_entries, 0xff, nseg * sh.seg_cap * sizeof(u32), st));
-  if (sh.merged)
-    k_sort_coarse<true><<<grid_tiles, SORT_THREADS, smem_coarse, st>>>(
-        d_scalars, n, ld, (u32)ncols, sh, nbins, fb, tile, region_cursor, (u32*)p_pay, (unsigned short*)p_key);
-  else
-    k_sort_coarse<false><<<grid_tiles, SORT_THREADS, smem_coarse, st>>>(
-        d_scalars, n, ld, (u32)ncols, sh, nbins, fb, tile, region_cursor, (u32*)p_pay, (unsigned short*)p_key);
+  EON_SORT_LAUNCH(k_sort_coarse, smem_coarse, d_scalars, n, ld, (u32)ncols, sh, nbins, fb, tile, region_cursor,
+                  (u32*)p_pay, (unsigned short*)p_key);
+#undef EON_SORT_LAUNCH
   EON_LAUNCHED(ctx);
   phase_end(ctx, PH_MSM_SCATTER);
 

@@ -26,6 +26,9 @@
 #ifndef EON_NTT_SHOUP_DEFAULT
 #define EON_NTT_SHOUP_DEFAULT 1
 #endif
+#ifndef EON_NTT_DB_DEFAULT
+#define EON_NTT_DB_DEFAULT 0
+#endif
 
 namespace eon {
 
@@ -532,15 +535,251 @@ __global__ void __launch_bounds__(NTT_THREADS, MINB) k_ntt_pass(const PassParams
   }
 }
 
+// ---- persistent, double-buffered form of the pass (fixed-operand twiddles in shared memory only) ----------
+// k_ntt_pass gives a CTA ONE tile: load, wait, butterflies, store -- the integer pipe of an SM idles whenever both of
+// its resident CTAs are in a memory phase at once (ncu: sm__pipe_fmaheavy_cycles_active 75-81 %).  Here a CTA walks
+// tiles blockIdx.x, blockIdx.x + gridDim.x, ... with TWO shared-memory buffers: the asynchronous copies of tile
+// i + 1 (and of its twiddles) are issued before the butterflies of tile i start and are only waited for when tile i
+// has been stored, so every CTA always has arithmetic to issue.  Same butterflies, same order, same results.
+struct TileGeom {
+  u64 v0, row_base;
+  u32 ncv;
+};
+__device__ __forceinline__ TileGeom tile_geom(const PassParams& p, u64 tile) {
+  TileGeom g;
+  const u64 vt = tile % p.tiles_v;
+  const u64 hi = tile / p.tiles_v;
+  g.v0 = vt << p.log_cv;
+  g.ncv = (u32)min((u64)(1u << p.log_cv), p.V - g.v0);
+  g.row_base = hi << p.r;
+  return g;
+}
+
+template <int THREADS>
+__device__ __forceinline__ void db_issue_tile(const PassParams& p, u64 tile, uint4* s_lo, uint4* s_hi, uint4* s_tw,
+                                              u32 tid) {
+  const TileGeom g = tile_geom(p, tile);
+  const u32 cv = 1u << p.log_cv;
+  const u32 tile_elems = (1u << p.r) << p.log_cv;
+  const bool plain_in = (p.k == 0 && !p.in_rev && p.ld_src == p.w);
+  for (u32 u = tid; u < tile_elems * 2; u += THREADS) {
+    const u32 e = u >> 1, half = u & 1;
+    const u32 m = e >> p.log_cv, vc = e & (cv - 1);
+    if (vc >= g.ncv) continue;
+    const u64 vidx = g.v0 + vc;
+    u64 src_elem;
+    if (plain_in) {
+      src_elem = (g.row_base + m) * p.V + vidx;
+    } else {
+      u64 lo;
+      u32 col;
+      split_vidx(p, vidx, lo, col);
+      u64 pos = ((g.row_base + m) << p.l0) + lo;
+      u64 srow = pos >> p.k;
+      if (p.in_rev) {
+        u32 bits = p.log_n - p.k;
+        srow = bits ? (u64)(__brev((u32)srow) >> (32 - bits)) : 0;
+      }
+      src_elem = srow * p.ld_src + col;
+    }
+    cp_async16((half ? s_hi : s_lo) + e, p.src + src_elem * 2 + half);
+  }
+  u64 lo_tile = 0;
+  if (p.l0) {
+    u32 col;
+    split_vidx(p, g.v0, lo_tile, col);
+  }
+  const u32 ntw = (1u << p.r) - 1;
+  for (u32 u = tid; u < ntw * 4; u += THREADS) {
+    const u32 i = u >> 2, q = u & 3;
+    const u32 t = 31 - __clz(i + 1);
+    const u32 jr = i + 1 - (1u << t);
+    const u64 gi = ((1ull << (p.l0 + t)) - 1) + ((u64)jr << p.l0) + lo_tile;
+    cp_async16(s_tw + i * 4 + q, p.tw + gi * 4 + q);
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
+template <int THREADS>
+__device__ __forceinline__ void db_butterflies(const PassParams& p, u32 ncv, uint4* s_lo, uint4* s_hi,
+                                               const uint4* s_tw, u32 tid) {
+  const u32 cv = 1u << p.log_cv;
+  const u32 tile_elems = (1u << p.r) << p.log_cv;
+  u32 step = 0;
+  const u32 nq = tile_elems >> 2;
+  for (; step + 1 < p.r; step += 2) {
+    const u32 t = p.dif ? (p.r - 2 - step) : step;
+    const u32 tmask = (1u << t) - 1;
+    for (u32 idx = tid; idx < nq; idx += THREADS) {
+      const u32 vc = idx & (cv - 1);
+      if (vc >= ncv) continue;
+      const u32 b = idx >> p.log_cv;
+      const u32 i0 = ((b >> t) << (t + 2)) | (b & tmask);
+      const u32 e0 = (i0 << p.log_cv) + vc;
+      const u32 st1 = (1u << t) << p.log_cv;
+      const u32 e1 = e0 + st1, e2 = e0 + 2 * st1, e3 = e0 + 3 * st1;
+      Fr x0 = fr_from_units(s_lo[e0], s_hi[e0]);
+      Fr x1 = fr_from_units(s_lo[e1], s_hi[e1]);
+      Fr x2 = fr_from_units(s_lo[e2], s_hi[e2]);
+      Fr x3 = fr_from_units(s_lo[e3], s_hi[e3]);
+      const u32 jr = b & tmask;
+      const uint4* tA = s_tw + (((1u << t) - 1) + jr) * 4;
+      const uint4* tB0 = s_tw + (((2u << t) - 1) + jr) * 4;
+      const uint4* tB1 = tB0 + (4u << t);
+      if (!p.dif) {
+        {
+          TwS twA;
+          twA.w = fr_lds(tA);
+          twA.wq = fr_lds(tA + 2);
+          bf_dit(x0, x1, twA);
+          bf_dit(x2, x3, twA);
+        }
+        {
+          TwS twB;
+          twB.w = fr_lds(tB0);
+          twB.wq = fr_lds(tB0 + 2);
+          bf_dit(x0, x2, twB);
+        }
+        {
+          TwS twB;
+          twB.w = fr_lds(tB1);
+          twB.wq = fr_lds(tB1 + 2);
+          bf_dit(x1, x3, twB);
+        }
+      } else {
+        {
+          TwS twB;
+          twB.w = fr_lds(tB0);
+          twB.wq = fr_lds(tB0 + 2);
+          bf_dif(x0, x2, twB);
+        }
+        {
+          TwS twB;
+          twB.w = fr_lds(tB1);
+          twB.wq = fr_lds(tB1 + 2);
+          bf_dif(x1, x3, twB);
+        }
+        {
+          TwS twA;
+          twA.w = fr_lds(tA);
+          twA.wq = fr_lds(tA + 2);
+          bf_dif(x0, x1, twA);
+          bf_dif(x2, x3, twA);
+        }
+      }
+      fr_to_units(x0, s_lo[e0], s_hi[e0]);
+      fr_to_units(x1, s_lo[e1], s_hi[e1]);
+      fr_to_units(x2, s_lo[e2], s_hi[e2]);
+      fr_to_units(x3, s_lo[e3], s_hi[e3]);
+    }
+    __syncthreads();
+  }
+  const u32 nbf = tile_elems >> 1;
+  for (; step < p.r; step++) {
+    const u32 t = p.dif ? (p.r - 1 - step) : step;
+    const u32 tmask = (1u << t) - 1;
+    for (u32 idx = tid; idx < nbf; idx += THREADS) {
+      const u32 vc = idx & (cv - 1);
+      if (vc >= ncv) continue;
+      const u32 b = idx >> p.log_cv;
+      const u32 i0 = ((b >> t) << (t + 1)) | (b & tmask);
+      const u32 e0 = (i0 << p.log_cv) + vc;
+      const u32 e1 = e0 + ((1u << t) << p.log_cv);
+      const uint4* tp = s_tw + (((1u << t) - 1) + (b & tmask)) * 4;
+      TwS tw;
+      tw.w = fr_lds(tp);
+      tw.wq = fr_lds(tp + 2);
+      Fr o0 = fr_from_units(s_lo[e0], s_hi[e0]);
+      Fr o1 = fr_from_units(s_lo[e1], s_hi[e1]);
+      if (!p.dif) bf_dit(o0, o1, tw);
+      else bf_dif(o0, o1, tw);
+      fr_to_units(o0, s_lo[e0], s_hi[e0]);
+      fr_to_units(o1, s_lo[e1], s_hi[e1]);
+    }
+    __syncthreads();
+  }
+}
+
+template <int THREADS>
+__device__ __forceinline__ void db_store_tile(const PassParams& p, u64 tile, const uint4* s_lo, const uint4* s_hi,
+                                              u32 tid) {
+  const TileGeom g = tile_geom(p, tile);
+  const u32 cv = 1u << p.log_cv;
+  const u32 tile_elems = (1u << p.r) << p.log_cv;
+  const bool plain_out = (p.ld_dst == p.w);
+  auto dst_of = [&](u32 m, u64 vidx) -> u64 {
+    if (p.out_rev) {
+      const u64 pos = g.row_base + m;  // l0 == 0, V == w
+      const u64 drow = p.log_n ? (u64)(__brev((u32)pos) >> (32 - p.log_n)) : 0;
+      return drow * p.ld_dst + vidx;
+    }
+    if (plain_out) return (g.row_base + m) * p.V + vidx;
+    u64 lo;
+    u32 col;
+    split_vidx(p, vidx, lo, col);
+    return (((g.row_base + m) << p.l0) + lo) * p.ld_dst + col;
+  };
+  if (!p.scale) {
+    for (u32 u = tid; u < tile_elems * 2; u += THREADS) {
+      const u32 e = u >> 1, half = u & 1;
+      const u32 m = e >> p.log_cv, vc = e & (cv - 1);
+      if (vc >= g.ncv) continue;
+      p.dst[dst_of(m, g.v0 + vc) * 2 + half] = (half ? s_hi : s_lo)[e];
+    }
+  } else {
+    for (u32 e = tid; e < tile_elems; e += THREADS) {
+      const u32 m = e >> p.log_cv, vc = e & (cv - 1);
+      if (vc >= g.ncv) continue;
+      const u64 d = dst_of(m, g.v0 + vc);
+      Fr x = fr_from_units(s_lo[e], s_hi[e]);
+      x = (p.scale == 1) ? fp_mul(p.scale_c, x) : fp_canon_4p<FrParams>(x.v);
+      uint4 lo, hi4;
+      fr_to_units(x, lo, hi4);
+      p.dst[d * 2] = lo;
+      p.dst[d * 2 + 1] = hi4;
+    }
+  }
+}
+
+template <int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) k_ntt_pass_db(const PassParams p, const u64 ntiles) {
+  extern __shared__ uint4 smem[];
+  const u32 tile_elems = (1u << p.r) << p.log_cv;
+  const u32 buf_units = 2 * (tile_elems + 4) + (4u << p.r);  // two 16-byte planes (+64 B skew each) | twiddle pairs
+  const u32 tid = threadIdx.x;
+  u64 tile = blockIdx.x;
+  if (tile >= ntiles) return;
+  u32 b = 0;
+  db_issue_tile<THREADS>(p, tile, smem, smem + tile_elems + 4, smem + 2 * (tile_elems + 4), tid);
+  for (; tile < ntiles; tile += gridDim.x, b ^= 1) {
+    uint4* s_lo = smem + b * buf_units;
+    uint4* s_hi = s_lo + tile_elems + 4;
+    uint4* s_tw = s_hi + tile_elems + 4;
+    const u64 next = tile + gridDim.x;
+    if (next < ntiles) {
+      // the other buffer was last read by the store of the previous iteration, which ended with a barrier
+      uint4* n_lo = smem + (b ^ 1) * buf_units;
+      db_issue_tile<THREADS>(p, next, n_lo, n_lo + tile_elems + 4, n_lo + 2 * (tile_elems + 4), tid);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();
+    db_butterflies<THREADS>(p, tile_geom(p, tile).ncv, s_lo, s_hi, s_tw, tid);
+    db_store_tile<THREADS>(p, tile, s_lo, s_hi, tid);
+    __syncthreads();
+  }
+}
+
 // ---- pass planning ------------------------------------------------------------------------
 struct PassPlan {
   u32 l0, r, log_cv;
 };
 
-static u32 log_cv_for(u64 V) {
+static u32 log_cv_for(u64 V, u32 cap = 4) {
   u32 lc = 0;
-  while (lc < 4 && (1ull << lc) < V) lc++;
-  return lc;  // cv = min(16, next_pow2(V))
+  while (lc < cap && (1ull << lc) < V) lc++;
+  return lc;  // cv = min(2^cap, next_pow2(V))
 }
 static u32 ilog2_u32(u32 x) {
   u32 l = 0;
@@ -549,9 +788,10 @@ static u32 ilog2_u32(u32 x) {
 }
 
 // split layers [first, last) into passes (ascending l0)
-static std::vector<PassPlan> plan_passes(u32 first, u32 last, size_t w) {
+static std::vector<PassPlan> plan_passes(u32 first, u32 last, size_t w, u32 tile_log = 0, u32 cv_cap = 4) {
   std::vector<PassPlan> out;
-  const u32 tile_log = ilog2_u32(ntt_tile_elems());
+  if (!tile_log) tile_log = ilog2_u32(ntt_tile_elems());
+  auto log_cv_for = [&](u64 V) { return eon::log_cv_for(V, cv_cap); };
   auto rmax_at = [&](u32 l0) {
     u64 V = ((u64)w) << l0;
     return tile_log - log_cv_for(V);
@@ -564,10 +804,10 @@ static std::vector<PassPlan> plan_passes(u32 first, u32 last, size_t w) {
   // first a tile row holds only w << first < 16 elements, so an evenly sized first pass would stage a tile of a
   // few hundred elements for 256 threads.  Give that pass all the layers a full tile can hold instead (r = 10 at
   // w = 2) and spread the remaining layers evenly.
-  if (log_cv_for(((u64)w) << first) < 4 && last - first > rmax_at(first)) {
+  if (log_cv_for(((u64)w) << first) < cv_cap && last - first > rmax_at(first)) {
     const u32 r0 = rmax_at(first);
     out.push_back({first, r0, log_cv_for(((u64)w) << first)});
-    std::vector<PassPlan> rest = plan_passes(first + r0, last, w);
+    std::vector<PassPlan> rest = plan_passes(first + r0, last, w, tile_log, cv_cap);
     out.insert(out.end(), rest.begin(), rest.end());
     return out;
   }
@@ -593,6 +833,39 @@ static std::vector<PassPlan> plan_passes(u32 first, u32 last, size_t w) {
   return out;
 }
 
+
+// MEASURED ON B200 (profiles/r02r_ntt_db.txt, 2^20 x 16 commit + LDE): passes 8.79 ms with k_ntt_pass, 9.73 ms
+// double-buffered at 256 threads / 1024-element tiles, 10.41 ms at 512 threads / 2048-element tiles -> OFF by
+// default.  The one-tile-per-CTA kernel at 2 CTAs per SM already hides its loads behind the other CTA; what the
+// persistent form adds is barriers (half the work per barrier interval, or 16 warps per barrier instead of 8).
+// Double-buffered persistent passes (k_ntt_pass_db).  EON_NTT_DB: 0 = off, 1 = 256 threads / 1024-element tiles /
+// 2 CTAs per SM, 2 = 512 threads / 2048-element tiles / 1 CTA per SM.  Used for fixed-operand twiddles on matrices
+// whose width is a power of two >= 8 (every tile then has ONE twiddle set, see k_ntt_pass) and passes with at least
+// two tiles per resident CTA; everything else takes k_ntt_pass.
+static int ntt_db_mode() {
+  static int m = -1;
+  if (m < 0) {
+    const char* e = getenv("EON_NTT_DB");
+    m = e ? atoi(e) : EON_NTT_DB_DEFAULT;
+    if (m < 0 || m > 2) m = 0;
+  }
+  return m;
+}
+static bool ntt_db_shape(size_t w, bool sh) { return sh && ntt_db_mode() && w >= 8 && (w & (w - 1)) == 0; }
+static std::vector<PassPlan> plan_passes_for(u32 first, u32 last, size_t w, bool sh) {
+  if (!ntt_db_shape(w, sh)) return plan_passes(first, last, w);
+  const u32 tile_log = ntt_db_mode() == 1 ? 10 : 11;
+  // layers per pass as if every tile row were 8 elements wide (r <= tile_log - 3); a pass with fewer layers than
+  // that widens its rows (cv = 16) so that the tile keeps its size
+  std::vector<PassPlan> plan = plan_passes(first, last, w, tile_log, 3);
+  for (PassPlan& pl : plan) {
+    const u64 V = ((u64)w) << pl.l0;
+    u32 lc = pl.log_cv;
+    while (lc < 4 && lc + pl.r < tile_log && (2ull << lc) <= V && (2ull << lc) <= w) lc++;
+    pl.log_cv = lc;
+  }
+  return plan;
+}
 
 static int launch_pass(eon_ctx* ctx, PassParams& p, const PassPlan& pl, unsigned log_n, size_t w, bool p_shoup) {
   p.log_n = log_n;
@@ -637,6 +910,23 @@ static int launch_pass(eon_ctx* ctx, PassParams& p, const PassPlan& pl, unsigned
     EON_CUDA(ctx, cudaFuncSetAttribute(k_ntt_pass<2, true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
     ctx->ntt_attr_set = true;
   }
+  if (tws && ntt_db_shape(w, p_shoup)) {
+    const int mode = ntt_db_mode();
+    const u64 resident = (u64)ctx->num_sms * (mode == 1 ? 2 : 1);
+    const size_t buf_units = 2 * (((size_t)1 << (pl.r + pl.log_cv)) + 4) + ((size_t)4 << pl.r);
+    const size_t smem_db = 2 * buf_units * 16;
+    if (grid >= 2 * resident && smem_db <= (mode == 1 ? 100u : 200u) * 1024) {
+      if (!ctx->ntt_db_attr_set) {
+        EON_CUDA(ctx, cudaFuncSetAttribute(k_ntt_pass_db<256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        EON_CUDA(ctx, cudaFuncSetAttribute(k_ntt_pass_db<512, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        ctx->ntt_db_attr_set = true;
+      }
+      if (mode == 1) k_ntt_pass_db<256, 2><<<(unsigned)resident, 256, smem_db, ctx->stream>>>(p, grid);
+      else k_ntt_pass_db<512, 1><<<(unsigned)resident, 512, smem_db, ctx->stream>>>(p, grid);
+      EON_LAUNCHED(ctx);
+      return EON_OK;
+    }
+  }
   if (p_shoup) {  // fixed-operand twiddles: radix-4 quartets only; 2 CTAs per SM unless EON_NTT_MINB asks for 3
     static int minb_sh = -1;
     if (minb_sh < 0) {
@@ -673,7 +963,7 @@ int ntt_forward(eon_ctx* ctx, const Fr* d_src, Fr* d_dst, unsigned log_n, unsign
   const Fr* tw = nullptr;
   const bool sh = ntt_use_shoup();
   EON_TRY(get_twiddles(ctx, log_n, shift, 0, sh, &tw));
-  std::vector<PassPlan> plan = plan_passes(k, log_n, width);
+  std::vector<PassPlan> plan = plan_passes_for(k, log_n, width, sh);
   phase_begin(ctx, PH_NTT_PASSES);
   for (size_t i = 0; i < plan.size(); i++) {
     PassParams p;
@@ -708,7 +998,7 @@ int ntt_inverse(eon_ctx* ctx, const Fr* d_src, Fr* d_dst, unsigned log_n, size_t
   const Fr* tw = nullptr;
   const bool sh = ntt_use_shoup();
   EON_TRY(get_twiddles(ctx, log_n, shift, 1, sh, &tw));
-  std::vector<PassPlan> plan = plan_passes(0, log_n, width);
+  std::vector<PassPlan> plan = plan_passes_for(0, log_n, width, sh);
   const size_t np = plan.size();
   const bool out_rev = (dst_layout == LAYOUT_NATURAL);
   Fr* work = d_dst;

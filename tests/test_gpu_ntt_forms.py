@@ -19,3 +19,14 @@ def test_dft_parity_with_montgomery_twiddles():
     out = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_gpu_dft.py"), "-q", "-x",
                           "-p", "no:cacheprovider"], cwd=ROOT, env=env, capture_output=True, text=True, timeout=900)
     assert out.returncode == 0 and " passed" in out.stdout, out.stdout[-3000:] + out.stderr[-2000:]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["1", "2"])
+def test_dft_parity_with_double_buffered_passes(mode):
+    """EON_NTT_DB selects the persistent double-buffered pass kernel (k_ntt_pass_db, off by default: measured
+    slower): same butterflies, so the same canonical limbs."""
+    env = dict(os.environ, EON_NTT_DB=mode)
+    out = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_gpu_dft.py"), "-q", "-x",
+                          "-p", "no:cacheprovider"], cwd=ROOT, env=env, capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0 and " passed" in out.stdout, out.stdout[-3000:] + out.stderr[-2000:]
