@@ -724,7 +724,9 @@ def run_eon(args):
     else:
         for _ in range(max(1, args.warmup)):                    # the same W untimed steps as the device leg
             step_e2e()
+        ctx.phase_reset()
         ms_e2e = H.timed(step_e2e, args.steps)
+        phases_e2e = ctx.phase_ms()    # GPU time of every phase inside the host-buffer steps (streams overlap)
         ok = bool(np.array_equal(commits, commits_first))
         # the LDE that came back over PCIe == the device-resident one (this rank's columns of the host result)
         ok = ok and bool(np.array_equal(lde_pin_np[:, c0:c1], d_lde.cpu().numpy().view(np.uint64)))
@@ -951,6 +953,7 @@ def run_eon(args):
                      "eon_kzg_commit_lde_ld (Pcs::commit with an LDE hint) on this rank's columns of the pinned host "
                      "matrix, LDE columns written back into the pinned host result"),
             "strided_ms_per_step": ms_e2e_strided / args.steps,
+            "phase_ms_per_step": {k: v / args.steps for k, v in phases_e2e.items()},
             "rowblock_ms_per_step": (ms_rowblock / args.steps) if ms_rowblock is not None else None,
             "two_calls_ms_per_step": ms_e2e2 / args.steps, "two_calls_value": units / (ms_e2e2 * 1e-3),
             "two_calls": "eon_kzg_commit_ld then eon_kzg_evals_on_coset_ld (unhinted Pcs::commit + "

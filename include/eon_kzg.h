@@ -155,7 +155,9 @@ unsigned eon_srs_window_bits(const eon_ctx* ctx);
  * -1 = automatic (3 rounds once buckets average >= 64 entries).  Results are identical either way. */
 int eon_msm_set_rounds(eon_ctx* ctx, int rounds);
 /* how entries are sorted by bucket: 0 = one pass of global atomics, 1 = coarse + fine coalesced
- * passes (csrc/msm_sort.cu), -1 = automatic.  Results are identical either way. */
+ * passes (csrc/msm_sort.cu; with the slice schedule the sort also writes round 0's pair records), 2 = the same
+ * passes with entries and pair records built separately (the unfused flow), -1 = automatic.  Results are
+ * identical either way. */
 int eon_msm_set_sort_mode(eon_ctx* ctx, int mode);
 /* order in which round 0 of the pairwise rounds walks its pairs: 1 = by 64 MiB slice of the base table
  * (the gathers of a multi-column commit then hit the L2 instead of DRAM; csrc/msm_tree.cu), 0 = in slot

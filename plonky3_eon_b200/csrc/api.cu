@@ -6,6 +6,7 @@
 #include <functional>
 
 #include "common.cuh"
+#include "msm.cuh"
 
 using namespace eon;
 
@@ -414,7 +415,7 @@ int eon_srs_set_window_tables(eon_ctx* ctx, unsigned window_bits) {
 unsigned eon_srs_window_bits(const eon_ctx* ctx) { return ctx ? ctx->srs_tab_c : 0; }
 
 int eon_msm_set_sort_mode(eon_ctx* ctx, int mode) {
-  if (!ctx || mode < -1 || mode > 1) return EON_ERR_BAD_ARG;
+  if (!ctx || mode < -1 || mode > 2) return EON_ERR_BAD_ARG;
   Lock lk(ctx);
   ctx->msm_sort_mode = mode;
   return EON_OK;
@@ -683,10 +684,23 @@ static int kzg_commit_locked(eon_ctx* ctx, const uint64_t* d_evals, unsigned log
   size_t cap = 0;
   EON_TRY(coeff_buffer_get(ctx, mat_bytes(log_h, width) + 32, &d_coeffs, &cap));
   int rc = ntt_inverse(ctx, (const Fr*)d_evals, d_coeffs, log_h, width, s, LAYOUT_NATURAL);
-  if (rc == EON_OK && want_lde) rc = lde_on_aux(ctx, d_coeffs, d_lde, lde_log_size, lde_log_size - log_h, width, ls, width, 19);
+  // The LDE transform is queued BEHIND round 0 of the MSM (hook in msm_tree_rounds): the sort passes leave no
+  // shared memory for a transform CTA beside them, round 0 lives on its table slice staying in the L2 (a transform
+  // streaming 1.5 GB through it at the same time cost 3-5 ms when the two happened to meet), and what the transform
+  // can really fill are the single-warp phases after it -- the inversion trees of rounds 1-2, the bucket reduction.
+  // EON_LDE_AFTER_R0=0: queued before the MSM, as in round 1.
+  static const int lde_after_r0 = getenv("EON_LDE_AFTER_R0") ? atoi(getenv("EON_LDE_AFTER_R0")) : 1;
+  const bool hook = want_lde && msm_prio_enabled() && lde_after_r0;
+  auto queue_lde = [&] { return lde_on_aux(ctx, d_coeffs, d_lde, lde_log_size, lde_log_size - log_h, width, ls, width, 19); };
+  if (rc == EON_OK && want_lde && !hook) rc = queue_lde();
   if (rc == EON_OK) {
     if (want_lde && msm_prio_enabled()) {
+      if (hook) ctx->after_round0 = queue_lde;
       rc = msm_on_prio(ctx, 18, [&] { return msm_to_host(ctx, ctx->d_srs, d_coeffs, h, width, width, h_commit_xy); });
+      if (ctx->after_round0) {  // the MSM had no pairwise rounds (small input) or failed before them
+        ctx->after_round0 = nullptr;
+        if (rc == EON_OK) rc = queue_lde();
+      }
       if (rc == EON_OK) rc = msm_prio_join(ctx, 18);
     } else {
       rc = msm_to_host(ctx, ctx->d_srs, d_coeffs, h, width, width, h_commit_xy);
@@ -907,6 +921,18 @@ static int kzg_commit_host(eon_ctx* ctx, const uint64_t* h_evals, size_t h_ld_in
     if (e == cudaSuccess) e = cudaEventRecord(ctx->ev_pipe[g], ctx->copy_stream);
     if (e != cudaSuccess) rc = fail(ctx, EON_ERR_CUDA, std::string("group upload failed: ") + cudaGetErrorString(e));
   }
+  // The MSM's digit / sort passes of a group are queued right behind its iDFT: they run while the next groups are
+  // still crossing PCIe (2.6 ms per group of 4 columns at 2^20 rows against 0.7 ms of iDFT), and only the pairwise
+  // rounds onwards -- which need every column in the same launch -- wait for the last group.  EON_PIPE_EARLY_SORT=0:
+  // the whole MSM after the last group.
+  static const int early_sort_env = getenv("EON_PIPE_EARLY_SORT") ? atoi(getenv("EON_PIPE_EARLY_SORT")) : 1;
+  MsmBatch msm_batch_state;
+  bool early_sort = false;
+  if (rc == EON_OK && !msm_per_group && early_sort_env && groups.size() > 1) {
+    const int brc = msm_stream_begin(ctx, ctx->d_srs, h, width, &msm_batch_state);
+    if (brc < 0) rc = brc;
+    early_sort = brc == EON_OK;
+  }
   for (size_t g = 0; rc == EON_OK && g < groups.size(); g++) {
     const size_t c0 = groups[g].first, gw = groups[g].second;
     cudaStreamWaitEvent(ctx->stream, ctx->ev_pipe[g], 0);
@@ -917,6 +943,14 @@ static int kzg_commit_host(eon_ctx* ctx, const uint64_t* h_evals, size_t h_ld_in
       rc = lde_on_aux(ctx, d_coeffs + c0, (Fr*)d_lde + c0, lde_log_size, lde_log_size - log_h, gw, ls, width, 8 + (int)g);
       if (rc == EON_OK) {
         cudaError_t e = cudaStreamWaitEvent(ctx->copy_stream2, ctx->ev_pipe[8 + g], 0);
+        // Downloads start when the LAST upload is through: the MSM's rounds cannot start before the last group is
+        // on the device, so the uploads are on the critical path, while the downloads have the whole of the rounds
+        // (30 ms at 2^20 x 16) to hide under -- and PCIe traffic in both directions at once slows the uploads
+        // (measured: e2e 47.98 ms with the two directions overlapped).  EON_PIPE_D2H_EARLY=1: as soon as a group's
+        // LDE is done.
+        static const int d2h_early = getenv("EON_PIPE_D2H_EARLY") ? atoi(getenv("EON_PIPE_D2H_EARLY")) : 0;
+        if (e == cudaSuccess && !d2h_early && g == 0 && groups.size() > 1)
+          e = cudaStreamWaitEvent(ctx->copy_stream2, ctx->ev_pipe[groups.size() - 1], 0);
         if (e == cudaSuccess)
           e = cudaMemcpy2DAsync((Fr*)h_lde_out + c0, hpitch_out, (const Fr*)d_lde + c0, pitch, gw * sizeof(Fr), lde_rows,
                                 cudaMemcpyDeviceToHost, ctx->copy_stream2);
@@ -928,9 +962,11 @@ static int kzg_commit_host(eon_ctx* ctx, const uint64_t* h_evals, size_t h_ld_in
     // 52.9 ms this way, 64.2 ms with the MSM on the high-priority stream)
     if (rc == EON_OK && msm_per_group)
       rc = msm_run(ctx, ctx->d_srs, d_coeffs + c0, h, gw, width, (G1Affine*)d_commit + c0);
+    if (rc == EON_OK && early_sort) rc = msm_batch_sort(ctx, msm_batch_state, d_coeffs + c0, width, c0, gw);
   }
   // one MSM over all columns, after the last group's iDFT (the uploads and the LDE downloads are long under way)
-  if (rc == EON_OK && !msm_per_group) rc = msm_run(ctx, ctx->d_srs, d_coeffs, h, width, width, (G1Affine*)d_commit);
+  if (rc == EON_OK && early_sort) rc = msm_batch_finish(ctx, msm_batch_state, (G1Affine*)d_commit);
+  else if (rc == EON_OK && !msm_per_group) rc = msm_run(ctx, ctx->d_srs, d_coeffs, h, width, width, (G1Affine*)d_commit);
   if (rc == EON_OK) {
     cudaError_t e = cudaMemcpyAsync(h_commit_xy, d_commit, width * sizeof(G1Affine), cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);

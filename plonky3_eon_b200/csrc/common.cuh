@@ -5,6 +5,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <functional>
 #include <map>
 #include <mutex>
 #include <string>
@@ -78,6 +79,7 @@ enum ScratchId {
   SC_MSM_SORT_REGION,
   SC_MSM_SORT_PAY,
   SC_MSM_SORT_KEY,
+  SC_MSM_SORT_MAT,
   SC_MSM_SEGTOTAL,
   SC_MSM_SLICE,
   SC_IO_A,
@@ -105,6 +107,9 @@ struct eon_ctx {
   std::map<eon::TwiddleKey, eon::Fr*> twiddles;
   size_t twiddle_bytes = 0;  // device bytes behind `twiddles` (bounded: see get_twiddles)
   // opt-in shared-memory sizes (cudaFuncSetAttribute) are per device: set once per context, not per process
+  // run once by msm_tree_rounds right after round 0 of the next MSM has been queued (then cleared): the device-
+  // resident commit + LDE queues its LDE transform there, behind round 0 (see kzg_commit_locked)
+  std::function<int()> after_round0;
   bool ntt_attr_set = false;
   bool ntt_db_attr_set = false;
   bool sort_attr_set = false;

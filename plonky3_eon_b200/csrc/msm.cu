@@ -569,73 +569,112 @@ static void msm_set_rounds(MsmShape& sh, size_t n, u32 rounds) {
   sh.seg_cap = rounds ? ((raw + (u64)sh.NB * (al - 1) + al - 1) & ~(al - 1)) : raw;
 }
 
-static int msm_batch(eon_ctx* ctx, const G1Affine* d_bases, const Fr* d_scalars, size_t n, size_t ncols, size_t ld,
-                     const MsmShape& sh, G1Affine* d_out) {
+// One batch of an MSM in three steps, so that the sort of a column group can be queued as soon as that group's
+// scalars exist (the host-buffer commit sorts group g while group g + 1 is still crossing PCIe, msm_stream_*):
+// msm_batch_setup (workspace, slice plan), msm_batch_sort (columns [c0, c0 + nc): digits, histogram, scan, sort --
+// every column is its own segment, so the groups write disjoint parts of the same arrays), msm_batch_finish
+// (pairwise rounds, finisher, bucket reduction over ALL columns of the batch at once: the slice schedule of round 0
+// needs every column in the same launch).
+int msm_batch_setup(eon_ctx* ctx, const G1Affine* d_bases, size_t n, size_t ncols, const MsmShape& sh, MsmBatch* B) {
+  B->bases = d_bases;
+  B->n = n;
+  B->ncols = ncols;
+  B->sh = sh;
   const size_t nseg = ncols * sh.nsets;
   const size_t total_buckets = nseg * sh.NB;
-  const u32 chunk_min = 256u << sh.rounds;  // entry slots per split-off task: 256 addends in the finisher
-  size_t max_tasks_sz = (nseg * sh.seg_cap) / chunk_min + 1024;
+  B->chunk_min = 256u << sh.rounds;  // entry slots per split-off task: 256 addends in the finisher
+  size_t max_tasks_sz = (nseg * sh.seg_cap) / B->chunk_min + 1024;
   if (max_tasks_sz > 0x7fffffffull) max_tasks_sz = 0x7fffffffull;
-  const u32 max_tasks = (u32)max_tasks_sz;
+  B->max_tasks = (u32)max_tasks_sz;
   if (sh.seg_cap >= 0xffffffffull) return fail(ctx, EON_ERR_BAD_ARG, "msm: segment too large");
-
-  void *p_hist, *p_cur, *p_ent, *p_bkt, *p_tasks, *p_tpart, *p_part, *p_seg, *p_misc, *p_ord;
-  EON_TRY(scratch_get(ctx, SC_MSM_ORDER, total_buckets * sizeof(u32), &p_ord));
-  EON_TRY(scratch_get(ctx, SC_MSM_HIST, total_buckets * sizeof(u32), &p_hist));
-  EON_TRY(scratch_get(ctx, SC_MSM_CURSOR, total_buckets * sizeof(u32), &p_cur));
-  EON_TRY(scratch_get(ctx, SC_MSM_ENTRIES, nseg * sh.seg_cap * sizeof(u32), &p_ent));
-  EON_TRY(scratch_get(ctx, SC_MSM_BUCKETS, total_buckets * sizeof(G1Xyzz), &p_bkt));
-  EON_TRY(scratch_get(ctx, SC_MSM_TASKS, (size_t)max_tasks * sizeof(MsmTask), &p_tasks));
-  EON_TRY(scratch_get(ctx, SC_MSM_TASKPART, (size_t)max_tasks * sizeof(G1Xyzz), &p_tpart));
-  // row sums, column sums (<= 2^ceil((c-1)/2) each) and 3 partial results per segment of the bucket reduction
-  EON_TRY(scratch_get(ctx, SC_MSM_PARTIALS, nseg * ((size_t)2 << ((sh.c - 1 + 1) / 2)) * sizeof(G1Xyzz) + nseg * 3 * sizeof(G1Xyzz),
-                      &p_part));
-  EON_TRY(scratch_get(ctx, SC_MSM_SEGSUM, nseg * sizeof(G1Xyzz), &p_seg));
-  EON_TRY(scratch_get(ctx, SC_MSM_MISC, 256, &p_misc));
-  void* p_segtot;
-  EON_TRY(scratch_get(ctx, SC_MSM_SEGTOTAL, nseg * sizeof(u32), &p_segtot));
-  u32* d_ntasks = (u32*)p_misc;
-  cudaStream_t st = ctx->stream;
   const size_t grid_pts_sz = ((n + MSM_THREADS - 1) / MSM_THREADS) * ncols;
   if (grid_pts_sz > 0x7fffffffull) return fail(ctx, EON_ERR_BAD_ARG, "msm: grid too large");
-  const unsigned grid_pts = (unsigned)grid_pts_sz;
 
-  const SlicePlan plan = msm_slice_plan(ctx, sh.merged ? (u64)sh.W * sh.tab_stride : (u64)n, (u64)nseg * sh.seg_cap,
-                                        sh.rounds);
+  EON_TRY(scratch_get(ctx, SC_MSM_ORDER, total_buckets * sizeof(u32), &B->p_ord));
+  EON_TRY(scratch_get(ctx, SC_MSM_HIST, total_buckets * sizeof(u32), &B->p_hist));
+  EON_TRY(scratch_get(ctx, SC_MSM_CURSOR, total_buckets * sizeof(u32), &B->p_cur));
+  EON_TRY(scratch_get(ctx, SC_MSM_ENTRIES, nseg * sh.seg_cap * sizeof(u32), &B->p_ent));
+  EON_TRY(scratch_get(ctx, SC_MSM_BUCKETS, total_buckets * sizeof(G1Xyzz), &B->p_bkt));
+  EON_TRY(scratch_get(ctx, SC_MSM_TASKS, (size_t)B->max_tasks * sizeof(MsmTask), &B->p_tasks));
+  EON_TRY(scratch_get(ctx, SC_MSM_TASKPART, (size_t)B->max_tasks * sizeof(G1Xyzz), &B->p_tpart));
+  // row sums, column sums (<= 2^ceil((c-1)/2) each) and 3 partial results per segment of the bucket reduction
+  EON_TRY(scratch_get(ctx, SC_MSM_PARTIALS, nseg * ((size_t)2 << ((sh.c - 1 + 1) / 2)) * sizeof(G1Xyzz) + nseg * 3 * sizeof(G1Xyzz),
+                      &B->p_part));
+  EON_TRY(scratch_get(ctx, SC_MSM_SEGSUM, nseg * sizeof(G1Xyzz), &B->p_seg));
+  EON_TRY(scratch_get(ctx, SC_MSM_MISC, 256, &B->p_misc));
+  EON_TRY(scratch_get(ctx, SC_MSM_SEGTOTAL, nseg * sizeof(u32), &B->p_segtot));
+  B->plan = msm_slice_plan(ctx, sh.merged ? (u64)sh.W * sh.tab_stride : (u64)n, (u64)nseg * sh.seg_cap, sh.rounds);
+  EON_CUDA(ctx, cudaMemsetAsync(B->p_misc, 0, sizeof(u32), ctx->stream));
+  B->place_deferred = false;
+  if (B->plan.on) EON_TRY(msm_sort_begin(ctx));
+  return EON_OK;
+}
 
-  EON_CUDA(ctx, cudaMemsetAsync(d_ntasks, 0, sizeof(u32), st));
-  {
-    static int env_mode = -2;
-    if (env_mode == -2) {
-      const char* e = getenv("EON_MSM_SORT");
-      env_mode = e ? atoi(e) : -1;
-    }
-    const int mode = ctx->msm_sort_mode >= 0 ? ctx->msm_sort_mode : env_mode;
-    int rc = 1;
-    // coalesced multi-pass sort (msm_sort.cu), which also produces the bucket histogram; small inputs and
-    // unsupported shapes: global histogram + one-pass atomic scatter
-    if (mode != 0 && (mode == 1 || n >= 4096))
-      rc = msm_sort_entries(ctx, d_scalars, n, ncols, ld, sh, plan, (u32*)p_hist, (u32*)p_segtot, (u32*)p_cur,
-                            (u32*)p_ent);
-    if (rc < 0) return rc;
-    if (rc > 0) {
-      phase_begin(ctx, PH_MSM_DIGITS);
-      EON_CUDA(ctx, cudaMemsetAsync(p_hist, 0, total_buckets * sizeof(u32), st));
-      k_msm_hist<<<grid_pts, MSM_THREADS, 0, st>>>(d_scalars, n, ld, (u32)ncols, sh, (u32*)p_hist);
-      EON_LAUNCHED(ctx);
-      phase_end(ctx, PH_MSM_DIGITS);
-      phase_begin(ctx, PH_MSM_SCAN);
-      EON_TRY(msm_scan_run(ctx, (u32*)p_hist, (u32*)p_cur, sh.NB, 1u << sh.rounds, (u32*)p_segtot, nseg));
-      phase_end(ctx, PH_MSM_SCAN);
-      phase_begin(ctx, PH_MSM_SCATTER);
-      if (sh.rounds)  // unused slots (bucket padding, segment tails) must read as ENTRY_NONE
-        EON_CUDA(ctx, cudaMemsetAsync(p_ent, 0xff, nseg * sh.seg_cap * sizeof(u32), st));
-      k_msm_scatter<<<grid_pts, MSM_THREADS, 0, st>>>(d_scalars, n, ld, (u32)ncols, sh, (u32*)p_cur, (u32*)p_ent);
-      EON_LAUNCHED(ctx);
-      phase_end(ctx, PH_MSM_SCATTER);
-    }
+int msm_batch_sort(eon_ctx* ctx, MsmBatch& S, const Fr* d_scalars, size_t ld, size_t c0, size_t nc) {
+  const MsmShape& sh = S.sh;
+  const size_t n = S.n;
+  const size_t seg0 = c0 * sh.nsets, nseg = nc * sh.nsets;
+  u32* d_hist = (u32*)S.p_hist + seg0 * sh.NB;
+  u32* d_cur = (u32*)S.p_cur + seg0 * sh.NB;
+  u32* d_ent = (u32*)S.p_ent + seg0 * sh.seg_cap;
+  u32* d_segtot = (u32*)S.p_segtot + seg0;
+  const size_t total_buckets = nseg * sh.NB;
+  cudaStream_t st = ctx->stream;
+  const unsigned grid_pts = (unsigned)(((n + MSM_THREADS - 1) / MSM_THREADS) * nc);
+  static int env_mode = -2;
+  if (env_mode == -2) {
+    const char* e = getenv("EON_MSM_SORT");
+    env_mode = e ? atoi(e) : -1;
   }
+  const int mode = ctx->msm_sort_mode >= 0 ? ctx->msm_sort_mode : env_mode;
+  int rc = 1;
+  // coalesced multi-pass sort (msm_sort.cu), which also produces the bucket histogram; small inputs and
+  // unsupported shapes: global histogram + one-pass atomic scatter
+  if (mode != 0 && (mode >= 1 || n >= 4096)) {
+    bool deferred = false;
+    rc = msm_sort_entries(ctx, d_scalars, n, nc, ld, sh, S.plan, seg0, S.ncols * sh.nsets, (u32*)S.p_hist,
+                          (u32*)S.p_segtot, (u32*)S.p_cur, (u32*)S.p_ent, &deferred);
+    if (rc == EON_OK && deferred) S.place_deferred = true;
+  }
+  if (rc < 0) return rc;
+  if (rc > 0) {
+    phase_begin(ctx, PH_MSM_DIGITS);
+    EON_CUDA(ctx, cudaMemsetAsync(d_hist, 0, total_buckets * sizeof(u32), st));
+    k_msm_hist<<<grid_pts, MSM_THREADS, 0, st>>>(d_scalars, n, ld, (u32)nc, sh, d_hist);
+    EON_LAUNCHED(ctx);
+    phase_end(ctx, PH_MSM_DIGITS);
+    phase_begin(ctx, PH_MSM_SCAN);
+    EON_TRY(msm_scan_run(ctx, d_hist, d_cur, sh.NB, 1u << sh.rounds, d_segtot, nseg));
+    phase_end(ctx, PH_MSM_SCAN);
+    phase_begin(ctx, PH_MSM_SCATTER);
+    if (sh.rounds)  // unused slots (bucket padding, segment tails) must read as ENTRY_NONE
+      EON_CUDA(ctx, cudaMemsetAsync(d_ent, 0xff, nseg * sh.seg_cap * sizeof(u32), st));
+    k_msm_scatter<<<grid_pts, MSM_THREADS, 0, st>>>(d_scalars, n, ld, (u32)nc, sh, d_cur, d_ent);
+    EON_LAUNCHED(ctx);
+    phase_end(ctx, PH_MSM_SCATTER);
+  }
+  return EON_OK;
+}
 
+int msm_batch_finish(eon_ctx* ctx, const MsmBatch& S, G1Affine* d_out) {
+  const MsmShape& sh = S.sh;
+  const size_t ncols = S.ncols;
+  const size_t nseg = ncols * sh.nsets;
+  const size_t total_buckets = nseg * sh.NB;
+  const u32 chunk_min = S.chunk_min, max_tasks = S.max_tasks;
+  void *p_hist = S.p_hist, *p_cur = S.p_cur, *p_ent = S.p_ent, *p_bkt = S.p_bkt, *p_tasks = S.p_tasks,
+       *p_tpart = S.p_tpart, *p_part = S.p_part, *p_seg = S.p_seg, *p_ord = S.p_ord;
+  u32* d_ntasks = (u32*)S.p_misc;
+  const G1Affine* d_bases = S.bases;
+  const SlicePlan& plan = S.plan;
+  cudaStream_t st = ctx->stream;
+
+  if (S.place_deferred) {  // fused sort: placement of all segments + the pair records of round 0
+    uint2* rec_e = nullptr;
+    u32* rec_dest = nullptr;
+    EON_TRY(msm_tree_records(ctx, (u64)nseg * sh.seg_cap, &rec_e, &rec_dest));
+    EON_TRY(msm_sort_place(ctx, sh, plan, nseg, (u32*)p_hist, (u32*)S.p_segtot, (u32*)p_cur, (u32*)p_ent, rec_e, rec_dest));
+  }
   if (ctx->ev_stagger) {  // two-stream split: the second half-batch starts here (see msm_run)
     EON_CUDA(ctx, cudaEventRecord(ctx->ev_stagger, st));
     ctx->ev_stagger = nullptr;
@@ -649,7 +688,8 @@ static int msm_batch(eon_ctx* ctx, const G1Affine* d_bases, const Fr* d_scalars,
     src.pts = nullptr;
     src.rshift = sh.rounds;
     if (sh.rounds)
-      EON_TRY(msm_tree_rounds(ctx, d_bases, plan, (const u32*)p_ent, (u64)nseg * sh.seg_cap, sh.rounds, &src.pts));
+      EON_TRY(msm_tree_rounds(ctx, d_bases, plan, (const u32*)p_ent, (u64)nseg * sh.seg_cap, sh.rounds, &src.pts,
+                              S.place_deferred));
     phase_begin(ctx, PH_MSM_FINISH);
     k_msm_order<<<(unsigned)nseg, 1024, 0, st>>>((const u32*)p_hist, (const u32*)p_cur, sh.NB, sh.rounds, (u32*)p_ord);
     EON_LAUNCHED(ctx);
@@ -708,15 +748,18 @@ static int msm_batch(eon_ctx* ctx, const G1Affine* d_bases, const Fr* d_scalars,
   return EON_OK;
 }
 
-int msm_run(eon_ctx* ctx, const G1Affine* d_bases, const Fr* d_scalars, size_t n, size_t ncols, size_t ld,
-            G1Affine* d_out) {
-  if (ncols == 0) return EON_OK;
-  if (n == 0) {  // empty MSM -> identity (curve.rs:165-167)
-    k_fill_identity<<<(unsigned)((ncols + 255) / 256), 256, 0, ctx->stream>>>(d_out, ncols);
-    EON_LAUNCHED(ctx);
-    return EON_OK;
-  }
-  if (n >= 0x7fffffffull) return fail(ctx, EON_ERR_BAD_ARG, "msm: more than 2^31 - 1 points");
+static int msm_batch(eon_ctx* ctx, const G1Affine* d_bases, const Fr* d_scalars, size_t n, size_t ncols, size_t ld,
+                     const MsmShape& sh, G1Affine* d_out) {
+  MsmBatch B;
+  EON_TRY(msm_batch_setup(ctx, d_bases, n, ncols, sh, &B));
+  EON_TRY(msm_batch_sort(ctx, B, d_scalars, ld, 0, ncols));
+  return msm_batch_finish(ctx, B, d_out);
+}
+
+// Shape of an MSM over d_bases (window tables when the bases lie inside the resident SRS), pairwise rounds, and the
+// number of columns one batch may hold.
+static void msm_select(eon_ctx* ctx, const G1Affine* d_bases, size_t n, MsmShape* out_sh, const G1Affine** out_bases,
+                       size_t* out_batch) {
   MsmShape sh = msm_shape_plain(n);
   const G1Affine* bases = d_bases;
   // bases inside the resident SRS and window tables available: all windows share one bucket set
@@ -755,6 +798,40 @@ int msm_run(eon_ctx* ctx, const G1Affine* d_bases, const Fr* d_scalars, size_t n
   size_t batch = budget / per_col;
   if (batch < 1) batch = 1;
   if (batch > 64) batch = 64;
+  *out_sh = sh;
+  *out_bases = bases;
+  *out_batch = batch;
+}
+
+// ---- an MSM whose sort is queued per column group (see msm_batch_setup) -----------------------------------------
+// msm_stream_begin returns 1 (nothing queued) when the MSM would not run as ONE unsplit batch: the caller then uses
+// msm_run after the last group.
+int msm_stream_begin(eon_ctx* ctx, const G1Affine* d_bases, size_t n, size_t ncols, MsmBatch* B) {
+  if (n == 0 || ncols == 0 || n >= 0x7fffffffull) return 1;
+  MsmShape sh;
+  const G1Affine* bases;
+  size_t batch;
+  msm_select(ctx, d_bases, n, &sh, &bases, &batch);
+  static const int split_env = getenv("EON_MSM_SPLIT") ? atoi(getenv("EON_MSM_SPLIT")) : -1;
+  const int split_mode = ctx->msm_split_mode >= 0 ? ctx->msm_split_mode : split_env;
+  // several batches, or the two-stream split of few columns (msm_run)
+  if (ncols > batch || split_mode == 1 || (split_mode != 0 && ncols <= 4)) return 1;
+  return msm_batch_setup(ctx, bases, n, ncols, sh, B);
+}
+
+int msm_run(eon_ctx* ctx, const G1Affine* d_bases, const Fr* d_scalars, size_t n, size_t ncols, size_t ld,
+            G1Affine* d_out) {
+  if (ncols == 0) return EON_OK;
+  if (n == 0) {  // empty MSM -> identity (curve.rs:165-167)
+    k_fill_identity<<<(unsigned)((ncols + 255) / 256), 256, 0, ctx->stream>>>(d_out, ncols);
+    EON_LAUNCHED(ctx);
+    return EON_OK;
+  }
+  if (n >= 0x7fffffffull) return fail(ctx, EON_ERR_BAD_ARG, "msm: more than 2^31 - 1 points");
+  MsmShape sh;
+  const G1Affine* bases;
+  size_t batch;
+  msm_select(ctx, d_bases, n, &sh, &bases, &batch);
   // Few columns: two half-batches on two streams.  A batch of 2 columns of 2^20 points spends ~1.8 of its 6.8 ms in
   // phases that leave the GPU idle (three inversion trees, the bucket reduction: single-warp dependent chains);
   // with two independent halves in flight those phases of one half run under the wide kernels of the other.

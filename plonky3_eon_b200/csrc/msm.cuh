@@ -42,8 +42,11 @@ struct SlicePlan {
 constexpr u32 SLICE_ORDER_MAX = 32;
 // nbases = number of points addressable through d_bases (all window-table levels).
 SlicePlan msm_slice_plan(const eon_ctx* ctx, u64 nbases, u64 total_slots, u32 rounds);
+// records_ready: the pair records of the slice schedule have been written by the sort (msm_sort_place) into the
+// arrays msm_tree_records names; d_entries is then not read.
 int msm_tree_rounds(eon_ctx* ctx, const G1Affine* d_bases, const SlicePlan& plan, const u32* d_entries,
-                    u64 total_slots, u32 rounds, const G1Affine** out_pts);
+                    u64 total_slots, u32 rounds, const G1Affine** out_pts, bool records_ready = false);
+int msm_tree_records(eon_ctx* ctx, u64 total_slots, uint2** rec_e, u32** rec_dest);
 
 
 // Counting sort of the (point, window) entries by bucket in coalesced passes (msm_sort.cu): bin histogram,
@@ -55,10 +58,40 @@ int msm_tree_rounds(eon_ctx* ctx, const G1Affine* d_bases, const SlicePlan& plan
 // caller falls back to the global histogram + one-pass atomic scatter).
 // plan.on: the entries of every bucket are additionally ordered by table slice (so that round 0 pairs operands
 // of the same slice); any order inside a bucket gives the same sums.
+// The array arguments are those of the whole batch (nseg_total segments); the call handles the segments
+// [seg0, seg0 + ncols * nsets).  With the slice schedule the sort takes a fused form: *deferred = true means the group
+// has been sorted coarsely and counted, and msm_sort_place (once per batch, after the last group) places everything
+// and writes the pair records round 0 walks, instead of the entry array.  msm_sort_begin: once per batch, before
+// the first group.
+int msm_sort_begin(eon_ctx* ctx);
 int msm_sort_entries(eon_ctx* ctx, const Fr* d_scalars, size_t n, size_t ncols, size_t ld, const MsmShape& sh,
-                     const SlicePlan& plan, u32* d_hist, u32* d_seg_total, u32* d_cur, u32* d_entries);
+                     const SlicePlan& plan, size_t seg0, size_t nseg_total, u32* d_hist, u32* d_seg_total, u32* d_cur,
+                     u32* d_entries, bool* deferred);
+int msm_sort_place(eon_ctx* ctx, const MsmShape& sh, const SlicePlan& plan, size_t nseg_total, u32* d_hist,
+                   u32* d_seg_total, u32* d_cur, u32* d_entries, uint2* rec_e, u32* rec_dest);
 // aligned exclusive scan of the bucket histogram, one block per segment (k_msm_scan, msm.cu)
 int msm_scan_run(eon_ctx* ctx, u32* d_hist, u32* d_cur, u32 NB, u32 align, u32* d_seg_total, size_t nseg);
+
+// One batch of an MSM (msm.cu): workspace, shape and slice plan, so that the sort can be queued per column group
+// before the pairwise rounds / finisher / reduction run over all columns of the batch.
+struct MsmBatch {
+  const G1Affine* bases = nullptr;
+  size_t n = 0, ncols = 0;
+  MsmShape sh;
+  SlicePlan plan;
+  u32 chunk_min = 0, max_tasks = 0;
+  bool place_deferred = false;  // set by msm_batch_sort: msm_batch_finish runs msm_sort_place first
+  void *p_hist = nullptr, *p_cur = nullptr, *p_ent = nullptr, *p_bkt = nullptr, *p_tasks = nullptr, *p_tpart = nullptr,
+       *p_part = nullptr, *p_seg = nullptr, *p_misc = nullptr, *p_ord = nullptr, *p_segtot = nullptr;
+};
+int msm_batch_setup(eon_ctx* ctx, const G1Affine* d_bases, size_t n, size_t ncols, const MsmShape& sh, MsmBatch* B);
+// columns [c0, c0 + nc) of the batch: d_scalars points at column c0 (row pitch ld)
+int msm_batch_sort(eon_ctx* ctx, MsmBatch& B, const Fr* d_scalars, size_t ld, size_t c0, size_t nc);
+int msm_batch_finish(eon_ctx* ctx, const MsmBatch& B, G1Affine* d_out);
+// An MSM over the resident SRS whose sort is queued group by group (host-buffer commit: group g is sorted while
+// group g + 1 crosses PCIe).  begin returns 1 without queueing anything when the MSM would not run as one unsplit
+// batch; the caller then falls back to msm_run.  Then msm_batch_sort per group and msm_batch_finish.
+int msm_stream_begin(eon_ctx* ctx, const G1Affine* d_bases, size_t n, size_t ncols, MsmBatch* B);
 
 #if defined(__CUDACC__)
 // ---- 1. scalar -> signed window digits --------------------------------------------------------

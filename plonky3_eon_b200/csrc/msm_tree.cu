@@ -523,8 +523,19 @@ static void launch_sliced(bool fwd, unsigned grid, cudaStream_t st, const uint2*
   else k_tree_bwd_sliced<B><<<grid, TREE_THREADS, 0, st>>>(rec_e, rec_dest, npairs, bases, T0, pre, out_x, out_y, ostride);
 }
 
+// Where the pair records of the slice schedule live: round 1's output buffer, which is idle during round 0 (12 bytes
+// per pair against the 32 bytes per pair of that buffer).  Also called by the fused sort, which writes them.
+int msm_tree_records(eon_ctx* ctx, u64 total_slots, uint2** rec_e, u32** rec_dest) {
+  const u64 m0 = total_slots / 2;
+  void* bufB;
+  EON_TRY(scratch_get(ctx, SC_MSM_TREE_B, (m0 / 2 + 1) * sizeof(G1Affine), &bufB));
+  *rec_e = (uint2*)bufB;
+  *rec_dest = (u32*)(*rec_e + m0);
+  return EON_OK;
+}
+
 int msm_tree_rounds(eon_ctx* ctx, const G1Affine* d_bases, const SlicePlan& plan, const u32* d_entries,
-                    u64 total_slots, u32 rounds, const G1Affine** out_pts) {
+                    u64 total_slots, u32 rounds, const G1Affine** out_pts, bool records_ready) {
   const u64 TREE_B = (u64)tree_b(total_slots / 2);
   if (rounds == 0 || (total_slots & ((1ull << rounds) - 1)))
     return fail(ctx, EON_ERR_BAD_ARG, "msm_tree_rounds: slot count not aligned to 2^rounds");
@@ -577,7 +588,11 @@ int msm_tree_rounds(eon_ctx* ctx, const G1Affine* d_bases, const SlicePlan& plan
     }
     const unsigned g0 = grid_for(lv[0].second);
     phase_begin(ctx, PH_MSM_TREE_FWD);
-    if (sl) {
+    if (sl && records_ready) {  // the sort wrote the records (msm_sort_place)
+      if (SLICED_B == 8) launch_sliced<8>(true, g0, st, rec_e, rec_dest, npairs, d_bases, lv[0].first, (Fq*)bufP, out_x, out_y, ostride);
+      else if (SLICED_B == 16) launch_sliced<16>(true, g0, st, rec_e, rec_dest, npairs, d_bases, lv[0].first, (Fq*)bufP, out_x, out_y, ostride);
+      else launch_sliced<32>(true, g0, st, rec_e, rec_dest, npairs, d_bases, lv[0].first, (Fq*)bufP, out_x, out_y, ostride);
+    } else if (sl) {
       void* bufC;
       EON_TRY(scratch_get(ctx, SC_MSM_SLICE, 2 * SLICE_MAX_BINS * sizeof(unsigned long long), &bufC));
       unsigned long long* counts = (unsigned long long*)bufC;
@@ -625,6 +640,11 @@ int msm_tree_rounds(eon_ctx* ctx, const G1Affine* d_bases, const SlicePlan& plan
     else launch_bwd<32>(r == 0, g0, st, src, npairs, lv[0].first, (const Fq*)bufP, out_x, out_y, ostride);
     EON_LAUNCHED(ctx);
     phase_end(ctx, PH_MSM_TREE_BWD);
+    if (r == 0 && ctx->after_round0) {  // work the caller wants queued behind round 0 (its gathers live in the L2)
+      std::function<int()> f = std::move(ctx->after_round0);
+      ctx->after_round0 = nullptr;
+      EON_TRY(f());
+    }
     src.pts_x = out_x;
     src.pts_y = out_y;
     npairs /= 2;

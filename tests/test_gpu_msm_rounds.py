@@ -144,3 +144,41 @@ def test_two_stream_split_matches_one_batch(ctx, log_n, ncols, bits):
         dl.append(a)
         a = a * alpha % fr.P
     assert T.pt(outs[1][0]) == g1.msm_via_dlog(dl, col0)
+
+
+@pytest.mark.parametrize("fused", [1, 0])
+def test_fused_sort_records_with_skewed_columns(ctx, fused):
+    """The sort of a sliced MSM emits the pair records of round 0 itself (csrc/msm_sort.cu: k_sort_count2 /
+    k_sort_place2 / k_pair_tail) once the table spans several slices: 2^16 points with a 14-bit window = 19 levels
+    = 3 slices of 2^19 points.  Columns: all scalars equal (19 buckets of 2^16 entries each: windows beyond the
+    shared-memory image, placed in global memory), three distinct values, sparse random with a zero block, dense
+    random.  Every column must equal the discrete-log shortcut; the unfused flow (EON_SORT_FUSED=0 in a child
+    process is not needed: the per-context switch below) gives the same bytes."""
+    n, alpha = 1 << 16, 424243
+    pcs = T.pcs_new(ctx, n - 1, alpha)
+    ctx.call("eon_srs_set_window_tables", 14)
+    rng = np.random.default_rng(77)
+    cols = []
+    cols.append([int.from_bytes(rng.bytes(31), "little")] * n)
+    cols.append([int(v) * 0x10001 for v in rng.integers(1, 4, size=n)])
+    sparse = fr.from_wire(fr.random_wire(rng, n))
+    sparse[: n // 2] = [0] * (n // 2)
+    cols.append(sparse)
+    cols.append(fr.from_wire(fr.random_wire(rng, n)))
+    sc = np.stack([fr.to_wire(c) for c in cols], axis=1)
+    ctx.call("eon_msm_set_rounds", 3)
+    ctx.call("eon_msm_set_slice_schedule", 1)
+    ctx.call("eon_msm_set_split", 0)
+    ctx.call("eon_msm_set_sort_mode", 1 if fused else 2)
+    out = np.zeros((len(cols), 8), dtype=np.uint64)
+    try:
+        ctx.call("eon_msm_srs", np.ascontiguousarray(sc), n, len(cols), len(cols), out)
+    finally:
+        ctx.call("eon_msm_set_rounds", -1)
+        ctx.call("eon_msm_set_slice_schedule", -1)
+        ctx.call("eon_msm_set_split", -1)
+        ctx.call("eon_msm_set_sort_mode", -1)
+        ctx.call("eon_srs_set_window_tables", 0)
+    dl = okzg.srs_dlogs(n - 1, alpha)
+    for c, vals in enumerate(cols):
+        assert T.pt(out[c]) == g1.msm_via_dlog(dl, vals), c
