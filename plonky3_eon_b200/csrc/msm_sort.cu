@@ -214,6 +214,7 @@ k_sort_coarse(const Fr* __restrict__ scalars, size_t n, size_t ld, u32 ncols, Ms
   // histogram of the tile by bin
 #pragma unroll
   for (int q = 0; q < 4; q++) {
+    if ((u32)q * SORT_THREADS >= tile) continue;  // (uniform) a tile of 3 scalars per thread has no fourth sweep
     for_each_digit_c<C>(kk[q], sh, [&](u32 w, int d) {
       u32 b = (u32)(d < 0 ? -d : d) - 1;
       atomicAdd(&s_cnt[(MERGED ? 0 : w * nbins) + (b >> fb)], 1u);
@@ -252,6 +253,7 @@ k_sort_coarse(const Fr* __restrict__ scalars, size_t n, size_t ld, u32 ncols, Ms
   const bool flat = MERGED && sh.NB <= 65536u;  // the bucket index fits the 16-bit staged key
 #pragma unroll
   for (int q = 0; q < 4; q++) {
+    if ((u32)q * SORT_THREADS >= tile) continue;  // (uniform) a tile of 3 scalars per thread has no fourth sweep
     const u32 i = (u32)(i0 + tid + q * SORT_THREADS);
     const u32 base0 = MERGED ? (u32)sh.base_first + i : i;  // entry = base index: + w * tab_stride with tables
     const u32 stride = MERGED ? (u32)sh.tab_stride : 0u;
@@ -577,53 +579,57 @@ k_sort_place2(const u32* __restrict__ tmp_pay, const unsigned short* __restrict_
     }
   }
   __syncthreads();
-  // placement: one sweep over the bin's run of the temporary array
-  for (u32 i0 = tbegin; i0 < tend; i0 += SORT_FINE_THREADS * SORT_U) {
-    u32 key[SORT_U], pay[SORT_U];
+  // placement: one sweep over the bin's run of the temporary array (warps stay converged: lanes past the end of the
+  // run take part in the ranking collectives with on = false)
+  constexpr int PLACE_U = 4;  // (8 spills at the 64 registers 1024 threads leave)
+  for (u32 i0 = tbegin; i0 < tend; i0 += SORT_FINE_THREADS * PLACE_U) {
+    u32 key[PLACE_U], pay[PLACE_U];
 #pragma unroll
-    for (int u = 0; u < SORT_U; u++) {
+    for (int u = 0; u < PLACE_U; u++) {
       const u32 i = i0 + u * SORT_FINE_THREADS + tid;
+      key[u] = 0;
+      pay[u] = 0;
       if (i < tend) {
         key[u] = tmp_key[off + i];
         pay[u] = tmp_pay[off + i];
       }
     }
 #pragma unroll
-    for (int u = 0; u < SORT_U; u++) {
-      const u32 i = i0 + u * SORT_FINE_THREADS + tid;
-      if (i < tend) {
-        const u32 sl = min((pay[u] & ~SIGN_BIT) >> slice_shift, ns - 1);
-        const u32 pos = smem_rank(s_c2, key[u] * ns + sl);
+    for (int u = 0; u < PLACE_U; u++) {
+      const bool on = i0 + u * SORT_FINE_THREADS + tid < tend;
+      const u32 sl = min((pay[u] & ~SIGN_BIT) >> slice_shift, ns - 1);
+      const u32 pos = smem_rank_conv(s_c2, key[u] * ns + sl, on);
+      if (on) {
         if (staged) s_win[pos - begin] = pay[u];
         else entries[off + pos] = pay[u];
       }
     }
   }
   __syncthreads();  // (also orders this CTA's global writes before its reads below)
-  // pair records of the window
+  // pair records of the window, one warp per bucket: lanes take the bucket's pairs in turn (no search for the
+  // bucket of a slot; the per-slot form with its 7-step search was half of the kernel's instructions in ncu)
   const volatile u32* gwin = entries + off + begin;
-  for (u32 j = tid; j < (wlen >> 1); j += SORT_FINE_THREADS) {
-    const u32 slot = begin + 2 * j;
-    const u32 e0 = staged ? s_win[2 * j] : gwin[2 * j];
-    const u32 e1 = staged ? s_win[2 * j + 1] : gwin[2 * j + 1];
-    // bucket of the slot: the last one that starts at or before it (empty buckets share their successor's start)
-    u32 f = 0;
-    for (u32 step = fine >> 1; step; step >>= 1)
-      if (s_start[f + step] <= slot) f += step;
+  for (u32 f = wid; f < fine; f += SORT_FINE_THREADS / 32) {
     const u32 st = s_start[f];
-    const u32 p = slot - st;
-    u32 q, first;
-    if (e0 != ENTRY_NONE) {
-      q = min((e0 & ~SIGN_BIT) >> slice_shift, ns - 1);
-      first = (q ? s_c2[f * ns + q - 1] : st) - st;  // cursors have advanced to the end of their runs
-    } else {
-      q = ns;
-      first = s_cur[f] - st;
+    const u32 npair = s_slots[f] >> 1;
+    const u32 nent = s_cur[f] - st;
+    const u32 w0 = st - begin;  // the bucket's first slot inside the window
+    for (u32 pp = lane; pp < npair; pp += 32) {
+      const u32 e0 = staged ? s_win[w0 + 2 * pp] : gwin[w0 + 2 * pp];
+      const u32 e1 = staged ? s_win[w0 + 2 * pp + 1] : gwin[w0 + 2 * pp + 1];
+      u32 q, first;
+      if (e0 != ENTRY_NONE) {
+        q = min((e0 & ~SIGN_BIT) >> slice_shift, ns - 1);
+        first = (q ? s_c2[f * ns + q - 1] : st) - st;  // cursors have advanced to the end of their runs
+      } else {
+        q = ns;
+        first = nent;
+      }
+      const u32 r = s_rb[f * (ns + 1) + q] + pp - ((first + 1) >> 1);
+      const unsigned long long kk = ((unsigned long long)s_gb[2 * q + 1] << 32 | s_gb[2 * q]) + r;
+      rec_e[kk] = make_uint2(e0, e1);
+      rec_dest[kk] = (u32)((off + st + 2 * pp) >> 1);
     }
-    const u32 r = s_rb[f * (ns + 1) + q] + (p >> 1) - ((first + 1) >> 1);
-    const unsigned long long kk = ((unsigned long long)s_gb[2 * q + 1] << 32 | s_gb[2 * q]) + r;
-    rec_e[kk] = make_uint2(e0, e1);
-    rec_dest[kk] = (u32)((off + slot) >> 1);
   }
   for (u32 f = tid; f < fine; f += SORT_FINE_THREADS) ends[g0 + f] = s_cur[f];
 }
@@ -678,7 +684,9 @@ static bool sort_geom(const MsmShape& sh, SortGeom* g) {
   if (g->tile_bins > 1024) return false;
   if (sh.seg_cap / g->nbins > ((size_t)g->win_cap * 9) / 10) return false;
   // scalars per coarse tile: stage (6 bytes per entry, up to W entries per scalar) within the smem budget
-  u32 tile = 4 * SORT_THREADS;  // k_sort_coarse keeps 4 scalars per thread in registers
+  // k_sort_coarse keeps up to 4 scalars per thread in registers; 3 per thread (75 KiB of staging at 15 windows)
+  // lets three CTAs share an SM: measured 1.86 -> 1.59 ms at 2^20 x 16 (profiles/r02y_sort_tile.txt)
+  u32 tile = 3 * SORT_THREADS;
   if (const char* e = getenv("EON_SORT_TILE")) tile = (u32)atoi(e);
   if (tile > 4 * SORT_THREADS || tile < 64) tile = 4 * SORT_THREADS;
   const size_t fixed = ((size_t)3 * g->tile_bins + 1) * sizeof(u32);
@@ -708,6 +716,8 @@ int msm_sort_entries(eon_ctx* ctx, const Fr* d_scalars, size_t n, size_t ncols, 
   const size_t nseg = ncols * sh.nsets;
   const size_t total_bins = nseg * nbins;
   const size_t tiles = (n + tile - 1) / tile;
+  const u32 tile_hist = 4 * SORT_THREADS;  // the bin histogram has no staging: always 4 scalars per thread
+  const size_t tiles_hist = (n + tile_hist - 1) / tile_hist;
   if (tiles * ncols > 0x7fffffffull || nseg_total * nbins > 0x7fffffffull) return 1;
   const bool ordered = sort_ordered(plan);
   const bool fused = ordered && sort_fused_env() && ctx->msm_sort_mode != 2 && ((u64)nseg_total * sh.seg_cap) / 2 < 0xffffffffull;
@@ -756,14 +766,15 @@ int msm_sort_entries(eon_ctx* ctx, const Fr* d_scalars, size_t n, size_t ncols, 
   const bool c17 = sh.c == 17 && sh.W == 15;
   phase_begin(ctx, PH_MSM_DIGITS);
   EON_CUDA(ctx, cudaMemsetAsync(bin_count, 0, total_bins * sizeof(u32), st));
-#define EON_SORT_LAUNCH(K, SMEM, ...)                                                                          \
+#define EON_SORT_LAUNCH(K, GRID, SMEM, ...)                                                                    \
   do {                                                                                                         \
-    if (sh.merged && c17) K<true, 17><<<grid_tiles, SORT_THREADS, SMEM, st>>>(__VA_ARGS__);                    \
-    else if (sh.merged) K<true, 0><<<grid_tiles, SORT_THREADS, SMEM, st>>>(__VA_ARGS__);                       \
-    else if (c17) K<false, 17><<<grid_tiles, SORT_THREADS, SMEM, st>>>(__VA_ARGS__);                           \
-    else K<false, 0><<<grid_tiles, SORT_THREADS, SMEM, st>>>(__VA_ARGS__);                                     \
+    if (sh.merged && c17) K<true, 17><<<GRID, SORT_THREADS, SMEM, st>>>(__VA_ARGS__);                          \
+    else if (sh.merged) K<true, 0><<<GRID, SORT_THREADS, SMEM, st>>>(__VA_ARGS__);                             \
+    else if (c17) K<false, 17><<<GRID, SORT_THREADS, SMEM, st>>>(__VA_ARGS__);                                 \
+    else K<false, 0><<<GRID, SORT_THREADS, SMEM, st>>>(__VA_ARGS__);                                           \
   } while (0)
-  EON_SORT_LAUNCH(k_bin_hist, tile_bins * sizeof(u32), d_scalars, n, ld, (u32)ncols, sh, nbins, fb, tile, bin_count);
+  EON_SORT_LAUNCH(k_bin_hist, (unsigned)(tiles_hist * ncols), tile_bins * sizeof(u32), d_scalars, n, ld, (u32)ncols, sh,
+                  nbins, fb, tile_hist, bin_count);
   EON_LAUNCHED(ctx);
   k_bin_scan<<<(unsigned)nseg, 1024, 0, st>>>(bin_count, nbins, tmp_start, region_cursor);
   EON_LAUNCHED(ctx);
@@ -772,8 +783,8 @@ int msm_sort_entries(eon_ctx* ctx, const Fr* d_scalars, size_t n, size_t ncols, 
   phase_begin(ctx, PH_MSM_SCATTER);
   if (sh.rounds && !fused)  // unused slots (bucket padding, segment tails) must read as ENTRY_NONE
     EON_CUDA(ctx, cudaMemsetAsync(d_entries, 0xff, nseg * sh.seg_cap * sizeof(u32), st));
-  EON_SORT_LAUNCH(k_sort_coarse, smem_coarse, d_scalars, n, ld, (u32)ncols, sh, nbins, fb, tile, region_cursor,
-                  tmp_pay, tmp_key);
+  EON_SORT_LAUNCH(k_sort_coarse, grid_tiles, smem_coarse, d_scalars, n, ld, (u32)ncols, sh, nbins, fb, tile,
+                  region_cursor, tmp_pay, tmp_key);
 #undef EON_SORT_LAUNCH
   EON_LAUNCHED(ctx);
   phase_end(ctx, PH_MSM_SCATTER);
