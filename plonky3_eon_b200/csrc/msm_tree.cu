@@ -31,10 +31,10 @@
 namespace eon {
 
 constexpr int TREE_THREADS = 128;
-// level size at which the values are inverted directly: with the binary-GCD inversion (fp.cuh) 2048 inversions on
-// 64 warps cost the same ~25 us as 256, and every level of the product tree saved is two launches and ~28
-// dependent products less per round
-constexpr u64 TREE_TOP = 2048;
+// level size at which the values are inverted directly: with the divstep inversion (fp.cuh, ~15 k instructions)
+// 16 k inversions are 512 warps = one per SMSP, i.e. the latency of a single inversion (~20 us), and every level of
+// the product tree saved is two launches and ~22 dependent products less per round (2048 with the binary GCD)
+constexpr u64 TREE_TOP = 16384;
 
 enum { PAIR_TRIVIAL = 0, PAIR_ADD = 1, PAIR_DBL = 2 };
 

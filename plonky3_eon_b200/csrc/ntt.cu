@@ -853,7 +853,23 @@ static int ntt_db_mode() {
 }
 static bool ntt_db_shape(size_t w, bool sh) { return sh && ntt_db_mode() && w >= 8 && (w & (w - 1)) == 0; }
 static std::vector<PassPlan> plan_passes_for(u32 first, u32 last, size_t w, bool sh) {
-  if (!ntt_db_shape(w, sh)) return plan_passes(first, last, w);
+  if (!ntt_db_shape(w, sh)) {
+    std::vector<PassPlan> plan = plan_passes(first, last, w);
+    // Narrow matrices (w < 16: a column group of the host-buffer pipeline, the shard of one GPU at N = 4, 8): a
+    // pass with fewer layers than its tile could hold (the 6 + 5 layers behind a 9-layer first pass at w = 4) would
+    // stage 1024 or 512 elements for 256 threads.  Such a pass takes more virtual columns instead (up to 64: rows of
+    // the 2^l0-blocks are contiguous in memory, so wider tile rows are longer contiguous runs), keeping the tile at
+    // its full size.  (With w >= 16 the tile row stays at 16 columns = one twiddle set per tile, see k_ntt_pass.)
+    static const int widen = getenv("EON_NTT_WIDEN") ? atoi(getenv("EON_NTT_WIDEN")) : 1;
+    if (w < 16 && widen) {
+      const u32 tile_log = ilog2_u32(ntt_tile_elems());
+      for (PassPlan& pl : plan) {
+        const u64 V = ((u64)w) << pl.l0;
+        while (pl.log_cv < 6 && pl.log_cv + pl.r < tile_log && (2ull << pl.log_cv) <= V) pl.log_cv++;
+      }
+    }
+    return plan;
+  }
   const u32 tile_log = ntt_db_mode() == 1 ? 10 : 11;
   // layers per pass as if every tile row were 8 elements wide (r <= tile_log - 3); a pass with fewer layers than
   // that widens its rows (cv = 16) so that the tile keeps its size

@@ -10,7 +10,7 @@ template <class F> static void st(uint32_t* p, const F& x) { memcpy(p, x.v, 32);
 
 extern "C" {
 // which: 0 = Fr, 1 = Fq.  op: 0 mul, 1 add, 2 sub, 3 neg, 4 inv (binary GCD), 5 from_mont, 6 to_mont, 7 sqr,
-// 8 inv by Fermat (cross-check)
+// 8 inv by Fermat (cross-check), 9 inv by safegcd divsteps, 10 inv by the binary GCD (4 = the library's fp_inv)
 void host_fp_op(int which, int op, const uint32_t* a, const uint32_t* b, uint32_t* r, int n) {
   for (int i = 0; i < n; i++, a += 8, b += 8, r += 8) {
     if (which == 0) {
@@ -24,6 +24,8 @@ void host_fp_op(int which, int op, const uint32_t* a, const uint32_t* b, uint32_
         case 5: fp_from_mont(z.v, x); break;
         case 6: z = fp_to_mont<FrParams>(x.v); break;
         case 8: z = fp_inv_fermat(x); break;
+        case 9: z = fp_inv_safegcd(x); break;
+        case 10: z = fp_inv_bgcd(x); break;
         default: z = fp_sqr(x);
       }
       st(r, z);
@@ -38,6 +40,8 @@ void host_fp_op(int which, int op, const uint32_t* a, const uint32_t* b, uint32_
         case 5: fp_from_mont(z.v, x); break;
         case 6: z = fp_to_mont<FqParams>(x.v); break;
         case 8: z = fp_inv_fermat(x); break;
+        case 9: z = fp_inv_safegcd(x); break;
+        case 10: z = fp_inv_bgcd(x); break;
         default: z = fp_sqr(x);
       }
       st(r, z);

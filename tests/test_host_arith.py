@@ -88,11 +88,32 @@ def test_binary_gcd_inverse(lib, which, mod):
     a = np.concatenate([np.array([from_int(v % mod) for v in vals]), rand_mont(rng, mod, 3000)])
     n = len(a)
     r, f = np.zeros_like(a), np.zeros_like(a)
-    lib.host_fp_op(which, 4, _ptr(a), _ptr(a), _ptr(r), n)
+    lib.host_fp_op(which, 10, _ptr(a), _ptr(a), _ptr(r), n)
     lib.host_fp_op(which, 8, _ptr(a[:64]), _ptr(a[:64]), _ptr(f[:64]), 64)
     assert np.array_equal(r[:64], f[:64])
     for i in range(n):
         x = to_int(a[i])                       # Montgomery form of x / R
+        want = pow(x, -1, mod) * R * R % mod if x else 0
+        assert to_int(r[i]) == want, (which, i, hex(x))
+
+
+@pytest.mark.parametrize("which,mod", [(0, fr.P), (1, g1.Q)])
+def test_safegcd_inverse(lib, which, mod):
+    """fp_inv_safegcd (Bernstein-Yang divsteps, 20 batches of 30 on signed 30-bit limbs; the inversion on the
+    latency-critical paths of the MSM) against pow(x, -1, p) and against the binary GCD: zero, one, values next to
+    the modulus, powers of two and their complements (long runs of even / odd steps), 20000 random elements."""
+    rng = np.random.default_rng(77 + which)
+    R = (1 << 256) % mod
+    vals = EDGE(mod) + [1 << k for k in range(0, 254)] + [mod - (1 << k) for k in range(0, 253)]
+    vals += [(1 << k) - 1 for k in range(2, 254, 3)] + [3, 5, mod // 2, mod // 2 + 1, mod // 3, R, (R * R) % mod]
+    a = np.concatenate([np.array([from_int(v % mod) for v in vals]), rand_mont(rng, mod, 20000)])
+    n = len(a)
+    r, b = np.zeros_like(a), np.zeros_like(a)
+    lib.host_fp_op(which, 9, _ptr(a), _ptr(a), _ptr(r), n)
+    lib.host_fp_op(which, 10, _ptr(a), _ptr(a), _ptr(b), n)
+    assert np.array_equal(r, b)
+    for i in range(0, n, 7):
+        x = to_int(a[i])
         want = pow(x, -1, mod) * R * R % mod if x else 0
         assert to_int(r[i]) == want, (which, i, hex(x))
 
