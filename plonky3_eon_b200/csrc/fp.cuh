@@ -533,7 +533,7 @@ EON_HD void fp_mul_lazy(u32 r[8], const u32 a[8], const u32 b[8]) {
 // r = a*a*2^-256 mod p in [0, 2p)  (a < p)
 template <class PP>
 EON_HD void fp_sqr_lazy(u32 r[8], const u32 a[8]) {
-#if defined(EON_FP_SPLIT)
+#if defined(EON_FP_SPLIT) || defined(EON_FP_SQR_SPLIT)
   fp_sqr_lazy_split<PP>(r, a);
 #else
   fp_mul_lazy_cios<PP>(r, a, a);
@@ -554,6 +554,20 @@ template <class PP>
 EON_HD Fp<PP> fp_sqr(const Fp<PP>& a) {
   u32 t[8];
   fp_sqr_lazy<PP>(t, a.v);
+  Fp<PP> r;
+  fp_final_sub<PP>(r.v, t);
+  return r;
+}
+
+// The same square through the dedicated squaring (36 limb products + separate reduction, fp_sqr_lazy_split) whatever
+// the build's default: 7 % faster than a product in isolation (profiles/r01m_modmul_variants.json), at the price of
+// ~10 more live registers.  Used where that is free (k_tree_bwd: 18.19 -> 18.04 ms, still 92 registers); in the
+// XYZZ finisher it spills (4.88 -> 5.17 ms), so fp_sqr itself stays the word-serial product
+// (profiles/r03h_dedicated_square.txt).
+template <class PP>
+EON_HD Fp<PP> fp_sqr_dedicated(const Fp<PP>& a) {
+  u32 t[8];
+  fp_sqr_lazy_split<PP>(t, a.v);
   Fp<PP> r;
   fp_final_sub<PP>(r.v, t);
   return r;

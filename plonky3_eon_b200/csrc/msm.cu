@@ -65,6 +65,7 @@ static MsmShape msm_shape_merged(size_t n, u32 c, u64 tab_stride, u64 first) {
   s.NB = 1u << (c - 1);
   s.nsets = 1;
   s.merged = 1;
+  s.mont_digits = 1;  // k_srs_tables pre-scales every base by R^-1
   s.chunk = (u32)chunk_env;
   s.nchunks = s.NB / s.chunk;
   s.tab_stride = tab_stride;
@@ -896,17 +897,32 @@ int msm_run(eon_ctx* ctx, const G1Affine* d_bases, const Fr* d_scalars, size_t n
 // Static bases (the SRS never changes between calls, kzg/src/params.rs:57-77) let every window of a
 // scalar use its own pre-shifted copy of the point, so all W windows of a column fall into ONE set
 // of 2^(c-1) buckets: the bucket reduction shrinks W-fold and c can grow (fewer windows).
+// Every table point carries the factor R^-1 mod r (R = 2^256, r = the group order): an MSM through the tables then
+// takes its digits from the Montgomery limbs s R mod r of a scalar as they arrive -- sum (s_i R) (R^-1 P_i) =
+// sum s_i P_i -- instead of paying a from-Montgomery product per scalar in every pass of the sort (two per scalar and
+// MSM: 0.5 ms of a 2^20 x 16 commit).  The price is one 254-bit scalar multiplication per SRS point when the tables
+// are built (once per SRS).
+struct RinvLimbs {
+  u32 k[8];
+};
 __global__ void __launch_bounds__(128) k_srs_tables(const G1Affine* __restrict__ srs, size_t n, u32 c, u32 W,
-                                                    G1Affine* __restrict__ tab) {
+                                                    RinvLimbs rinv, G1Affine* __restrict__ tab) {
   size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   if (i >= n) return;
-  G1Affine p = srs[i];
-  tab[i] = p;
-  G1Xyzz acc = G1Xyzz::from_affine(p);
+  G1Xyzz acc = g1_mul_canonical(srs[i], rinv.k);
+  tab[i] = g1_to_affine(acc);
   for (u32 t = 1; t < W; t++) {
     for (u32 k = 0; k < c; k++) acc = g1_dbl(acc);
     tab[(size_t)t * n + i] = g1_to_affine(acc);
   }
+}
+
+static RinvLimbs rinv_limbs() {
+  Fr one_int = Fr::zero();
+  one_int.v[0] = 1;            // the INTEGER 1 read as limbs: from-Montgomery gives 1 * R^-1 mod r
+  RinvLimbs r;
+  fp_from_mont(r.k, one_int);
+  return r;
 }
 
 int srs_build_tables(eon_ctx* ctx, unsigned window_bits) {
@@ -922,7 +938,7 @@ int srs_build_tables(eon_ctx* ctx, unsigned window_bits) {
   const u32 c = window_bits, W = msm_windows(c);
   if ((u64)W * n >= 0x7fffffffull) return fail(ctx, EON_ERR_BAD_ARG, "SRS too large for window tables");
   EON_CUDA(ctx, cudaMalloc(&ctx->d_srs_tab, (size_t)W * n * sizeof(G1Affine)));
-  k_srs_tables<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(ctx->d_srs, n, c, W, ctx->d_srs_tab);
+  k_srs_tables<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(ctx->d_srs, n, c, W, rinv_limbs(), ctx->d_srs_tab);
   EON_LAUNCHED(ctx);
   ctx->srs_tab_c = c;
   return EON_OK;
@@ -965,7 +981,7 @@ int srs_build_range_tables(eon_ctx* ctx, size_t first, size_t n, unsigned window
   const u32 c = window_bits, W = msm_windows(c);
   if ((u64)W * n >= 0x7fffffffull) return fail(ctx, EON_ERR_BAD_ARG, "range too large for window tables");
   EON_CUDA(ctx, cudaMalloc(&ctx->d_rng_tab, (size_t)W * n * sizeof(G1Affine)));
-  k_srs_tables<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(ctx->d_srs + first, n, c, W, ctx->d_rng_tab);
+  k_srs_tables<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(ctx->d_srs + first, n, c, W, rinv_limbs(), ctx->d_rng_tab);
   EON_LAUNCHED(ctx);
   ctx->rng_first = first;
   ctx->rng_n = n;

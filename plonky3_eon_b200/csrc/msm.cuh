@@ -20,6 +20,8 @@ struct MsmShape {
   u64 tab_stride;  // merged: points per table level
   u64 base_first;  // merged: index of this MSM's point 0 inside a table level
   u64 seg_cap;     // entry slots per segment: n (plain) or n * W (merged), plus alignment padding
+  u32 mont_digits; // merged: the window tables hold R^-1 * 2^(c t) * P_i, so the digits are taken from the Montgomery
+                   // limbs of a scalar as they are (sum (s R) (R^-1 P) = sum s P): no from-Montgomery product per scalar
   u32 rounds;      // batched-affine pairwise rounds before the serial XYZZ finisher (0 = none);
                    // bucket starts are aligned to 2^rounds entry slots
 };
@@ -173,10 +175,20 @@ __device__ __forceinline__ void for_each_digit_c(const u32 (&k)[8], const MsmSha
   }
 }
 
+// the integer whose digits index the buckets: the canonical scalar, or its Montgomery limbs with pre-scaled tables
+__device__ __forceinline__ void scalar_digits_source(u32 (&k)[8], const Fr& s, const MsmShape& sh) {
+  if (sh.mont_digits) {
+#pragma unroll
+    for (int j = 0; j < 8; j++) k[j] = s.v[j];
+  } else {
+    fp_from_mont(k, s);
+  }
+}
+
 template <class F>
 __device__ __forceinline__ void for_each_digit(const Fr& s, const MsmShape& sh, F f) {
   u32 k[8];
-  fp_from_mont(k, s);
+  scalar_digits_source(k, s, sh);
   for_each_digit_canonical(k, sh, f);
 }
 

@@ -99,7 +99,7 @@ k_bin_hist(const Fr* __restrict__ scalars, size_t n, size_t ld, u32 ncols, MsmSh
 #pragma unroll
   for (int q = 0; q < 4; q++) {
     u32 kk[8];
-    fp_from_mont(kk, sc[q]);
+    scalar_digits_source(kk, sc[q], sh);
     for_each_digit_c<C>(kk, sh, [&](u32 w, int d) {
       u32 b = (u32)(d < 0 ? -d : d) - 1;
       atomicAdd(&smem[(MERGED ? 0 : w * nbins) + (b >> fb)], 1u);
@@ -205,7 +205,7 @@ k_sort_coarse(const Fr* __restrict__ scalars, size_t n, size_t ld, u32 ncols, Ms
     const u32 t = tid + q * SORT_THREADS;
     const size_t i = i0 + t;
     if (t < tile && i < n) {
-      fp_from_mont(kk[q], load_scalar(scalars, i, ld, col));
+      scalar_digits_source(kk[q], load_scalar(scalars, i, ld, col), sh);
     } else {
 #pragma unroll
       for (int j = 0; j < 8; j++) kk[q][j] = 0;  // zero scalar: no digits

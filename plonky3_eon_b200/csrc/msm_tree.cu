@@ -254,7 +254,7 @@ __device__ __forceinline__ G1Affine pair_sum(const Operand<R0>& P, const Operand
       lam = fp_mul(fp_add(fp_dbl(xx), xx), dinv);
       xsum = fp_dbl(P.x);
     }
-    r.x = fp_sub(fp_sqr(lam), xsum);
+    r.x = fp_sub(fp_sqr_dedicated(lam), xsum);
     r.y = fp_sub(fp_mul(lam, fp_sub(P.x, r.x)), py);
   }
   return r;
