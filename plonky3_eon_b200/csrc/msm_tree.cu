@@ -15,8 +15,8 @@
 //
 // One round =
 //   k_tree_fwd   thread t: denominators d_j of its B = 8 pairs, pre[j] = d_0 .. d_(j-1), T0[t] = prod d_j
-//   k_tree_up    T(l+1)[u] = prod of 8 consecutive T(l)        (until <= 256 values remain)
-//   k_tree_top   Fermat inversion of the top level              (the only inversions of the round)
+//   k_tree_up    T(l+1)[u] = prod of 8 consecutive T(l)        (until <= TREE_TOP values remain)
+//   k_tree_top   inversion of every value of the top level       (the only inversions of the round)
 //   k_tree_down  T(l)[i] <- 1 / T(l)[i] from 1 / T(l+1)[u]
 //   k_tree_bwd   thread t: peel 1/d_j = pre[j] / (d_0 .. d_j) off 1/T0[t], last pair first, and finish
 //                lambda = (y2 - y1)/d, x3 = lambda^2 - x1 - x2, y3 = lambda (x1 - x3) - y1
@@ -293,7 +293,8 @@ k_tree_bwd(TreeSrc src, u64 npairs, const Fq* __restrict__ T0inv, const Fq* __re
 //   1. the sort orders the entries of every bucket by table slice (2^19 points = 32 MiB; k_sort_fine<true>),
 //      so that most pairs take both operands from the same slice;
 //   2. a pair record (entry0, entry1, destination slot) is appended to the list of the slice of its first
-//      operand (tile-local counting sort, k_pair_hist / k_pair_scatter);
+//      operand (tile-local counting sort, k_pair_hist / k_pair_scatter -- or, in the fused form of the sort,
+//      written by k_sort_place2 itself: msm_sort.cu);
 //   3. k_tree_fwd_sliced / k_tree_bwd_sliced walk the records in that order with coalesced record reads: at
 //      any time the in-flight pairs gather from one or two slices, which stay L2-resident.
 // Each result is written to the slot the slot-order schedule would have used, so rounds >= 1 and the finisher
