@@ -482,6 +482,56 @@ k_bucket_weighted(const G1Xyzz* __restrict__ rows, const G1Xyzz* __restrict__ co
   }
 }
 
+// The same weighted sum by the BITS of the index: sum_i i X_i = sum_b 2^b S_b with S_b = the sum of the elements
+// whose index has bit b set.  One warp per bit (n / 2 elements: a strip per lane + a shuffle tree), one more warp for
+// the plain total S; then b doublings of S_b (all bits in parallel) and a tree over the bits: ~16 dependent
+// additions for n = 256 against ~23 of the suffix-scan form above -- this launch runs alone on the GPU, so the depth
+// of the chain is its duration.  blockDim = 32 * (max(logL, logH) + 1).  EON_BUCKET_W2=0: the suffix-scan form.
+constexpr int BW2_MAX_THREADS = 384;  // up to 12 warps (n <= 2^11); 170 registers per thread
+__global__ void __launch_bounds__(BW2_MAX_THREADS)
+k_bucket_weighted2(const G1Xyzz* __restrict__ rows, const G1Xyzz* __restrict__ cols, u32 logL, u32 logH,
+                   G1Xyzz* __restrict__ out) {
+  __shared__ G1Xyzz s_grp[16];
+  const size_t seg = blockIdx.x >> 1;
+  const u32 which = blockIdx.x & 1;
+  const u32 logn = which ? logL : logH;
+  const u32 n = 1u << logn;
+  const G1Xyzz* X = which ? cols + (seg << logL) : rows + (seg << logH);
+  const u32 tid = threadIdx.x, lane = tid & 31, g = tid >> 5;  // warp g: bit g, or (g == logn) the total
+  if (g <= logn) {
+    G1Xyzz acc = G1Xyzz::identity();
+    const u32 count = (g == logn) ? n : (n >> 1);
+    for (u32 k = lane; k < count; k += 32) {
+      // k-th index with bit g set: bit g inserted into k
+      const u32 i = (g == logn) ? k : ((((k >> g) << 1) | 1u) << g) | (k & ((1u << g) - 1));
+      g1_add(acc, ld_xyzz(X + i));
+    }
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) {
+      const G1Xyzz t = shfl_down_xyzz(acc, d);
+      if (lane < (u32)d) g1_add(acc, t);
+    }
+    if (lane == 0) {
+      if (g < logn)
+        for (u32 j = 0; j < g; j++) acc = g1_dbl(acc);  // 2^g S_g
+      s_grp[g] = acc;
+    }
+  }
+  __syncthreads();
+  if (g == 0) {
+    G1Xyzz v = lane < logn ? s_grp[lane] : G1Xyzz::identity();
+#pragma unroll
+    for (int d = 8; d >= 1; d >>= 1) {  // logn <= 15
+      const G1Xyzz t = shfl_down_xyzz(v, d);
+      if (lane < (u32)d) g1_add(v, t);
+    }
+    if (lane == 0) {
+      st_xyzz(out + 3 * seg + which, v);
+      if (which == 0) st_xyzz(out + 3 * seg + 2, s_grp[logn]);  // S = the plain sum of the row sums
+    }
+  }
+}
+
 // segsum[seg] = S + W_C + 2^logL W_R
 __global__ void __launch_bounds__(32) k_bucket_finish(const G1Xyzz* __restrict__ parts, u32 logL, size_t nseg,
                                                       G1Xyzz* __restrict__ segsum) {
@@ -737,7 +787,11 @@ int msm_batch_finish(eon_ctx* ctx, const MsmBatch& S, G1Affine* d_out) {
     EON_LAUNCHED(ctx);
     const unsigned bt = std::min<unsigned>(BW_THREADS, std::max(32u, 1u << logL));
     cudaStream_t ts = tiny_begin(ctx);  // three single-CTA-per-segment launches in a dependent chain
-    k_bucket_weighted<<<(unsigned)(2 * nseg), bt, 0, ts>>>(rows, cols, logL, logH, parts);
+    static const int w2_env = getenv("EON_BUCKET_W2") ? atoi(getenv("EON_BUCKET_W2")) : 1;
+    if (w2_env && 32u * (std::max(logL, logH) + 1) <= (u32)BW2_MAX_THREADS)
+      k_bucket_weighted2<<<(unsigned)(2 * nseg), 32u * (std::max(logL, logH) + 1), 0, ts>>>(rows, cols, logL, logH, parts);
+    else
+      k_bucket_weighted<<<(unsigned)(2 * nseg), bt, 0, ts>>>(rows, cols, logL, logH, parts);
     EON_LAUNCHED(ctx);
     k_bucket_finish<<<(unsigned)((nseg + 31) / 32), 32, 0, ts>>>(parts, logL, nseg, (G1Xyzz*)p_seg);
     EON_LAUNCHED(ctx);
