@@ -205,14 +205,10 @@ k_msm_order(const u32* __restrict__ starts, const u32* __restrict__ ends, u32 NB
   for (u32 i = threadIdx.x; i < ORDER_BINS; i += blockDim.x) bin_count[i] = 0;
   __syncthreads();
   const u32 rnd = (1u << rshift) - 1;  // after `rshift` pairwise rounds a bucket holds ceil(cnt / 2^rshift) points
-  // (random scalars give nearly every bucket the same size: a warp's 32 increments hit one or two counters, so they
-  // are aggregated per warp -- plain shared-memory atomics serialised 32-way here, 59 us with the whole GPU waiting)
-  const u32 lane = threadIdx.x & 31;
+  // (warp-aggregated increments through MATCH.ANY were tried: 56 -> 93 us per launch, profiles/r03s_ncu_launches_agg.txt)
   for (u32 b = threadIdx.x; b < NB; b += blockDim.x) {
     u32 cnt = (en[b] - st[b] + rnd) >> rshift;
-    const u32 k = min(cnt, ORDER_BINS - 1);
-    const u32 peers = __match_any_sync(__activemask(), k);
-    if (lane == (u32)(__ffs(peers) - 1)) atomicAdd(&bin_count[k], (u32)__popc(peers));
+    atomicAdd(&bin_count[min(cnt, ORDER_BINS - 1)], 1u);
   }
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -225,13 +221,8 @@ k_msm_order(const u32* __restrict__ starts, const u32* __restrict__ ends, u32 NB
   __syncthreads();
   for (u32 b = threadIdx.x; b < NB; b += blockDim.x) {
     u32 cnt = (en[b] - st[b] + rnd) >> rshift;
-    const u32 k = min(cnt, ORDER_BINS - 1);
-    const u32 peers = __match_any_sync(__activemask(), k);
-    const u32 leader = (u32)(__ffs(peers) - 1);
-    u32 base = 0;
-    if (lane == leader) base = atomicAdd(&bin_pos[k], (u32)__popc(peers));
-    base = __shfl_sync(peers, base, leader);
-    ord[base + __popc(peers & ((1u << lane) - 1))] = b;
+    u32 pos = atomicAdd(&bin_pos[min(cnt, ORDER_BINS - 1)], 1u);
+    ord[pos] = b;
   }
 }
 
